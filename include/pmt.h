@@ -1,0 +1,136 @@
+/*
+ * pmt.h -- C ABI of libpmt.so: B200-native Poseidon-Goldilocks Merkle commitment engine.
+ *
+ * The reference (hashcloak/plonky2-merkle-trees) is pure Rust with NO FFI of its own; this header is the boundary a
+ * maintainer binds with `extern "C"` (see INTEGRATION.md for the Rust shim) so that the reference's public types keep
+ * their shape.  Each entry point names the reference function it replaces (file:line under /root/reference, or
+ * [UPSTREAM] = plonky2 v0.1.3 @ 3b21b87d, the un-vendored dependency of Cargo.toml:7).
+ *
+ * Conventions
+ *   - felt   = one Goldilocks element as little-endian u64.  INPUTS may be any u64 (non-canonical allowed, like
+ *              GoldilocksField.0); OUTPUTS are always canonical (< p = 2^64 - 2^32 + 1).
+ *   - digest = HashOut = 4 consecutive felts (32 bytes).
+ *   - plain pointers + sizes, caller owns every buffer; nothing returned by the library outlives the ctx.
+ *   - return value: 0 = PMT_OK, negative = PMT_E_*; pmt_last_error(ctx) has the message.  Never unwinds.
+ *   - a ctx is bound to one CUDA device and one stream and is NOT thread-safe; use one ctx per host thread / rank.
+ *   - *_dev entry points take DEVICE pointers, only ENQUEUE work on the ctx stream (no host sync) and return; call
+ *     pmt_sync() before reading results on the host.  The host-buffer entry points are synchronous.
+ *   - there is no CPU fallback: every entry point that computes fails with PMT_E_CUDA when no device is usable.
+ */
+#ifndef PMT_H
+#define PMT_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PMT_OK 0
+#define PMT_E_INVALID_ARG (-1) /* null pointer, zero size where the reference would panic, width 0 ... */
+#define PMT_E_NOT_POW2 (-2)    /* log2_strict panic: simple_merkle_tree.rs:30, [UPSTREAM] MerkleTree::new */
+#define PMT_E_OOM (-3)
+#define PMT_E_CUDA (-4)
+#define PMT_E_RANGE (-5) /* index assert: simple_merkle_tree.rs:56,77; cap_height > log2 n; MMR leaf >= 2^30 (:264) */
+
+typedef struct pmt_ctx pmt_ctx;
+
+/* ---- context ---------------------------------------------------------------------------------------------------- */
+int pmt_init(pmt_ctx** out, int device_id);
+void pmt_destroy(pmt_ctx* ctx);
+const char* pmt_last_error(const pmt_ctx* ctx);
+const char* pmt_version(void);
+int pmt_device_id(const pmt_ctx* ctx);
+/* use an externally owned cudaStream_t (e.g. the caller's current stream); NULL restores the ctx's own stream */
+int pmt_set_stream(pmt_ctx* ctx, void* cuda_stream);
+void* pmt_get_stream(const pmt_ctx* ctx);
+int pmt_sync(pmt_ctx* ctx);
+/* number of CUDA kernels this ctx has launched since pmt_init (monotonic; bench.py reports the delta) */
+uint64_t pmt_kernel_launches(const pmt_ctx* ctx);
+/* optional per-launch timing: CUDA events on the launching stream around every kernel.  pmt_profile_read synchronises,
+ * writes one text line per kernel ("name launches total_ms total_permutations") into buf, and resets the records. */
+int pmt_profile_enable(pmt_ctx* ctx, int on);
+int pmt_profile_read(pmt_ctx* ctx, char* buf, size_t cap);
+/* device memory helpers for hosts without their own allocator (Rust shim); freed by pmt_free or pmt_destroy */
+int pmt_malloc(pmt_ctx* ctx, size_t bytes, void** dptr_out);
+int pmt_free(pmt_ctx* ctx, void* dptr);
+int pmt_memcpy_h2d(pmt_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+int pmt_memcpy_d2h(pmt_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+
+/* ---- Hasher: [UPSTREAM] plonk/config.rs Hasher for PoseidonHash ------------------------------------------------------ */
+/* n independent width-12 permutations (parity hook for Poseidon::poseidon); in/out n*12 felts */
+int pmt_permute(pmt_ctx* ctx, const uint64_t* in, size_t n, uint64_t* out);
+/* out[i] = PoseidonHash::two_to_one(l[i], r[i])   (simple_merkle_tree.rs:23,45,100,102; merkle_mountain_ranges.rs:111,238,240) */
+int pmt_hash_two_to_one(pmt_ctx* ctx, const uint64_t* l, const uint64_t* r, size_t n, uint64_t* out);
+/* out[i] = PoseidonHash::hash_or_noop(row i), rows row-major n_rows x width (simple_merkle_tree.rs:33,93;
+ * merkle_mountain_ranges.rs:91,96,125,233,249): width <= 4 => canonicalise + zero pad, else overwrite-mode sponge */
+int pmt_hash_or_noop(pmt_ctx* ctx, const uint64_t* rows, size_t n_rows, size_t width, uint64_t* out);
+/* always the sponge (hash_n_to_hash_no_pad), also for width <= 4 */
+int pmt_hash_no_pad(pmt_ctx* ctx, const uint64_t* rows, size_t n_rows, size_t width, uint64_t* out);
+int pmt_permute_dev(pmt_ctx* ctx, const uint64_t* d_in, size_t n, uint64_t* d_out);
+int pmt_hash_two_to_one_dev(pmt_ctx* ctx, const uint64_t* d_l, const uint64_t* d_r, size_t n, uint64_t* d_out);
+/* noop_rule != 0: hash_or_noop, == 0: hash_no_pad */
+int pmt_hash_rows_dev(pmt_ctx* ctx, const uint64_t* d_rows, size_t n_rows, size_t width, int noop_rule, uint64_t* d_out);
+
+/* ---- simple tree: simple_merkle_tree.rs ------------------------------------------------------------------------------ */
+/* MerkleTree::build (:28-51).  leaves: n felts, n a power of two >= 2.  levels_out: (2n-2) digests, level-major
+ * (level 0 = n leaf digests, level 1 = n/2, ..., last = 2) = MerkleTree.tree flattened; root_out: 1 digest. */
+int pmt_simple_tree_build(pmt_ctx* ctx, const uint64_t* leaves, size_t n, uint64_t* levels_out, uint64_t* root_out);
+int pmt_simple_tree_build_dev(pmt_ctx* ctx, const uint64_t* d_leaves, size_t n, uint64_t* d_levels, uint64_t* d_root);
+/* get_merkle_proof (:55-74) for a batch: siblings_out n_idx * log2(n) digests, bottom-up.  levels on the DEVICE. */
+int pmt_simple_tree_prove_dev(pmt_ctx* ctx, const uint64_t* d_levels, size_t n, const uint64_t* d_idx, size_t n_idx,
+                              uint64_t* d_siblings_out);
+/* verify_merkle_proof (:91-109) for a batch sharing one root: ok_out[i] = 1/0.  proofs: n_idx * path_len digests */
+int pmt_simple_tree_verify_dev(pmt_ctx* ctx, const uint64_t* d_leaves, const uint64_t* d_idx, size_t n_idx,
+                               const uint64_t* d_root, const uint64_t* d_proofs, size_t path_len, uint8_t* d_ok_out);
+
+/* ---- plonky2 tree: [UPSTREAM] hash/merkle_tree.rs, hash/merkle_proofs.rs ------------------------------------------------ */
+/* MerkleTree::new(leaves, cap_height).  leaves row-major n x width; digests_out 2(n - 2^h) digests in upstream's
+ * interleaved layout (per cap subtree: left subtree || left digest || right digest || right subtree); cap_out 2^h. */
+int pmt_merkle_tree_build(pmt_ctx* ctx, const uint64_t* leaves, size_t n, size_t width, uint32_t cap_height,
+                          uint64_t* digests_out, uint64_t* cap_out);
+int pmt_merkle_tree_build_dev(pmt_ctx* ctx, const uint64_t* d_leaves, size_t n, size_t width, uint32_t cap_height,
+                              uint64_t* d_digests, uint64_t* d_cap);
+/* MerkleTree::prove for a batch: siblings_out n_idx * (log2 n - h) digests */
+int pmt_merkle_prove_dev(pmt_ctx* ctx, const uint64_t* d_digests, size_t n, uint32_t cap_height, const uint64_t* d_idx,
+                         size_t n_idx, uint64_t* d_siblings_out);
+/* verify_merkle_proof_to_cap for a batch: leaves row-major n_idx x width */
+int pmt_merkle_verify_dev(pmt_ctx* ctx, const uint64_t* d_leaf_rows, size_t width, const uint64_t* d_idx, size_t n_idx,
+                          const uint64_t* d_cap, uint32_t cap_height, const uint64_t* d_proofs, size_t path_len,
+                          uint8_t* d_ok_out);
+/* multi-GPU finish: given the 2^g subtree roots gathered from the ranks (rank order), compute the g - h levels above
+ * them.  d_top_out is level-major: 2^g/2, 2^g/4, ..., 2^h digests (2^g - 2^h in total); its last 2^h digests are the
+ * cap.  cap_height == g: nothing to do (the roots are the cap). */
+int pmt_top_levels_dev(pmt_ctx* ctx, const uint64_t* d_roots, size_t n_roots, uint32_t cap_height, uint64_t* d_top_out);
+
+/* ---- MMR: merkle_mountain_ranges.rs ------------------------------------------------------------------------------------ */
+/* number of elements of an MMR with n leaves = 2n - popcount(n) */
+size_t pmt_mmr_size(size_t n_leaves);
+/* get_mmr_index (:257-270) = 2i - popcount(i) */
+size_t pmt_mmr_index(size_t leaf_normal_index);
+/* batch of MMR::add_leaf (:89-120): append m single-felt leaves to an MMR that already has n_before leaves.
+ * elements: post-order array with capacity >= pmt_mmr_size(n_before + m) digests, first pmt_mmr_size(n_before) valid. */
+int pmt_mmr_extend(pmt_ctx* ctx, uint64_t* elements, size_t n_before, const uint64_t* new_leaves, size_t m);
+int pmt_mmr_extend_dev(pmt_ctx* ctx, uint64_t* d_elements, size_t n_before, const uint64_t* d_new_leaves, size_t m);
+/* get_peaks (:179-200): peaks_out up to 64 digests, largest mountain first; *n_peaks_out = popcount(n_leaves) */
+int pmt_mmr_peaks_dev(pmt_ctx* ctx, const uint64_t* d_elements, size_t n_leaves, uint64_t* d_peaks_out,
+                      uint32_t* n_peaks_out);
+/* bagging_the_peaks (:122-127): hash_or_noop over the flattened peaks */
+int pmt_mmr_bag_dev(pmt_ctx* ctx, const uint64_t* d_elements, size_t n_leaves, uint64_t* d_root_out);
+/* get_proof_normal_index (:203-223) for a batch of NORMAL leaf indices.  Per proof: up to 32 (sibling, on_left) entries
+ * at stride 32 digests / 32 bytes; path_len_out[i] = height of the leaf's mountain.  Peaks: use pmt_mmr_peaks_dev. */
+int pmt_mmr_prove_dev(pmt_ctx* ctx, const uint64_t* d_elements, size_t n_leaves, const uint64_t* d_leaf_idx,
+                      size_t n_idx, uint64_t* d_siblings_out, uint8_t* d_on_left_out, uint32_t* d_path_len_out);
+/* MMR_proof::verify (:232-252) for a batch sharing peaks + root: status_out[i] = 1 true, 0 false,
+ * -1 = the reference would panic (subtree root not among the peaks, assert! at :245) */
+int pmt_mmr_verify_dev(pmt_ctx* ctx, const uint64_t* d_leaves, size_t n_idx, const uint64_t* d_siblings,
+                       const uint8_t* d_on_left, const uint32_t* d_path_len, const uint64_t* d_peaks, uint32_t n_peaks,
+                       const uint64_t* d_root, int8_t* d_status_out);
+/* host-buffer conveniences (upload, run, download) */
+int pmt_mmr_bag(pmt_ctx* ctx, const uint64_t* elements, size_t n_leaves, uint64_t* root_out);
+int pmt_mmr_peaks(pmt_ctx* ctx, const uint64_t* elements, size_t n_leaves, uint64_t* peaks_out, uint32_t* n_peaks_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PMT_H */

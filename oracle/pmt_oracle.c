@@ -75,46 +75,74 @@ void pmt_oracle_permute(uint64_t s[12]) {
   for (int i = 0; i < 12; i++) s[i] = pmt_oracle_canonical(s[i]);
 }
 
-/* Same permutation, partial rounds in upstream's "fast" sparse-matrix form (tables re-derived by
- * tools/gen_constants.py, equality with the naive form is a unit test).  Used for CPU-baseline timing. */
-void pmt_oracle_permute_fast(uint64_t s[12]) {
-  int r = 0;
-  for (; r < PMT_FULL_HALF; r++) {
-    for (int i = 0; i < 12; i++) s[i] = sbox7(fadd(s[i], PMT_RC[12 * r + i]));
-    mds_layer(s);
+/* ---- CPU-baseline speed path ------------------------------------------------------------------------------------
+ * Same permutation, engineered the way upstream's scalar x86 path is ([UPSTREAM hash/poseidon.rs mds_layer via
+ * u64 hi/lo accumulation, fast partial rounds]): the MDS layer works on 32-bit halves with plain u64 MACs (sums
+ * < 2^42, one reduction per lane), partial rounds use the sparse-matrix form.  Tables re-derived by
+ * tools/gen_constants.py; equality with the naive form is a unit test.  Used for CPU-baseline timing. */
+static inline uint64_t reduce96(uint64_t lo, uint64_t hi /* < 2^32 */) {
+  return add_no_canon(lo, hi * EPSILON);
+}
+
+static inline void mds_layer_fast(uint64_t s[12], const uint64_t *add) {
+  static const uint64_t C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+  uint64_t lo[24], hi[24], out[12];
+  for (int i = 0; i < 12; i++) {
+    lo[i] = lo[i + 12] = s[i] & EPSILON;
+    hi[i] = hi[i + 12] = s[i] >> 32;
   }
-  for (int i = 0; i < 12; i++) s[i] = fadd(s[i], PMT_FP_FIRST_RC[i]);
+  for (int r = 0; r < 12; r++) {
+    uint64_t L = 0, H = 0;
+    for (int i = 0; i < 12; i++) { L += lo[i + r] * C[i]; H += hi[i + r] * C[i]; }
+    if (r == 0) { L += lo[0] * 8; H += hi[0] * 8; }
+    /* value = L + 2^32 H, H = hh 2^32 + hl  ->  L + 2^32 hl + (2^32 - 1) hh */
+    u128 v = (u128)L + ((u128)(H & EPSILON) << 32) + (u128)(H >> 32) * EPSILON + (add ? add[r] : 0);
+    out[r] = reduce96((uint64_t)v, (uint64_t)(v >> 64));
+  }
+  memcpy(s, out, sizeof out);
+}
+
+/* x^7 on all 12 lanes, staged so that the 12 independent multiplications of each stage overlap in the pipeline */
+static inline void sbox_layer_fast(uint64_t s[12]) {
+  uint64_t x2[12], x3[12], x4[12];
+  for (int i = 0; i < 12; i++) x2[i] = fmul(s[i], s[i]);
+  for (int i = 0; i < 12; i++) x4[i] = fmul(x2[i], x2[i]);
+  for (int i = 0; i < 12; i++) x3[i] = fmul(x2[i], s[i]);
+  for (int i = 0; i < 12; i++) s[i] = fmul(x3[i], x4[i]);
+}
+
+static inline uint64_t dot12(const uint64_t *x, const uint64_t *k, int n) {
+  u128 lo = 0, hi = 0; /* sum of n <= 12 128-bit products kept as two 68-bit halves */
+  for (int i = 0; i < n; i++) {
+    u128 pr = (u128)x[i] * k[i];
+    lo += (uint64_t)pr;
+    hi += (uint64_t)(pr >> 64);
+  }
+  return fadd(reduce128(lo), reduce128(hi * (u128)EPSILON));
+}
+
+void pmt_oracle_permute_fast(uint64_t s[12]) {
+  for (int i = 0; i < 12; i++) s[i] = fadd(s[i], PMT_RC[i]);
+  for (int r = 0; r < PMT_FULL_HALF; r++) {
+    sbox_layer_fast(s);
+    mds_layer_fast(s, r + 1 < PMT_FULL_HALF ? &PMT_RC[12 * (r + 1)] : PMT_FP_FIRST_RC);
+  }
   {
     uint64_t t[12];
     t[0] = s[0];
-    for (int a = 1; a < 12; a++) {
-      u128 lo = 0, hi = 0; /* sum of 11 128-bit products: keep two halves to avoid overflow */
-      for (int b = 1; b < 12; b++) {
-        u128 pr = (u128)s[b] * PMT_FP_INIT[11 * (a - 1) + (b - 1)];
-        lo += (uint64_t)pr;
-        hi += (uint64_t)(pr >> 64);
-      }
-      /* value = lo + hi * 2^64  (lo, hi < 2^68) */
-      uint64_t h = reduce128(hi * (u128)EPSILON); /* hi * 2^64 mod p */
-      t[a] = fadd(reduce128(lo), h);
-    }
+    for (int a = 1; a < 12; a++) t[a] = dot12(s + 1, &PMT_FP_INIT[11 * (a - 1)], 11);
     memcpy(s, t, sizeof t);
   }
   for (int k = 0; k < PMT_PARTIAL; k++) {
     uint64_t x0 = fadd(sbox7(s[0]), PMT_FP_POST_RC[k]);
-    u128 lo = (u128)x0 * PMT_FP_M00, hi = 0;
-    for (int i = 1; i < 12; i++) {
-      u128 pr = (u128)s[i] * PMT_FP_W_HAT[11 * k + (i - 1)];
-      lo += (uint64_t)pr;
-      hi += (uint64_t)(pr >> 64);
-    }
-    uint64_t d = fadd(reduce128(lo), reduce128(hi * (u128)EPSILON));
+    uint64_t d = fadd(dot12(s + 1, &PMT_FP_W_HAT[11 * k], 11), reduce128((u128)x0 * PMT_FP_M00));
     for (int i = 1; i < 12; i++) s[i] = reduce128((u128)x0 * PMT_FP_V[11 * k + (i - 1)] + s[i]);
     s[0] = d;
   }
-  for (r = PMT_FULL_HALF + PMT_PARTIAL; r < PMT_ROUNDS; r++) {
-    for (int i = 0; i < 12; i++) s[i] = sbox7(fadd(s[i], PMT_RC[12 * r + i]));
-    mds_layer(s);
+  for (int i = 0; i < 12; i++) s[i] = fadd(s[i], PMT_RC[12 * (PMT_FULL_HALF + PMT_PARTIAL) + i]);
+  for (int r = PMT_FULL_HALF + PMT_PARTIAL; r < PMT_ROUNDS; r++) {
+    sbox_layer_fast(s);
+    mds_layer_fast(s, r + 1 < PMT_ROUNDS ? &PMT_RC[12 * (r + 1)] : NULL);
   }
   for (int i = 0; i < 12; i++) s[i] = pmt_oracle_canonical(s[i]);
 }

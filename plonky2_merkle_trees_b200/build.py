@@ -1,0 +1,29 @@
+"""Build libpmt.so in-tree with nvcc for sm_100a (no GPU needed: nvcc cross-compiles)."""
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "libpmt.so")
+SOURCES = [os.path.join(HERE, "csrc", "pmt_api.cu")]
+DEPS = SOURCES + [os.path.join(HERE, "csrc", f) for f in
+                  ("goldilocks.cuh", "poseidon.cuh", "poseidon_constants.cuh", "merkle_kernels.cuh")] + [
+    os.path.join(HERE, "..", "include", "pmt.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
+              "-Xcompiler", "-fPIC", "-cudart", "static"]
+
+
+def needs_build():
+    return not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in DEPS)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return SO
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + SOURCES
+    subprocess.check_call(cmd)
+    return SO
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=True))

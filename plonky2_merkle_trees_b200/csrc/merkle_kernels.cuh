@@ -1,0 +1,307 @@
+// merkle_kernels.cuh -- tree / MMR kernels over the per-thread Poseidon permutation (sm_100a).
+//
+// HBM layouts (all digests are 4 x u64 = 32 B, canonical):
+//   LevelMajor  simple tree, /root/reference/src/simple_merkle_tree/simple_merkle_tree.rs:12-16 (MerkleTree.tree
+//               flattened): level l (0 = leaf digests) starts at digest 2n - (2n >> l); the root is a separate output.
+//   Plonky2     [UPSTREAM hash/merkle_tree.rs] `digests`: per cap subtree  left subtree || left digest || right digest ||
+//               right subtree;  node (l, k') of a subtree sits at 2*(((k'>>1) << (l+1)) + (1<<l) - 1) + (k'&1);
+//               subtree roots go to `cap`.
+//   Mmr         /root/reference/src/mmr/merkle_mountain_ranges.rs:8-12 `elements`, post-order: node (l, k) covering leaves
+//               [k 2^l, (k+1) 2^l) sits at 2*last - popcount(last) + l, last = (k+1) 2^l - 1; children at pos-2^l, pos-1.
+// In every layout the two children of a node are read with 128-bit loads and the parent is written once; nodes are
+// never re-read by the level that produced them, so HBM traffic is the algorithmic 96 B per two_to_one.
+#pragma once
+#include "poseidon.cuh"
+
+namespace pmt {
+
+using poseidon::WIDTH;
+
+// the production permutation (see DESIGN.md "Permutation variants" for the measurements behind this choice)
+__device__ __forceinline__ void permute(uint64_t (&s)[WIDTH]) { poseidon::permute_fast<false, false>(s); }
+
+struct Digest { uint64_t v[4]; };
+
+__device__ __forceinline__ Digest load_digest(const uint64_t* __restrict__ p) {
+  const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(p);
+  const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(p + 2);
+  Digest d; d.v[0] = a.x; d.v[1] = a.y; d.v[2] = b.x; d.v[3] = b.y;
+  return d;
+}
+__device__ __forceinline__ void store_digest(uint64_t* __restrict__ p, const Digest& d) {
+  *reinterpret_cast<ulonglong2*>(p) = make_ulonglong2(d.v[0], d.v[1]);
+  *reinterpret_cast<ulonglong2*>(p + 2) = make_ulonglong2(d.v[2], d.v[3]);
+}
+
+// [UPSTREAM hash/hashing.rs compress]: perm(l || r || 0^4)[0..4)
+__device__ __forceinline__ Digest two_to_one(const Digest& l, const Digest& r) {
+  uint64_t s[WIDTH] = {l.v[0], l.v[1], l.v[2], l.v[3], r.v[0], r.v[1], r.v[2], r.v[3], 0, 0, 0, 0};
+  permute(s);
+  Digest d;
+#pragma unroll
+  for (int i = 0; i < 4; i++) d.v[i] = gl::canonical(s[i]);
+  return d;
+}
+
+// [UPSTREAM hash/hashing.rs hash_n_to_m_no_pad]: overwrite-mode sponge, rate 8, no padding; row = w felts at `row`
+__device__ __forceinline__ Digest hash_no_pad(const uint64_t* __restrict__ row, size_t w) {
+  uint64_t s[WIDTH];
+#pragma unroll
+  for (int i = 0; i < WIDTH; i++) s[i] = 0;
+  for (size_t off = 0; off < w; off += 8) {
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+      if (off + i < w) s[i] = __ldg(row + off + i);
+    permute(s);
+  }
+  Digest d;
+#pragma unroll
+  for (int i = 0; i < 4; i++) d.v[i] = gl::canonical(s[i]);
+  return d;
+}
+
+// [UPSTREAM plonk/config.rs Hasher::hash_or_noop]: <= 4 felts => identity with zero padding (canonicalised)
+__device__ __forceinline__ Digest hash_or_noop(const uint64_t* __restrict__ row, size_t w) {
+  if (w <= 4) {
+    Digest d;
+#pragma unroll
+    for (int i = 0; i < 4; i++) d.v[i] = (size_t)i < w ? gl::canonical(__ldg(row + i)) : 0ull;
+    return d;
+  }
+  return hash_no_pad(row, w);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// layouts
+// ---------------------------------------------------------------------------------------------------------------
+struct LevelMajor {
+  uint64_t* base;   // (2n - 2) digests
+  uint64_t* root;   // 1 digest
+  size_t n;         // leaves
+  int top;          // log2 n  (level `top` = root)
+  __device__ __forceinline__ uint64_t* at(int l, size_t k) const {
+    if (l == top) return root;
+    return base + 4 * ((2 * n - ((2 * n) >> l)) + k);
+  }
+  __device__ __forceinline__ void children(int l, size_t k, const uint64_t*& a, const uint64_t*& b) const {
+    a = at(l - 1, 2 * k); b = a + 4;
+  }
+};
+
+struct Plonky2 {
+  uint64_t* digests;  // 2 (n - 2^h) digests
+  uint64_t* cap;      // 2^h digests
+  int sub_levels;     // L = log2 n - h  (level L = subtree roots -> cap)
+  __device__ __forceinline__ uint64_t* at(int l, size_t k) const {
+    if (l == sub_levels) return cap + 4 * k;
+    const int per = sub_levels - l;                       // log2(nodes of this level per subtree)
+    const size_t c = k >> per, kk = k & (((size_t)1 << per) - 1);
+    const size_t sub_len = ((size_t)2 << sub_levels) - 2;
+    const size_t idx = 2 * (((kk >> 1) << (l + 1)) + ((size_t)1 << l) - 1) + (kk & 1);
+    return digests + 4 * (c * sub_len + idx);
+  }
+  __device__ __forceinline__ void children(int l, size_t k, const uint64_t*& a, const uint64_t*& b) const {
+    a = at(l - 1, 2 * k); b = a + 4;                      // siblings are adjacent in this layout
+  }
+};
+
+struct Mmr {
+  uint64_t* elements;
+  __device__ __forceinline__ static size_t pos(int l, size_t k) {
+    const size_t last = ((k + 1) << l) - 1;
+    return 2 * last - (size_t)__popcll((unsigned long long)last) + (size_t)l;
+  }
+  __device__ __forceinline__ uint64_t* at(int l, size_t k) const { return elements + 4 * pos(l, k); }
+  __device__ __forceinline__ void children(int l, size_t k, const uint64_t*& a, const uint64_t*& b) const {
+    const size_t p = pos(l, k);
+    a = elements + 4 * (p - ((size_t)1 << l));
+    b = elements + 4 * (p - 1);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// kernels.  Block = 128 threads: the permutation needs ~90 registers, so 5 blocks (20 warps) are resident per SM and
+// grids are sized in whole waves of 148 x 5 blocks by the host where the level is large enough.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int BLOCK = 128;
+
+// level 0: digest(0, k0 + i) = hash_or_noop(row i),  rows row-major count x w
+template <class Layout>
+__global__ void __launch_bounds__(BLOCK) k_leaves(Layout lay, const uint64_t* __restrict__ rows, size_t w, size_t k0,
+                                                  size_t count) {
+  for (size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x; i < count; i += (size_t)gridDim.x * BLOCK)
+    store_digest(lay.at(0, k0 + i), hash_or_noop(rows + i * w, w));
+}
+
+// one level: digest(l, k) = two_to_one(children) for k in [k0, k0 + count)
+template <class Layout>
+__global__ void __launch_bounds__(BLOCK) k_level(Layout lay, int l, size_t k0, size_t count) {
+  for (size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x; i < count; i += (size_t)gridDim.x * BLOCK) {
+    const uint64_t *a, *b;
+    lay.children(l, k0 + i, a, b);
+    store_digest(lay.at(l, k0 + i), two_to_one(load_digest(a), load_digest(b)));
+  }
+}
+
+constexpr int TOP_BLOCK = 256;  // 256 x ~100 registers fits one SM's register file without spilling the state
+
+// fused upper levels, ONE block: levels l0 .. l1 (inclusive); level l has count0 >> (l - l0) nodes starting at node 0.
+// Children written by this block in the previous iteration are read back through L2 after a block barrier.
+template <class Layout>
+__global__ void __launch_bounds__(TOP_BLOCK) k_top(Layout lay, int l0, int l1, size_t count0) {
+  size_t count = count0;
+  for (int l = l0; l <= l1; l++, count >>= 1) {
+    for (size_t i = threadIdx.x; i < count; i += blockDim.x) {
+      const uint64_t *a, *b;
+      lay.children(l, i, a, b);
+      store_digest(lay.at(l, i), two_to_one(load_digest(a), load_digest(b)));
+    }
+    __threadfence_block();
+    __syncthreads();
+  }
+}
+
+// generic batches (parity hooks of the Hasher trait)
+__global__ void __launch_bounds__(BLOCK) k_permute(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x; i < n; i += (size_t)gridDim.x * BLOCK) {
+    uint64_t s[WIDTH];
+#pragma unroll
+    for (int j = 0; j < WIDTH; j++) s[j] = in[i * WIDTH + j];
+    permute(s);
+#pragma unroll
+    for (int j = 0; j < WIDTH; j++) out[i * WIDTH + j] = gl::canonical(s[j]);
+  }
+}
+
+// out[i] = two_to_one(l[i], r[i]); `stride` u64 between consecutive inputs (4 = dense arrays, 8 = adjacent sibling pairs)
+__global__ void __launch_bounds__(BLOCK) k_two_to_one(const uint64_t* __restrict__ l, const uint64_t* __restrict__ r,
+                                                      uint64_t* __restrict__ out, size_t n, size_t stride) {
+  for (size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x; i < n; i += (size_t)gridDim.x * BLOCK)
+    store_digest(out + 4 * i, two_to_one(load_digest(l + stride * i), load_digest(r + stride * i)));
+}
+
+template <bool NOOP_RULE>
+__global__ void __launch_bounds__(BLOCK) k_hash_rows(const uint64_t* __restrict__ rows, size_t n, size_t w,
+                                                     uint64_t* __restrict__ out) {
+  for (size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x; i < n; i += (size_t)gridDim.x * BLOCK)
+    store_digest(out + 4 * i, NOOP_RULE ? hash_or_noop(rows + i * w, w) : hash_no_pad(rows + i * w, w));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// proofs: pure gathers, one thread per (proof, level)
+// ---------------------------------------------------------------------------------------------------------------
+// simple_merkle_tree.rs:55-74 get_merkle_proof: level_i[idx_i ^ 1], i = 0 .. log2(n) - 1
+__global__ void k_simple_prove(LevelMajor lay, const uint64_t* __restrict__ idx, size_t n_idx, uint64_t* __restrict__ out) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int depth = lay.top;
+  if (t >= n_idx * (size_t)depth) return;
+  const size_t q = t / depth; const int l = (int)(t % depth);
+  const size_t k = (idx[q] >> l) ^ 1;
+  store_digest(out + 4 * t, load_digest(lay.at(l, k)));
+}
+
+// [UPSTREAM hash/merkle_tree.rs MerkleTree::prove]
+__global__ void k_plonky2_prove(Plonky2 lay, const uint64_t* __restrict__ idx, size_t n_idx, uint64_t* __restrict__ out) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int depth = lay.sub_levels;
+  if (t >= n_idx * (size_t)depth) return;
+  const size_t q = t / depth; const int l = (int)(t % depth);
+  const size_t k = (idx[q] >> l) ^ 1;
+  store_digest(out + 4 * t, load_digest(lay.at(l, k)));
+}
+
+// merkle_mountain_ranges.rs:147-176 get_subtree_proof_elm, closed form: the leaf's mountain has height H = the bit of
+// n_leaves that covers it; entry j = (node (j, (i >> j) ^ 1), sibling_on_left = bit j of i)
+__global__ void k_mmr_prove(Mmr lay, size_t n_leaves, const uint64_t* __restrict__ idx, size_t n_idx,
+                            uint64_t* __restrict__ sib_out, uint8_t* __restrict__ left_out, uint32_t* __restrict__ len_out) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_idx * 32) return;
+  const size_t q = t / 32; const int j = (int)(t % 32);
+  const size_t i = idx[q];
+  // mountains from the largest: the leaf is in the first mountain whose end exceeds i
+  int H = 0; size_t base = 0;
+  for (int b = 63 - __clzll((unsigned long long)n_leaves); b >= 0; b--) {
+    if ((n_leaves >> b) & 1) {
+      if (i < base + ((size_t)1 << b)) { H = b; break; }
+      base += (size_t)1 << b;
+    }
+  }
+  if (j == 0) len_out[q] = (uint32_t)H;
+  if (j < H) {
+    store_digest(sib_out + 4 * t, load_digest(lay.at(j, (i >> j) ^ 1)));
+    left_out[t] = (uint8_t)((i >> j) & 1);
+  }
+}
+
+// merkle_mountain_ranges.rs:179-200 get_peaks: one peak per set bit of n_leaves, largest mountain first
+__global__ void k_mmr_peaks(Mmr lay, size_t n_leaves, uint64_t* __restrict__ out) {
+  const int want = threadIdx.x;
+  int seen = 0; size_t base = 0;
+  for (int b = 63 - __clzll((unsigned long long)n_leaves); b >= 0; b--) {
+    if ((n_leaves >> b) & 1) {
+      if (seen == want) { store_digest(out + 4 * want, load_digest(lay.at(b, base >> b))); return; }
+      seen++; base += (size_t)1 << b;
+    }
+  }
+}
+
+// merkle_mountain_ranges.rs:122-127 bagging_the_peaks = hash_or_noop(flattened peaks); one thread (<= 32 permutations)
+__global__ void k_hash_one(const uint64_t* __restrict__ felts, size_t w, uint64_t* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) store_digest(out, hash_or_noop(felts, w));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// verification: one thread folds one path
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool digest_eq(const Digest& a, const Digest& b) {
+  return a.v[0] == b.v[0] && a.v[1] == b.v[1] && a.v[2] == b.v[2] && a.v[3] == b.v[3];
+}
+__device__ __forceinline__ Digest load_digest_canonical(const uint64_t* __restrict__ p) {
+  Digest d = load_digest(p);
+#pragma unroll
+  for (int i = 0; i < 4; i++) d.v[i] = gl::canonical(d.v[i]);
+  return d;
+}
+
+// simple_merkle_tree.rs:91-109 verify_merkle_proof and [UPSTREAM hash/merkle_proofs.rs verify_merkle_proof_to_cap]:
+// fold by index parity, compare with cap[index >> path_len] (cap_height 0 + width 1 = the simple tree's root)
+__global__ void __launch_bounds__(BLOCK) k_verify_to_cap(const uint64_t* __restrict__ rows, size_t w,
+                                                         const uint64_t* __restrict__ idx, size_t n_idx,
+                                                         const uint64_t* __restrict__ cap, uint32_t cap_height,
+                                                         const uint64_t* __restrict__ proofs, size_t path_len,
+                                                         uint8_t* __restrict__ ok) {
+  const size_t q = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (q >= n_idx) return;
+  size_t index = idx[q];
+  Digest cur = hash_or_noop(rows + q * w, w);
+  for (size_t j = 0; j < path_len; j++) {
+    const Digest sib = load_digest(proofs + 4 * (q * path_len + j));
+    cur = (index & 1) ? two_to_one(sib, cur) : two_to_one(cur, sib);
+    index >>= 1;
+  }
+  ok[q] = (index < ((size_t)1 << cap_height)) && digest_eq(cur, load_digest_canonical(cap + 4 * index));
+}
+
+// merkle_mountain_ranges.rs:232-252 MMR_proof::verify: fold by sibling_on_left, membership in peaks (else the
+// reference panics: status -1), re-bag, compare with root
+__global__ void __launch_bounds__(BLOCK) k_mmr_verify(const uint64_t* __restrict__ leaves, size_t n_idx,
+                                                      const uint64_t* __restrict__ sib, const uint8_t* __restrict__ left,
+                                                      const uint32_t* __restrict__ len, const uint64_t* __restrict__ peaks,
+                                                      uint32_t n_peaks, const uint64_t* __restrict__ bagged,
+                                                      const uint64_t* __restrict__ root, int8_t* __restrict__ status) {
+  const size_t q = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (q >= n_idx) return;
+  Digest cur = hash_or_noop(leaves + q, 1);
+  const uint32_t L = len[q];
+  for (uint32_t j = 0; j < L; j++) {
+    const Digest s = load_digest(sib + 4 * (q * 32 + j));
+    cur = left[q * 32 + j] ? two_to_one(s, cur) : two_to_one(cur, s);
+  }
+  bool found = false;
+  for (uint32_t k = 0; k < n_peaks; k++) found |= digest_eq(cur, load_digest_canonical(peaks + 4 * k));
+  if (!found) { status[q] = -1; return; }
+  // the re-bagged root is identical for every proof of the batch: computed once by k_hash_one into `bagged`
+  status[q] = digest_eq(load_digest(bagged), load_digest_canonical(root)) ? 1 : 0;
+}
+
+}  // namespace pmt

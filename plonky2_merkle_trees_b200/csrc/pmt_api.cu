@@ -1,0 +1,621 @@
+// pmt_api.cu -- C ABI of libpmt.so (include/pmt.h): context, host<->device staging and the launch plans of the
+// tree / MMR builders.  Every entry point returns a status code and never throws across the boundary.
+#include "../../include/pmt.h"
+#include "merkle_kernels.cuh"
+
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+using namespace pmt;
+
+struct pmt_ctx {
+  int device = 0;
+  int sms = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  uint64_t launches = 0;
+  char err[512] = {0};
+  // grow-only staging arenas for the host-buffer entry points
+  void* arena[3] = {nullptr, nullptr, nullptr};
+  size_t arena_bytes[3] = {0, 0, 0};
+  std::vector<void*> user_allocs;
+  // optional per-launch timing (pmt_profile_enable): CUDA events on the launching stream around every kernel
+  struct Rec { const char* name; double units; cudaEvent_t a, b; };
+  bool profiling = false;
+  std::vector<Rec> recs;
+  bool rec_open = false;
+};
+
+static inline void prof_begin(pmt_ctx* c, const char* name, double units) {
+  if (!c->profiling) return;
+  pmt_ctx::Rec r{name, units, nullptr, nullptr};
+  cudaEventCreate(&r.a);
+  cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, c->stream);
+  c->recs.push_back(r);
+  c->rec_open = true;
+}
+static inline void prof_end(pmt_ctx* c) {
+  if (!c->profiling || !c->rec_open) return;
+  cudaEventRecord(c->recs.back().b, c->stream);
+  c->rec_open = false;
+}
+
+namespace {
+
+int fail(pmt_ctx* c, int code, const char* fmt, ...) {
+  if (c) {
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(c->err, sizeof c->err, fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+
+#define CU(c, call)                                                                                        \
+  do {                                                                                                     \
+    cudaError_t e_ = (call);                                                                               \
+    if (e_ != cudaSuccess)                                                                                 \
+      return fail((c), e_ == cudaErrorMemoryAllocation ? PMT_E_OOM : PMT_E_CUDA, "%s: %s (%s:%d)", #call,  \
+                  cudaGetErrorString(e_), __FILE__, __LINE__);                                             \
+  } while (0)
+
+// TAG(c, "kernel", units) goes right before a launch, CHECK_LAUNCH(c) right after it
+#define TAG(c, nm, u) prof_begin((c), (nm), (double)(u))
+
+#define CHECK_LAUNCH(c)                                                                                    \
+  do {                                                                                                     \
+    (c)->launches++;                                                                                       \
+    prof_end(c);                                                                                           \
+    cudaError_t e_ = cudaGetLastError();                                                                   \
+    if (e_ != cudaSuccess) return fail((c), PMT_E_CUDA, "kernel launch: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+int bind(pmt_ctx* c) {
+  if (!c) return PMT_E_INVALID_ARG;
+  CU(c, cudaSetDevice(c->device));
+  return PMT_OK;
+}
+
+int log2_strict(size_t n) {  // plonky2_util::log2_strict: -1 unless n is a power of two
+  if (n == 0 || (n & (n - 1))) return -1;
+  int l = 0;
+  while (((size_t)1 << l) < n) l++;
+  return l;
+}
+
+// grid for `count` independent permutations: whole waves of (SMs x 5 resident 128-thread blocks) when the level is
+// large, otherwise just enough blocks
+unsigned grid_for(const pmt_ctx* c, size_t count) {
+  const size_t wave = (size_t)c->sms * 5;
+  size_t blocks = (count + BLOCK - 1) / BLOCK;
+  if (blocks > wave) {
+    // persistent-style: a multiple of the wave, at most 8 waves; threads stride over the rest
+    size_t waves = (blocks + wave - 1) / wave;
+    if (waves > 8) waves = 8;
+    blocks = waves * wave;
+  }
+  return (unsigned)(blocks ? blocks : 1);
+}
+
+int arena_get(pmt_ctx* c, int slot, size_t bytes, void** out) {
+  if (bytes > c->arena_bytes[slot]) {
+    if (c->arena[slot]) { CU(c, cudaFree(c->arena[slot])); c->arena[slot] = nullptr; c->arena_bytes[slot] = 0; }
+    size_t want = bytes + bytes / 8 + 256;
+    CU(c, cudaMalloc(&c->arena[slot], want));
+    c->arena_bytes[slot] = want;
+  }
+  *out = c->arena[slot];
+  return PMT_OK;
+}
+
+// levels l0 .. top of a perfect tree whose level l0 has `count` nodes starting at node 0: big levels one launch each,
+// the last levels (<= TOP_BLOCK nodes) fused into one single-block launch.
+template <class Layout>
+int run_levels(pmt_ctx* c, const Layout& lay, int l0, int top, size_t count) {
+  int l = l0;
+  for (; l <= top && count > (size_t)TOP_BLOCK; l++, count >>= 1) {
+    TAG(c, "k_level", count);
+    k_level<Layout><<<grid_for(c, count), BLOCK, 0, c->stream>>>(lay, l, 0, count);
+    CHECK_LAUNCH(c);
+  }
+  if (l <= top) {
+    unsigned threads = (unsigned)(count < 32 ? 32 : count);
+    TAG(c, "k_top", 2 * count - 1);
+    k_top<Layout><<<1, threads, 0, c->stream>>>(lay, l, top, count);
+    CHECK_LAUNCH(c);
+  }
+  return PMT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---- context -------------------------------------------------------------------------------------------------------
+int pmt_init(pmt_ctx** out, int device_id) {
+  if (!out) return PMT_E_INVALID_ARG;
+  *out = nullptr;
+  pmt_ctx* c = new (std::nothrow) pmt_ctx();
+  if (!c) return PMT_E_OOM;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0 || device_id < 0 || device_id >= n) {
+    // no CPU fallback: without a usable device the engine refuses to exist
+    delete c;
+    return PMT_E_CUDA;
+  }
+  c->device = device_id;
+  cudaDeviceProp prop;
+  if (cudaSetDevice(device_id) != cudaSuccess || cudaGetDeviceProperties(&prop, device_id) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete c;
+    return PMT_E_CUDA;
+  }
+  c->sms = prop.multiProcessorCount;
+  c->stream = c->own_stream;
+  *out = c;
+  return PMT_OK;
+}
+
+void pmt_destroy(pmt_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (void* p : c->arena) if (p) cudaFree(p);
+  for (void* p : c->user_allocs) cudaFree(p);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+}
+
+const char* pmt_last_error(const pmt_ctx* c) { return c ? c->err : "null ctx"; }
+const char* pmt_version(void) { return "pmt 0.1 (sm_100a)"; }
+int pmt_device_id(const pmt_ctx* c) { return c ? c->device : -1; }
+int pmt_set_stream(pmt_ctx* c, void* s) {
+  if (!c) return PMT_E_INVALID_ARG;
+  c->stream = s ? (cudaStream_t)s : c->own_stream;
+  return PMT_OK;
+}
+void* pmt_get_stream(const pmt_ctx* c) { return c ? (void*)c->stream : nullptr; }
+int pmt_sync(pmt_ctx* c) {
+  if (int rc = bind(c)) return rc;
+  CU(c, cudaStreamSynchronize(c->stream));
+  return PMT_OK;
+}
+uint64_t pmt_kernel_launches(const pmt_ctx* c) { return c ? c->launches : 0; }
+
+// per-launch timing with CUDA events on the launching stream; read() synchronises, aggregates by kernel and resets.
+// Output: one line per kernel "name launches total_ms total_units" (units = permutations the launches computed).
+int pmt_profile_enable(pmt_ctx* c, int on) {
+  if (!c) return PMT_E_INVALID_ARG;
+  c->profiling = on != 0;
+  return PMT_OK;
+}
+int pmt_profile_read(pmt_ctx* c, char* buf, size_t cap) {
+  if (int rc = bind(c)) return rc;
+  if (!buf || cap == 0) return fail(c, PMT_E_INVALID_ARG, "pmt_profile_read: null buffer");
+  CU(c, cudaStreamSynchronize(c->stream));
+  struct Agg { const char* name; int launches; double ms, units; };
+  std::vector<Agg> agg;
+  for (auto& r : c->recs) {
+    float ms = 0;
+    if (r.a && r.b && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      Agg* hit = nullptr;
+      for (auto& a : agg) if (!strcmp(a.name, r.name)) hit = &a;
+      if (!hit) { agg.push_back(Agg{r.name, 0, 0, 0}); hit = &agg.back(); }
+      hit->launches++; hit->ms += ms; hit->units += r.units;
+    }
+    if (r.a) cudaEventDestroy(r.a);
+    if (r.b) cudaEventDestroy(r.b);
+  }
+  c->recs.clear();
+  c->rec_open = false;
+  size_t off = 0;
+  buf[0] = 0;
+  for (auto& a : agg) {
+    int k = snprintf(buf + off, cap - off, "%s %d %.6f %.0f\n", a.name, a.launches, a.ms, a.units);
+    if (k < 0 || (size_t)k >= cap - off) break;
+    off += (size_t)k;
+  }
+  return PMT_OK;
+}
+
+int pmt_malloc(pmt_ctx* c, size_t bytes, void** out) {
+  if (int rc = bind(c)) return rc;
+  if (!out) return fail(c, PMT_E_INVALID_ARG, "pmt_malloc: null out");
+  void* p = nullptr;
+  CU(c, cudaMalloc(&p, bytes ? bytes : 1));
+  c->user_allocs.push_back(p);
+  *out = p;
+  return PMT_OK;
+}
+int pmt_free(pmt_ctx* c, void* p) {
+  if (int rc = bind(c)) return rc;
+  for (size_t i = 0; i < c->user_allocs.size(); i++)
+    if (c->user_allocs[i] == p) {
+      c->user_allocs.erase(c->user_allocs.begin() + i);
+      CU(c, cudaFree(p));
+      return PMT_OK;
+    }
+  return fail(c, PMT_E_INVALID_ARG, "pmt_free: pointer not owned by this ctx");
+}
+int pmt_memcpy_h2d(pmt_ctx* c, void* dst, const void* src, size_t bytes) {
+  if (int rc = bind(c)) return rc;
+  CU(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return PMT_OK;
+}
+int pmt_memcpy_d2h(pmt_ctx* c, void* dst, const void* src, size_t bytes) {
+  if (int rc = bind(c)) return rc;
+  CU(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return PMT_OK;
+}
+
+// ---- device-pointer entry points ---------------------------------------------------------------------------------------
+int pmt_permute_dev(pmt_ctx* c, const uint64_t* d_in, size_t n, uint64_t* d_out) {
+  if (int rc = bind(c)) return rc;
+  if (n == 0) return PMT_OK;
+  if (!d_in || !d_out) return fail(c, PMT_E_INVALID_ARG, "pmt_permute: null pointer");
+  TAG(c, "k_permute", n);
+  k_permute<<<grid_for(c, n), BLOCK, 0, c->stream>>>(d_in, d_out, n);
+  CHECK_LAUNCH(c);
+  return PMT_OK;
+}
+
+int pmt_hash_two_to_one_dev(pmt_ctx* c, const uint64_t* d_l, const uint64_t* d_r, size_t n, uint64_t* d_out) {
+  if (int rc = bind(c)) return rc;
+  if (n == 0) return PMT_OK;
+  if (!d_l || !d_r || !d_out) return fail(c, PMT_E_INVALID_ARG, "pmt_hash_two_to_one: null pointer");
+  TAG(c, "k_two_to_one", n);
+  k_two_to_one<<<grid_for(c, n), BLOCK, 0, c->stream>>>(d_l, d_r, d_out, n, 4);
+  CHECK_LAUNCH(c);
+  return PMT_OK;
+}
+
+int pmt_hash_rows_dev(pmt_ctx* c, const uint64_t* d_rows, size_t n, size_t w, int noop_rule, uint64_t* d_out) {
+  if (int rc = bind(c)) return rc;
+  if (n == 0) return PMT_OK;
+  if (!d_out || (!d_rows && w)) return fail(c, PMT_E_INVALID_ARG, "pmt_hash_rows: null pointer");
+  TAG(c, "k_hash_rows", w <= 4 && noop_rule ? 0 : n * ((w + 7) / 8));
+  if (noop_rule) k_hash_rows<true><<<grid_for(c, n), BLOCK, 0, c->stream>>>(d_rows, n, w, d_out);
+  else k_hash_rows<false><<<grid_for(c, n), BLOCK, 0, c->stream>>>(d_rows, n, w, d_out);
+  CHECK_LAUNCH(c);
+  return PMT_OK;
+}
+
+int pmt_simple_tree_build_dev(pmt_ctx* c, const uint64_t* d_leaves, size_t n, uint64_t* d_levels, uint64_t* d_root) {
+  if (int rc = bind(c)) return rc;
+  const int lg = log2_strict(n);
+  if (lg < 0) return fail(c, PMT_E_NOT_POW2, "simple tree: %zu leaves is not a power of two (log2_strict, simple_merkle_tree.rs:30)", n);
+  if (lg < 1) return fail(c, PMT_E_INVALID_ARG, "simple tree: needs at least 2 leaves (simple_merkle_tree.rs:38)");
+  if (!d_leaves || !d_levels || !d_root) return fail(c, PMT_E_INVALID_ARG, "simple tree: null pointer");
+  LevelMajor lay{d_levels, d_root, n, lg};
+  TAG(c, "k_leaves", 0);
+  k_leaves<LevelMajor><<<grid_for(c, n), BLOCK, 0, c->stream>>>(lay, d_leaves, 1, 0, n);
+  CHECK_LAUNCH(c);
+  return run_levels(c, lay, 1, lg, n / 2);
+}
+
+int pmt_simple_tree_prove_dev(pmt_ctx* c, const uint64_t* d_levels, size_t n, const uint64_t* d_idx, size_t n_idx,
+                              uint64_t* d_out) {
+  if (int rc = bind(c)) return rc;
+  const int lg = log2_strict(n);
+  if (lg < 1) return fail(c, PMT_E_NOT_POW2, "simple tree prove: bad leaf count %zu", n);
+  if (n_idx == 0) return PMT_OK;
+  if (!d_levels || !d_idx || !d_out) return fail(c, PMT_E_INVALID_ARG, "simple tree prove: null pointer");
+  LevelMajor lay{const_cast<uint64_t*>(d_levels), nullptr, n, lg};
+  const size_t total = n_idx * (size_t)lg;
+  k_simple_prove<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(lay, d_idx, n_idx, d_out);
+  CHECK_LAUNCH(c);
+  return PMT_OK;
+}
+
+int pmt_merkle_verify_dev(pmt_ctx* c, const uint64_t* d_rows, size_t w, const uint64_t* d_idx, size_t n_idx,
+                          const uint64_t* d_cap, uint32_t cap_height, const uint64_t* d_proofs, size_t path_len,
+                          uint8_t* d_ok) {
+  if (int rc = bind(c)) return rc;
+  if (n_idx == 0) return PMT_OK;
+  if (!d_rows || !d_idx || !d_cap || !d_ok || (!d_proofs && path_len)) return fail(c, PMT_E_INVALID_ARG, "verify: null pointer");
+  if (w == 0 || cap_height > 40 || path_len > 63) return fail(c, PMT_E_INVALID_ARG, "verify: bad width / cap_height / path_len");
+  k_verify_to_cap<<<(unsigned)((n_idx + BLOCK - 1) / BLOCK), BLOCK, 0, c->stream>>>(d_rows, w, d_idx, n_idx, d_cap, cap_height,
+                                                                                   d_proofs, path_len, d_ok);
+  CHECK_LAUNCH(c);
+  return PMT_OK;
+}
+
+int pmt_simple_tree_verify_dev(pmt_ctx* c, const uint64_t* d_leaves, const uint64_t* d_idx, size_t n_idx,
+                               const uint64_t* d_root, const uint64_t* d_proofs, size_t path_len, uint8_t* d_ok) {
+  // verify_merkle_proof == verify_to_cap with width 1 and a one-entry cap; an index beyond 2^path_len simply fails
+  return pmt_merkle_verify_dev(c, d_leaves, 1, d_idx, n_idx, d_root, 0, d_proofs, path_len, d_ok);
+}
+
+int pmt_merkle_tree_build_dev(pmt_ctx* c, const uint64_t* d_leaves, size_t n, size_t w, uint32_t cap_height,
+                              uint64_t* d_digests, uint64_t* d_cap) {
+  if (int rc = bind(c)) return rc;
+  const int lg = log2_strict(n);
+  if (lg < 0) return fail(c, PMT_E_NOT_POW2, "MerkleTree::new: %zu leaves is not a power of two (log2_strict)", n);
+  if ((int)cap_height > lg) return fail(c, PMT_E_RANGE, "MerkleTree::new: cap_height=%u should be at most log2(leaves.len())=%d", cap_height, lg);
+  if (w == 0) return fail(c, PMT_E_INVALID_ARG, "MerkleTree::new: zero-width leaves");
+  if (!d_leaves || !d_cap || (!d_digests && (size_t)lg > cap_height)) return fail(c, PMT_E_INVALID_ARG, "MerkleTree::new: null pointer");
+  const int L = lg - (int)cap_height;
+  Plonky2 lay{d_digests, d_cap, L};
+  TAG(c, "k_leaves", w <= 4 ? 0 : n * ((w + 7) / 8));
+  k_leaves<Plonky2><<<grid_for(c, n), BLOCK, 0, c->stream>>>(lay, d_leaves, w, 0, n);
+  CHECK_LAUNCH(c);
+  // levels 1 .. L over all subtrees at once: level l has n >> l nodes (2^h subtrees x 2^(L-l))
+  size_t count = n / 2;
+  for (int l = 1; l <= L; l++, count >>= 1) {
+    TAG(c, "k_level", count);
+    k_level<Plonky2><<<grid_for(c, count), BLOCK, 0, c->stream>>>(lay, l, 0, count);
+    CHECK_LAUNCH(c);
+  }
+  return PMT_OK;
+}
+
+int pmt_merkle_prove_dev(pmt_ctx* c, const uint64_t* d_digests, size_t n, uint32_t cap_height, const uint64_t* d_idx,
+                         size_t n_idx, uint64_t* d_out) {
+  if (int rc = bind(c)) return rc;
+  const int lg = log2_strict(n);
+  if (lg < 0) return fail(c, PMT_E_NOT_POW2, "prove: %zu leaves is not a power of two", n);
+  if ((int)cap_height > lg) return fail(c, PMT_E_RANGE, "prove: cap_height %u > log2 n", cap_height);
+  const int L = lg - (int)cap_height;
+  if (n_idx == 0 || L == 0) return PMT_OK;
+  if (!d_digests || !d_idx || !d_out) return fail(c, PMT_E_INVALID_ARG, "prove: null pointer");
+  Plonky2 lay{const_cast<uint64_t*>(d_digests), nullptr, L};
+  const size_t total = n_idx * (size_t)L;
+  k_plonky2_prove<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(lay, d_idx, n_idx, d_out);
+  CHECK_LAUNCH(c);
+  return PMT_OK;
+}
+
+// top of a sharded tree: the g - h levels above the gathered subtree roots.  d_top_out is level-major: n_roots/2,
+// n_roots/4, ..., 2^h digests (n_roots - 2^h in total); its last 2^h digests are the cap.
+int pmt_top_levels_dev(pmt_ctx* c, const uint64_t* d_roots, size_t n_roots, uint32_t cap_height, uint64_t* d_top_out) {
+  if (int rc = bind(c)) return rc;
+  const int g = log2_strict(n_roots);
+  if (g < 0) return fail(c, PMT_E_NOT_POW2, "top levels: %zu roots is not a power of two", n_roots);
+  if ((int)cap_height > g) return fail(c, PMT_E_RANGE, "top levels: cap_height %u > log2(roots)", cap_height);
+  if ((int)cap_height == g) return PMT_OK;  // the roots are the cap
+  if (!d_roots || !d_top_out) return fail(c, PMT_E_INVALID_ARG, "top levels: null pointer");
+  const uint64_t* cur = d_roots;
+  uint64_t* out = d_top_out;
+  for (size_t m = n_roots / 2; m >= ((size_t)1 << cap_height); m >>= 1) {
+    TAG(c, "k_two_to_one", m);
+    k_two_to_one<<<grid_for(c, m), BLOCK, 0, c->stream>>>(cur, cur + 4, out, m, 8);
+    CHECK_LAUNCH(c);
+    cur = out;
+    out += 4 * m;
+    if (m == 1) break;
+  }
+  return PMT_OK;
+}
+
+// ---- MMR ---------------------------------------------------------------------------------------------------------------
+size_t pmt_mmr_size(size_t n) { return 2 * n - (size_t)__builtin_popcountll((unsigned long long)n); }
+size_t pmt_mmr_index(size_t i) { return 2 * i - (size_t)__builtin_popcountll((unsigned long long)i); }
+
+// batch add_leaf (merkle_mountain_ranges.rs:89-120): the nodes created by appending leaves [n0, n0 + m) are, per
+// height l, the k with n0 < (k + 1) 2^l <= n0 + m, i.e. k in [n0 >> l, (n0 + m) >> l).  Level l only reads level l - 1
+// (new or already present in `elements`), so one launch per height is a correct schedule.
+int pmt_mmr_extend_dev(pmt_ctx* c, uint64_t* d_elements, size_t n0, const uint64_t* d_new, size_t m) {
+  if (int rc = bind(c)) return rc;
+  if (m == 0) return PMT_OK;
+  if (!d_elements || !d_new) return fail(c, PMT_E_INVALID_ARG, "mmr extend: null pointer");
+  if (n0 + m > ((size_t)1 << 30)) return fail(c, PMT_E_RANGE, "mmr extend: more than 2^30 leaves (get_mmr_index is i32, merkle_mountain_ranges.rs:264)");
+  Mmr lay{d_elements};
+  TAG(c, "k_leaves", 0);
+  k_leaves<Mmr><<<grid_for(c, m), BLOCK, 0, c->stream>>>(lay, d_new, 1, n0, m);
+  CHECK_LAUNCH(c);
+  for (int l = 1; l < 40; l++) {
+    const size_t k0 = n0 >> l, k1 = (n0 + m) >> l;
+    if (k1 == 0) break;
+    if (k1 > k0) {
+      TAG(c, "k_level", k1 - k0);
+      k_level<Mmr><<<grid_for(c, k1 - k0), BLOCK, 0, c->stream>>>(lay, l, k0, k1 - k0);
+      CHECK_LAUNCH(c);
+    }
+  }
+  return PMT_OK;
+}
+
+int pmt_mmr_peaks_dev(pmt_ctx* c, const uint64_t* d_elements, size_t n_leaves, uint64_t* d_peaks, uint32_t* n_peaks_out) {
+  if (int rc = bind(c)) return rc;
+  const uint32_t k = (uint32_t)__builtin_popcountll((unsigned long long)n_leaves);
+  if (n_peaks_out) *n_peaks_out = k;
+  if (k == 0) return PMT_OK;
+  if (!d_elements || !d_peaks) return fail(c, PMT_E_INVALID_ARG, "mmr peaks: null pointer");
+  if (n_leaves >> 32) return fail(c, PMT_E_RANGE, "mmr peaks: size does not fit u32 (merkle_mountain_ranges.rs:184)");
+  k_mmr_peaks<<<1, 64, 0, c->stream>>>(Mmr{const_cast<uint64_t*>(d_elements)}, n_leaves, d_peaks);
+  CHECK_LAUNCH(c);
+  return PMT_OK;
+}
+
+int pmt_mmr_bag_dev(pmt_ctx* c, const uint64_t* d_elements, size_t n_leaves, uint64_t* d_root) {
+  if (int rc = bind(c)) return rc;
+  if (n_leaves == 0) return fail(c, PMT_E_INVALID_ARG, "mmr bag: empty MMR");
+  if (!d_root) return fail(c, PMT_E_INVALID_ARG, "mmr bag: null pointer");
+  void* peaks = nullptr;
+  if (int rc = arena_get(c, 2, 64 * 32 + 64, &peaks)) return rc;
+  uint32_t k = 0;
+  if (int rc = pmt_mmr_peaks_dev(c, d_elements, n_leaves, (uint64_t*)peaks, &k)) return rc;
+  k_hash_one<<<1, 32, 0, c->stream>>>((const uint64_t*)peaks, (size_t)4 * k, d_root);
+  CHECK_LAUNCH(c);
+  return PMT_OK;
+}
+
+int pmt_mmr_prove_dev(pmt_ctx* c, const uint64_t* d_elements, size_t n_leaves, const uint64_t* d_idx, size_t n_idx,
+                      uint64_t* d_sib, uint8_t* d_left, uint32_t* d_len) {
+  if (int rc = bind(c)) return rc;
+  if (n_idx == 0) return PMT_OK;
+  if (!d_elements || !d_idx || !d_sib || !d_left || !d_len) return fail(c, PMT_E_INVALID_ARG, "mmr prove: null pointer");
+  if (n_leaves == 0 || n_leaves > ((size_t)1 << 30)) return fail(c, PMT_E_RANGE, "mmr prove: bad leaf count");
+  const size_t total = n_idx * 32;
+  k_mmr_prove<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(Mmr{const_cast<uint64_t*>(d_elements)}, n_leaves, d_idx,
+                                                                      n_idx, d_sib, d_left, d_len);
+  CHECK_LAUNCH(c);
+  return PMT_OK;
+}
+
+int pmt_mmr_verify_dev(pmt_ctx* c, const uint64_t* d_leaves, size_t n_idx, const uint64_t* d_sib, const uint8_t* d_left,
+                       const uint32_t* d_len, const uint64_t* d_peaks, uint32_t n_peaks, const uint64_t* d_root,
+                       int8_t* d_status) {
+  if (int rc = bind(c)) return rc;
+  if (n_idx == 0) return PMT_OK;
+  if (!d_leaves || !d_sib || !d_left || !d_len || !d_peaks || !d_root || !d_status) return fail(c, PMT_E_INVALID_ARG, "mmr verify: null pointer");
+  if (n_peaks == 0 || n_peaks > 64) return fail(c, PMT_E_INVALID_ARG, "mmr verify: bad peak count");
+  void* bag = nullptr;
+  if (int rc = arena_get(c, 2, 64 * 32 + 64, &bag)) return rc;
+  uint64_t* d_bag = (uint64_t*)bag + 64 * 4;
+  k_hash_one<<<1, 32, 0, c->stream>>>(d_peaks, (size_t)4 * n_peaks, d_bag);
+  CHECK_LAUNCH(c);
+  k_mmr_verify<<<(unsigned)((n_idx + BLOCK - 1) / BLOCK), BLOCK, 0, c->stream>>>(d_leaves, n_idx, d_sib, d_left, d_len, d_peaks,
+                                                                                n_peaks, d_bag, d_root, d_status);
+  CHECK_LAUNCH(c);
+  return PMT_OK;
+}
+
+// ---- host-buffer entry points: stage through the ctx arenas, run the *_dev plan, copy back, synchronise ------------------
+#define H2D(c, dst, src, bytes) CU(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (c)->stream))
+#define D2H(c, dst, src, bytes) CU(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (c)->stream))
+#define FINISH(c) CU(c, cudaStreamSynchronize((c)->stream))
+
+int pmt_permute(pmt_ctx* c, const uint64_t* in, size_t n, uint64_t* out) {
+  if (int rc = bind(c)) return rc;
+  if (n == 0) return PMT_OK;
+  if (!in || !out) return fail(c, PMT_E_INVALID_ARG, "pmt_permute: null pointer");
+  void *a, *b;
+  if (int rc = arena_get(c, 0, n * 96, &a)) return rc;
+  if (int rc = arena_get(c, 1, n * 96, &b)) return rc;
+  H2D(c, a, in, n * 96);
+  if (int rc = pmt_permute_dev(c, (uint64_t*)a, n, (uint64_t*)b)) return rc;
+  D2H(c, out, b, n * 96);
+  FINISH(c);
+  return PMT_OK;
+}
+
+int pmt_hash_two_to_one(pmt_ctx* c, const uint64_t* l, const uint64_t* r, size_t n, uint64_t* out) {
+  if (int rc = bind(c)) return rc;
+  if (n == 0) return PMT_OK;
+  if (!l || !r || !out) return fail(c, PMT_E_INVALID_ARG, "pmt_hash_two_to_one: null pointer");
+  void *a, *b;
+  if (int rc = arena_get(c, 0, n * 64, &a)) return rc;
+  if (int rc = arena_get(c, 1, n * 32, &b)) return rc;
+  uint64_t* dl = (uint64_t*)a; uint64_t* dr = dl + 4 * n;
+  H2D(c, dl, l, n * 32);
+  H2D(c, dr, r, n * 32);
+  if (int rc = pmt_hash_two_to_one_dev(c, dl, dr, n, (uint64_t*)b)) return rc;
+  D2H(c, out, b, n * 32);
+  FINISH(c);
+  return PMT_OK;
+}
+
+static int hash_rows_host(pmt_ctx* c, const uint64_t* rows, size_t n, size_t w, int noop, uint64_t* out) {
+  if (int rc = bind(c)) return rc;
+  if (n == 0) return PMT_OK;
+  if (!out || (!rows && w)) return fail(c, PMT_E_INVALID_ARG, "pmt_hash_rows: null pointer");
+  void *a, *b;
+  if (int rc = arena_get(c, 0, n * w * 8 + 8, &a)) return rc;
+  if (int rc = arena_get(c, 1, n * 32, &b)) return rc;
+  if (w) H2D(c, a, rows, n * w * 8);
+  if (int rc = pmt_hash_rows_dev(c, (uint64_t*)a, n, w, noop, (uint64_t*)b)) return rc;
+  D2H(c, out, b, n * 32);
+  FINISH(c);
+  return PMT_OK;
+}
+int pmt_hash_or_noop(pmt_ctx* c, const uint64_t* rows, size_t n, size_t w, uint64_t* out) { return hash_rows_host(c, rows, n, w, 1, out); }
+int pmt_hash_no_pad(pmt_ctx* c, const uint64_t* rows, size_t n, size_t w, uint64_t* out) { return hash_rows_host(c, rows, n, w, 0, out); }
+
+int pmt_simple_tree_build(pmt_ctx* c, const uint64_t* leaves, size_t n, uint64_t* levels_out, uint64_t* root_out) {
+  if (int rc = bind(c)) return rc;
+  const int lg = log2_strict(n);
+  if (lg < 0) return fail(c, PMT_E_NOT_POW2, "simple tree: %zu leaves is not a power of two (log2_strict, simple_merkle_tree.rs:30)", n);
+  if (lg < 1) return fail(c, PMT_E_INVALID_ARG, "simple tree: needs at least 2 leaves (simple_merkle_tree.rs:38)");
+  if (!leaves || !levels_out || !root_out) return fail(c, PMT_E_INVALID_ARG, "simple tree: null pointer");
+  void *a, *b;
+  if (int rc = arena_get(c, 0, n * 8, &a)) return rc;
+  if (int rc = arena_get(c, 1, (2 * n - 1) * 32, &b)) return rc;
+  uint64_t* d_levels = (uint64_t*)b; uint64_t* d_root = d_levels + 4 * (2 * n - 2);
+  H2D(c, a, leaves, n * 8);
+  if (int rc = pmt_simple_tree_build_dev(c, (uint64_t*)a, n, d_levels, d_root)) return rc;
+  D2H(c, levels_out, d_levels, (2 * n - 2) * 32);
+  D2H(c, root_out, d_root, 32);
+  FINISH(c);
+  return PMT_OK;
+}
+
+int pmt_merkle_tree_build(pmt_ctx* c, const uint64_t* leaves, size_t n, size_t w, uint32_t cap_height,
+                          uint64_t* digests_out, uint64_t* cap_out) {
+  if (int rc = bind(c)) return rc;
+  const int lg = log2_strict(n);
+  if (lg < 0) return fail(c, PMT_E_NOT_POW2, "MerkleTree::new: %zu leaves is not a power of two (log2_strict)", n);
+  if ((int)cap_height > lg) return fail(c, PMT_E_RANGE, "MerkleTree::new: cap_height=%u should be at most log2(leaves.len())=%d", cap_height, lg);
+  if (w == 0) return fail(c, PMT_E_INVALID_ARG, "MerkleTree::new: zero-width leaves");
+  const size_t n_cap = (size_t)1 << cap_height, n_dig = 2 * (n - n_cap);
+  if (!leaves || !cap_out || (!digests_out && n_dig)) return fail(c, PMT_E_INVALID_ARG, "MerkleTree::new: null pointer");
+  void *a, *b;
+  if (int rc = arena_get(c, 0, n * w * 8, &a)) return rc;
+  if (int rc = arena_get(c, 1, (n_dig + n_cap) * 32, &b)) return rc;
+  uint64_t* d_dig = (uint64_t*)b; uint64_t* d_cap = d_dig + 4 * n_dig;
+  H2D(c, a, leaves, n * w * 8);
+  if (int rc = pmt_merkle_tree_build_dev(c, (uint64_t*)a, n, w, cap_height, d_dig, d_cap)) return rc;
+  if (n_dig) D2H(c, digests_out, d_dig, n_dig * 32);
+  D2H(c, cap_out, d_cap, n_cap * 32);
+  FINISH(c);
+  return PMT_OK;
+}
+
+int pmt_mmr_extend(pmt_ctx* c, uint64_t* elements, size_t n0, const uint64_t* new_leaves, size_t m) {
+  if (int rc = bind(c)) return rc;
+  if (m == 0) return PMT_OK;
+  if (!elements || !new_leaves) return fail(c, PMT_E_INVALID_ARG, "mmr extend: null pointer");
+  if (n0 + m > ((size_t)1 << 30)) return fail(c, PMT_E_RANGE, "mmr extend: more than 2^30 leaves (get_mmr_index is i32, merkle_mountain_ranges.rs:264)");
+  const size_t s0 = pmt_mmr_size(n0), s1 = pmt_mmr_size(n0 + m);
+  void *a, *b;
+  if (int rc = arena_get(c, 0, m * 8, &a)) return rc;
+  if (int rc = arena_get(c, 1, s1 * 32, &b)) return rc;
+  H2D(c, a, new_leaves, m * 8);
+  if (s0) H2D(c, b, elements, s0 * 32);  // the old peaks (and only they) are read; uploading the prefix keeps it simple
+  if (int rc = pmt_mmr_extend_dev(c, (uint64_t*)b, n0, (uint64_t*)a, m)) return rc;
+  D2H(c, elements + 4 * s0, (uint64_t*)b + 4 * s0, (s1 - s0) * 32);
+  FINISH(c);
+  return PMT_OK;
+}
+
+int pmt_mmr_peaks(pmt_ctx* c, const uint64_t* elements, size_t n_leaves, uint64_t* peaks_out, uint32_t* n_peaks_out) {
+  if (int rc = bind(c)) return rc;
+  const size_t s = pmt_mmr_size(n_leaves);
+  if (n_leaves == 0) { if (n_peaks_out) *n_peaks_out = 0; return PMT_OK; }
+  if (!elements || !peaks_out) return fail(c, PMT_E_INVALID_ARG, "mmr peaks: null pointer");
+  void *b, *p;
+  if (int rc = arena_get(c, 1, s * 32, &b)) return rc;
+  if (int rc = arena_get(c, 0, 64 * 32, &p)) return rc;
+  H2D(c, b, elements, s * 32);
+  uint32_t k = 0;
+  if (int rc = pmt_mmr_peaks_dev(c, (uint64_t*)b, n_leaves, (uint64_t*)p, &k)) return rc;
+  D2H(c, peaks_out, p, (size_t)k * 32);
+  FINISH(c);
+  if (n_peaks_out) *n_peaks_out = k;
+  return PMT_OK;
+}
+
+int pmt_mmr_bag(pmt_ctx* c, const uint64_t* elements, size_t n_leaves, uint64_t* root_out) {
+  if (int rc = bind(c)) return rc;
+  if (n_leaves == 0) return fail(c, PMT_E_INVALID_ARG, "mmr bag: empty MMR");
+  if (!elements || !root_out) return fail(c, PMT_E_INVALID_ARG, "mmr bag: null pointer");
+  const size_t s = pmt_mmr_size(n_leaves);
+  void *b, *r;
+  if (int rc = arena_get(c, 1, s * 32, &b)) return rc;
+  if (int rc = arena_get(c, 0, 64, &r)) return rc;
+  H2D(c, b, elements, s * 32);
+  if (int rc = pmt_mmr_bag_dev(c, (uint64_t*)b, n_leaves, (uint64_t*)r)) return rc;
+  D2H(c, root_out, r, 32);
+  FINISH(c);
+  return PMT_OK;
+}
+
+}  // extern "C"

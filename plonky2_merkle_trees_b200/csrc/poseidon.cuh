@@ -1,0 +1,190 @@
+// poseidon.cuh -- width-12 Poseidon permutation over Goldilocks, one state per thread, in registers.
+//
+// Replaces [UPSTREAM plonky2 hash/poseidon.rs Poseidon::poseidon, hash/poseidon_goldilocks.rs, hash/hashing.rs
+// compress / hash_n_to_m_no_pad], i.e. what PoseidonHash::{two_to_one, hash_or_noop} execute for
+// /root/reference/src/simple_merkle_tree/simple_merkle_tree.rs:23,33,45 and
+// /root/reference/src/mmr/merkle_mountain_ranges.rs:96,111,125.
+//
+// sm_100a mapping (no tensor cores: this is not a contraction):
+//   * state = 12 x u64 = 24 registers per thread; rounds fully unrolled so every round constant is a c[3][imm] operand.
+//   * MDS layer: the circulant coefficients are < 64, so each lane is split in 32-bit halves and every
+//     coefficient*half MAC is ONE IMAD.WIDE.U32 into a 64-bit column accumulator (no carries: sums < 2^42);
+//     the next round's constants are the accumulators' initial values, so "add round constants" costs nothing.
+//     Two column sums are folded with 2^64 = 2^32 - 1 (gl::combine_halves, 1 IMAD + 4 ALU).
+//   * S-box x^7 = 2 squarings + 2 multiplies, 16 SASS instructions each (gl::mul).
+#pragma once
+#include "goldilocks.cuh"
+#include "poseidon_constants.cuh"
+
+namespace poseidon {
+
+static constexpr int WIDTH = 12;
+
+// out[r] = add[r] + sum_i s[(i + r) % 12] * CIRC[i] + 8 * s[0] * [r == 0];   add = next round's constants
+//
+// Measured on B200 (tools/perm_bench.cu, profiles/pipes_r1.jsonl): IMAD.WIDE.U32 with a zero addend issues at
+// 64 lanes/clk/SM, but with a 64-bit register addend (the "accumulate" form) only at 32, and IMAD.HI at 32.  So the
+// MACs are written as plain C: ptxas turns them into zero-addend IMAD.WIDE.U32 (fma pipe) plus 3-input
+// IADD3/IADD3.X pairs that fold two products per pair (alu pipe) -- one slot on each pipe per product, which
+// balances against the S-box (also one fma slot per alu slot).
+__device__ __forceinline__ void mds_layer(uint64_t (&s)[WIDTH], const uint64_t* __restrict__ add) {
+  uint32_t lo[WIDTH], hi[WIDTH], coef[WIDTH];
+#pragma unroll
+  for (int i = 0; i < WIDTH; i++) { lo[i] = gl::lo32(s[i]); hi[i] = gl::hi32(s[i]); coef[i] = PMT_MDS_CIRC32[i]; }
+  const uint32_t coef00 = PMT_MDS_CIRC32[12];
+#pragma unroll
+  for (int r = 0; r < WIDTH; r++) {
+    // low column starts at the full 64-bit round constant: every constant is < 2^64 - 2^48 (upstream invariant,
+    // asserted by tools/gen_constants.py) and the column sums are < 2^42, so nothing overflows
+    uint64_t L = add ? add[r] : 0ull;
+    uint64_t H = 0ull;
+#pragma unroll
+    for (int i = 0; i < WIDTH; i++) {
+      const uint32_t c = (r == 0 && i == 0) ? coef00 : coef[i];  // MDS_MATRIX_DIAG = [8, 0, ..., 0]
+      L += (uint64_t)lo[(i + r) % WIDTH] * c;
+      H += (uint64_t)hi[(i + r) % WIDTH] * c;
+    }
+    s[r] = gl::combine_halves(L, H);
+  }
+}
+
+// Limb form of the same layer.  Each lane is split 22/21/21 bits; limb * coefficient sums (12 terms + the constant's
+// limb) stay below 2^31, so every MAC is one full-rate 32-bit IMAD with a free accumulate (432 fma slots instead of the
+// 576 that 288 half-rate IMAD.WIDE accumulates cost), at the price of 4 ALU ops per lane to split and 15 to recombine
+// y = A0 + 2^22 A1 + 2^43 A2 (74 bits) and fold the top word with 2^64 = 2^32 - 1.  add_l = limbs of the constants.
+__device__ __forceinline__ void mds_layer_limb3(uint64_t (&s)[WIDTH], const uint32_t* __restrict__ add_l) {
+  uint32_t l0[WIDTH], l1[WIDTH], l2[WIDTH], coef[WIDTH];
+#pragma unroll
+  for (int i = 0; i < WIDTH; i++) {
+    const uint32_t w0 = gl::lo32(s[i]), w1 = gl::hi32(s[i]);
+    l0[i] = w0 & 0x3FFFFFu;
+    l1[i] = __funnelshift_r(w0, w1, 22) & 0x1FFFFFu;
+    l2[i] = w1 >> 11;
+    coef[i] = PMT_MDS_CIRC32[i];
+  }
+  const uint32_t coef00 = PMT_MDS_CIRC32[12];
+#pragma unroll
+  for (int r = 0; r < WIDTH; r++) {
+    uint32_t a0 = add_l[3 * r], a1 = add_l[3 * r + 1], a2 = add_l[3 * r + 2];
+#pragma unroll
+    for (int i = 0; i < WIDTH; i++) {
+      const uint32_t c = (r == 0 && i == 0) ? coef00 : coef[i];
+      a0 += l0[(i + r) % WIDTH] * c;
+      a1 += l1[(i + r) % WIDTH] * c;
+      a2 += l2[(i + r) % WIDTH] * c;
+    }
+    uint32_t lo, hi, top, net;
+    // (top:hi:lo) = a0 + (a1 << 22) + (a2 << 43)
+    asm("add.cc.u32 %0, %3, %4;\n\taddc.cc.u32 %1, %5, %6;\n\taddc.u32 %2, %7, 0;"
+        : "=r"(lo), "=r"(hi), "=r"(top) : "r"(a0), "r"(a1 << 22), "r"(a1 >> 10), "r"(a2 << 11), "r"(a2 >> 21));
+    // + top * (2^32 - 1) = (top << 32) - top; net = carry - borrow is 0 or 1 (a borrow forces the carry, as in
+    // gl::reduce128_alu), folded once more
+    asm("sub.cc.u32 %0, %0, %3;\n\tsubc.cc.u32 %1, %1, 0;\n\tsubc.u32 %2, 0, 0;" : "+r"(lo), "+r"(hi), "=r"(net) : "r"(top));
+    asm("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, %1, 0;" : "+r"(hi), "+r"(net) : "r"(top));
+    asm("sub.cc.u32 %0, %0, %2;\n\tsubc.u32 %1, %1, 0;" : "+r"(lo), "+r"(hi) : "r"(net));
+    hi += net;
+    s[r] = gl::pack(lo, hi);
+  }
+}
+
+// Specification form: 30 x (add constants, x^7 on all lanes / lane 0, MDS).  Output lanes are NOT canonicalised.
+// One rolled loop over the rounds: the body (12 s-boxes + 1 s-box + one MDS layer, ~1.2k SASS instructions = 19 KB)
+// stays inside the 32 KB L1.5 instruction cache; a fully unrolled permutation (~290 KB) would be fetch-bound.
+template <bool SBOX_ALU = false>
+__device__ __forceinline__ void permute_naive(uint64_t (&s)[WIDTH]) {
+#pragma unroll
+  for (int i = 0; i < WIDTH; i++) s[i] = gl::add_canonical(s[i], PMT_RC[i]);
+#pragma unroll 1
+  for (int r = 0; r < PMT_ROUNDS; r++) {
+    if (r < PMT_FULL_HALF || r >= PMT_FULL_HALF + PMT_PARTIAL) {
+#pragma unroll
+      for (int i = 0; i < WIDTH; i++) s[i] = gl::pow7<SBOX_ALU>(s[i]);
+    } else {
+      s[0] = gl::pow7<SBOX_ALU>(s[0]);
+    }
+    // the table has 30 rows; the last layer adds row 30 = zeros (PMT_RC_PAD)
+    mds_layer(s, &PMT_RC[WIDTH * (r + 1)]);
+  }
+}
+
+// sum_{t < N} x[t] * K[t] mod p, K given as 22/22/20-bit limbs kl[3 t + j] (constant memory).
+// Each 32-bit half of x[t] times a limb is < 2^54; N <= 12 such terms stay < 2^58, so the six column sums need no
+// carry handling at all (plain 64-bit adds, which ptxas pairs into 3-input IADD3/IADD3.X).
+template <int N>
+__device__ __forceinline__ uint64_t dot_limbs(const uint64_t (&x)[N], const uint32_t* __restrict__ kl) {
+  uint64_t t00 = 0, t01 = 0, t02 = 0, t10 = 0, t11 = 0, t12 = 0;
+#pragma unroll
+  for (int t = 0; t < N; t++) {
+    const uint32_t a0 = gl::lo32(x[t]), a1 = gl::hi32(x[t]);
+    const uint32_t b0 = kl[3 * t], b1 = kl[3 * t + 1], b2 = kl[3 * t + 2];
+    t00 += (uint64_t)a0 * b0; t01 += (uint64_t)a0 * b1; t02 += (uint64_t)a0 * b2;
+    t10 += (uint64_t)a1 * b0; t11 += (uint64_t)a1 * b1; t12 += (uint64_t)a1 * b2;
+  }
+  // V = G0 + 2^32 G1,  G0 = t00 + 2^22 t01 + 2^44 t02 (< 2^103), G1 likewise.
+  // 2^32 G1 = 2^32 g_lo + 2^96 g_hi = 2^32 g_lo - g_hi (mod p); adding 2^40 p keeps the total non-negative.
+  gl::u128 g0 = (gl::u128)t00 + ((gl::u128)t01 << 22) + ((gl::u128)t02 << 44);
+  gl::u128 g1 = (gl::u128)t10 + ((gl::u128)t11 << 22) + ((gl::u128)t12 << 44);
+  const uint64_t g_lo = (uint64_t)g1, g_hi = (uint64_t)(g1 >> 64);
+  gl::u128 v = g0 + ((gl::u128)g_lo << 32) + (((gl::u128)gl::P << 40) - g_hi);
+  return gl::reduce128(v);
+}
+
+// The same permutation with the 22 partial rounds in the sparse-matrix ("fast") form that upstream also executes
+// [UPSTREAM hash/poseidon.rs partial_first_constant_layer / mds_partial_layer_init / mds_partial_layer_fast]; tables
+// re-derived in tools/gen_constants.py.  Per partial round: 1 s-box, one 12-term dot product, 11 multiply-adds.
+//
+// Code layout matters as much as instruction count here: ncu on the first version (two copies of the full round,
+// 56 KB of SASS) showed a 93.7 % instruction-cache hit rate and 0.45 "no instruction" stalls per issue.  The two
+// halves therefore share ONE full-round body (outer loop over the halves) and the dot product is one shared
+// __noinline__ routine, which keeps the whole permutation under the 32 KB L1.5 instruction cache.
+// (scalar parameters: the CUDA ABI passes them in registers, an array reference would spill the state to local memory)
+__device__ __noinline__ uint64_t dot12_limbs(uint64_t x0, uint64_t x1, uint64_t x2, uint64_t x3, uint64_t x4, uint64_t x5,
+                                             uint64_t x6, uint64_t x7, uint64_t x8, uint64_t x9, uint64_t x10,
+                                             uint64_t x11, const uint32_t* __restrict__ kl) {
+  const uint64_t x[WIDTH] = {x0, x1, x2, x3, x4, x5, x6, x7, x8, x9, x10, x11};
+  return dot_limbs<WIDTH>(x, kl);
+}
+__device__ __forceinline__ uint64_t dot12_limbs(const uint64_t (&s)[WIDTH], const uint32_t* __restrict__ kl) {
+  return dot12_limbs(s[0], s[1], s[2], s[3], s[4], s[5], s[6], s[7], s[8], s[9], s[10], s[11], kl);
+}
+
+template <bool SBOX_ALU = false, bool PART_ALU = false, bool MDS_LIMB = false>
+__device__ __forceinline__ void permute_fast(uint64_t (&s)[WIDTH]) {
+#pragma unroll
+  for (int i = 0; i < WIDTH; i++) s[i] = gl::add_canonical(s[i], PMT_RC[i]);
+#pragma unroll 1
+  for (int half = 0; half < 2; half++) {
+#pragma unroll 1
+    for (int r = 0; r < PMT_FULL_HALF; r++) {
+#pragma unroll
+      for (int i = 0; i < WIDTH; i++) s[i] = gl::pow7<SBOX_ALU>(s[i]);
+      if (MDS_LIMB) mds_layer_limb3(s, &PMT_RC_AFTER_FULL_L[3 * WIDTH * (PMT_FULL_HALF * half + r)]);
+      else mds_layer(s, &PMT_RC_AFTER_FULL[WIDTH * (PMT_FULL_HALF * half + r)]);
+    }
+    if (half == 0) {
+      {  // dense INIT matrix on lanes 1..11 (lane 0 passes through); rows carry a zero coefficient for lane 0
+        uint64_t y[WIDTH];
+#pragma unroll 1
+        for (int a = 1; a < WIDTH; a++) {
+          const uint64_t v = dot12_limbs(s, &PMT_FP_INIT_L[3 * WIDTH * (a - 1)]);
+#pragma unroll
+          for (int i = 1; i < WIDTH; i++) if (i == a) y[i] = v;   // static indexing keeps y[] in registers
+        }
+#pragma unroll
+        for (int i = 1; i < WIDTH; i++) s[i] = y[i];
+      }
+#pragma unroll 1
+      for (int k = 0; k < PMT_PARTIAL; k++) {
+        s[0] = gl::add_canonical(gl::pow7<PART_ALU>(s[0]), PMT_FP_POST_RC[k]);
+        const uint64_t d = dot12_limbs(s, &PMT_FP_W_HAT_L[3 * WIDTH * k]);
+#pragma unroll
+        for (int i = 1; i < WIDTH; i++) s[i] = gl::mul_add<PART_ALU>(s[0], PMT_FP_V[(WIDTH - 1) * k + (i - 1)], s[i]);
+        s[0] = d;
+      }
+#pragma unroll
+      for (int i = 0; i < WIDTH; i++) s[i] = gl::add_canonical(s[i], PMT_RC[WIDTH * (PMT_FULL_HALF + PMT_PARTIAL) + i]);
+    }
+  }
+}
+
+}  // namespace poseidon

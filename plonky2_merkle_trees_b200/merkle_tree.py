@@ -1,0 +1,96 @@
+"""Host mirror of plonky2's `MerkleTree::new(leaves, cap_height)` / `prove` / `verify_merkle_proof_to_cap`
+([UPSTREAM] plonky2 v0.1.3 @ 3b21b87d hash/merkle_tree.rs, hash/merkle_proofs.rs -- what the reference's verifier tests
+run implicitly inside `circuit_data.prove`, e.g. /root/reference/src/mmr/mmr_plonky2_verifier.rs:148).
+
+Fields keep upstream's names: `leaves`, `digests` (interleaved layout), `cap`.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import PmtError, as_u64
+from .device import dev_u64, dptr, to_device, to_host
+
+
+class MerkleTree:
+    def __init__(self, ctx, n, width, cap_height, d_leaves, d_digests, d_cap):
+        self.ctx, self.n, self.width, self.cap_height = ctx, n, width, cap_height
+        self.d_leaves, self.d_digests, self.d_cap = d_leaves, d_digests, d_cap
+        self._digests = self._cap = None
+
+    @classmethod
+    def new(cls, leaves, cap_height, ctx=None):
+        ctx = ctx or _lib.default_context()
+        leaves = as_u64(leaves)
+        if leaves.ndim != 2:
+            raise ValueError("leaves must be (n, width)")
+        n, w = leaves.shape
+        return cls.new_dev(to_device(leaves, "cuda:%d" % ctx.device), cap_height, ctx)
+
+    @classmethod
+    def new_dev(cls, d_leaves, cap_height, ctx=None):
+        """d_leaves: (n, width) int64 CUDA tensor holding u64 felts."""
+        ctx = ctx or _lib.default_context()
+        n, w = d_leaves.shape
+        lg = n.bit_length() - 1
+        if n == 0 or n & (n - 1):
+            raise PmtError(_lib.PMT_E_NOT_POW2, "log2_strict: %d leaves is not a power of two" % n)
+        if cap_height > lg:
+            raise PmtError(_lib.PMT_E_RANGE, "cap_height=%d should be at most log2(leaves.len())=%d" % (cap_height, lg))
+        ncap = 1 << cap_height
+        d_digests = dev_u64((2 * (n - ncap), 4), d_leaves.device)
+        d_cap = dev_u64((ncap, 4), d_leaves.device)
+        ctx.call("pmt_merkle_tree_build_dev", dptr(d_leaves), n, w, cap_height, dptr(d_digests), dptr(d_cap))
+        ctx.sync()
+        return cls(ctx, n, w, cap_height, d_leaves, d_digests, d_cap)
+
+    @property
+    def leaves(self):
+        return to_host(self.d_leaves)
+
+    @property
+    def digests(self):
+        if self._digests is None:
+            self._digests = to_host(self.d_digests)
+        return self._digests
+
+    @property
+    def cap(self):
+        if self._cap is None:
+            self._cap = to_host(self.d_cap)
+        return self._cap
+
+    def prove_batch(self, leaf_indices):
+        idx = as_u64(leaf_indices).reshape(-1)
+        if idx.size and int(idx.max()) >= self.n:
+            raise IndexError("leaf_index out of range")
+        depth = (self.n.bit_length() - 1) - self.cap_height
+        d_idx = to_device(idx, self.d_digests.device)
+        d_out = dev_u64((idx.size, depth, 4), self.d_digests.device)
+        self.ctx.call("pmt_merkle_prove_dev", dptr(self.d_digests), self.n, self.cap_height, dptr(d_idx), idx.size, dptr(d_out))
+        self.ctx.sync()
+        return to_host(d_out)
+
+    def prove(self, leaf_index):
+        """MerkleProof.siblings for one leaf."""
+        return self.prove_batch([leaf_index])[0]
+
+
+def verify_merkle_proofs_to_cap(leaf_rows, leaf_indices, cap, cap_height, proofs, ctx=None):
+    ctx = ctx or _lib.default_context()
+    rows = as_u64(leaf_rows)
+    idx = as_u64(leaf_indices).reshape(-1)
+    rows = rows.reshape(idx.size, -1)
+    proofs = as_u64(proofs).reshape(idx.size, -1, 4)
+    dev = "cuda:%d" % ctx.device
+    d_ok = torch.empty(idx.size, dtype=torch.uint8, device=dev)
+    d_r, d_i, d_c, d_p = to_device(rows, dev), to_device(idx, dev), to_device(as_u64(cap).reshape(-1, 4), dev), to_device(proofs, dev)
+    ctx.call("pmt_merkle_verify_dev", dptr(d_r), rows.shape[1], dptr(d_i), idx.size, dptr(d_c), cap_height, dptr(d_p),
+             proofs.shape[1], dptr(d_ok))
+    ctx.sync()
+    return d_ok.cpu().numpy().astype(bool)
+
+
+def verify_merkle_proof_to_cap(leaf_data, leaf_index, cap, cap_height, siblings, ctx=None):
+    return bool(verify_merkle_proofs_to_cap(as_u64(leaf_data).reshape(1, -1), [leaf_index], cap, cap_height,
+                                            as_u64(siblings).reshape(1, -1, 4), ctx)[0])

@@ -1,0 +1,125 @@
+"""CPU-side tests: the C ABI library loads and exports every symbol include/pmt.h declares, the host-side index math
+matches the reference's tables, and the sharded build's collective logic works across 2 gloo ranks (oracle engine)."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, splitmix_felts
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from plonky2_merkle_trees_b200 import _lib, build
+    build.build()
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "pmt.h")).read()
+    declared = set(re.findall(r"\b(pmt_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 35
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(_lib.exported_symbols())
+    assert lib.pmt_version().startswith(b"pmt")
+    # pure index helpers need no GPU
+    assert [lib.pmt_mmr_size(n) for n in (0, 1, 2, 3, 4, 7, 8)] == [0, 1, 3, 4, 7, 11, 15]
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    from plonky2_merkle_trees_b200 import PmtError, _lib
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(PmtError):
+        _lib.Context(0)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "plonky2_merkle_trees_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("# oracle-free", ""), os.path.join(dirpath, f)
+
+
+def test_mmr_index_math_matches_reference_tables(golden, oracle):
+    from plonky2_merkle_trees_b200 import mmr
+    t = golden["reference"]["mmr_tables"]
+    for size, bitmap in t["heights_bitmap"]:       # merkle_mountain_ranges.rs:280-297
+        assert mmr.get_heights_bitmap_for_mmr_size(size) == (bitmap, 0)
+    for normal, idx in t["mmr_index"]:             # :307-324
+        assert mmr.get_mmr_index(normal) == idx
+        assert mmr._normal_index(idx) == normal
+    for size in range(0, 200):
+        assert mmr.get_heights_bitmap_for_mmr_size(size) == oracle.mmr_heights_bitmap(size)
+    with pytest.raises(ValueError):
+        mmr._normal_index(2)                       # position 2 is an internal node
+    with pytest.raises(OverflowError):
+        mmr.get_mmr_index(1 << 30)
+
+
+def test_sharding_index_math(oracle):
+    from plonky2_merkle_trees_b200 import sharded
+    import py_oracle as po
+    assert sharded.shard_range(1 << 10, 8, 3) == (384, 128)
+    for lg, h in [(3, 0), (4, 1), (5, 0), (6, 2)]:
+        n = 1 << lg
+        seen = set()
+        for l in range(lg - h):
+            for k in range(n >> l):
+                seen.add(sharded.global_digest_index(n, h, l, k))
+        assert seen == set(range(2 * (n - (1 << h))))
+    assert [sharded.digest_index(l, k) for l, k in [(0, 0), (0, 1), (1, 0), (1, 1), (0, 2), (0, 3), (2, 0), (2, 1)]] == list(range(8))
+    assert sharded.digest_index(1, 3) == po.digest_index(1, 3)
+
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "oracle")); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import numpy as np, torch, torch.distributed as dist
+import oracle as orc
+from conftest import splitmix_felts
+from plonky2_merkle_trees_b200 import sharded
+
+class OracleEngine:   # TEST DOUBLE: stands in for the GPU engine so the collective logic runs on CPU/gloo
+    def build_local(self, leaves, h):
+        dg, cap = orc.merkle_tree_new(leaves.numpy().view(np.uint64), h, threads=2, fast=True)
+        return torch.from_numpy(dg.view(np.int64)), torch.from_numpy(cap.view(np.int64))
+    def top_levels(self, roots, h):
+        cur = roots.numpy().view(np.uint64); out = []
+        while cur.shape[0] > (1 << h):
+            cur = orc.two_to_one_batch(cur[0::2], cur[1::2]); out.append(cur)
+        return torch.from_numpy(np.concatenate(out).view(np.int64))
+    def sync(self): pass
+
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+rank = dist.get_rank()
+for lg, w, h in [(6, 4, 0), (5, 9, 1), (5, 135, 3)]:
+    n = 1 << lg
+    rows = splitmix_felts(lg * 13 + w, n * w).reshape(n, w)
+    s, c = sharded.shard_range(n, 2, rank)
+    t = sharded.build_sharded_tree(torch.from_numpy(rows[s:s + c].view(np.int64)), n, h, OracleEngine())
+    chunks = [torch.empty_like(t.local_digests) for _ in range(2)]
+    dist.all_gather(chunks, t.local_digests)
+    odg, ocap = orc.merkle_tree_new(rows, h)
+    assert np.array_equal(t.cap.numpy().view(np.uint64), ocap), (lg, w, h)
+    full = t.assemble_global([x.numpy().view(np.uint64) for x in chunks])
+    assert np.array_equal(full, odg), (lg, w, h)
+    assert t.local_offset() == (0 if rank == 0 else [i for i in range(full.shape[0]) if np.array_equal(full[i], chunks[1][0].numpy().view(np.uint64))][0])
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_sharded_build_two_gloo_ranks(oracle, tmp_path):
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0].decode() for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, o
+        assert "rank %d ok" % r in o

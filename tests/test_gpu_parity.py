@@ -1,0 +1,346 @@
+"""GPU parity: the CUDA path, called through the C ABI (libpmt.so), against the CPU oracle -- bit-exact.
+
+Run on the B200 box: python -m pytest tests -m gpu.  Nothing here reads /root/reference.
+"""
+import ctypes as C
+import random
+
+import numpy as np
+import pytest
+
+from conftest import EDGE, P, splitmix_felts, u64
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from plonky2_merkle_trees_b200 import _lib
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return _lib.default_context(0)
+
+
+@pytest.fixture(scope="module")
+def api(ctx):
+    from plonky2_merkle_trees_b200 import hasher, merkle_tree, mmr, simple_merkle_tree
+    class NS: pass
+    ns = NS()
+    ns.hasher, ns.mt, ns.mmr, ns.smt = hasher, merkle_tree, mmr, simple_merkle_tree
+    return ns
+
+
+def edge_states(count, seed):
+    rnd = random.Random(seed)
+    out = np.zeros((count, 12), np.uint64)
+    for i in range(count):
+        for j in range(12):
+            out[i, j] = rnd.choice(EDGE) if rnd.random() < 0.35 else rnd.getrandbits(64)
+    return out
+
+
+# ---- permutation / Hasher ------------------------------------------------------------------------------------------
+def test_permute_upstream_vectors_and_random(api, oracle, golden):
+    st = np.concatenate([np.zeros((1, 12), np.uint64), np.arange(12, dtype=np.uint64).reshape(1, 12), edge_states(3000, 1),
+                         np.full((1, 12), 2**64 - 1, np.uint64), np.full((1, 12), P - 1, np.uint64)])
+    got = api.hasher.permute(st)
+    assert got[0, :4].tolist() == golden["upstream"]["perm_zero"]
+    assert got[1, :4].tolist() == golden["upstream"]["perm_range12"]
+    for i in range(st.shape[0]):
+        assert got[i].tolist() == oracle.permute(st[i]).tolist(), i
+    assert (got < np.uint64(P)).all()
+
+
+def test_two_to_one_reference_vectors(api, golden):
+    # every two_to_one pair pinned by simple_merkle_tree.rs:136-140, :181-190
+    for name in ("test_build_merkle_tree_4_leaves", "test_build_merkle_tree_16_leaves"):
+        g = golden["reference"]["simple_tree"][name]
+        levels = [u64(l) for l in g["levels"]] + [u64([g["root"]])]
+        for a, b in zip(levels[:-1], levels[1:]):
+            assert api.hasher.two_to_one(a[0::2], a[1::2]).tolist() == b.tolist()
+
+
+def test_two_to_one_random_and_noncanonical(api, oracle):
+    st = edge_states(2000, 2)
+    l, r = st[:, :4].copy(), st[:, 4:8].copy()
+    got = api.hasher.two_to_one(l, r)
+    assert got.tolist() == oracle.two_to_one_batch(l, r).tolist()
+
+
+@pytest.mark.parametrize("w", [1, 2, 3, 4, 5, 7, 8, 9, 12, 15, 16, 17, 24, 25, 135])
+def test_hash_or_noop_widths(api, oracle, golden, w):
+    rows = splitmix_felts(w, 257 * w).reshape(257, w)
+    rows[0] = np.arange(w, dtype=np.uint64)
+    rows[1, :] = np.uint64(2**64 - 1)
+    rows[2, :] = np.uint64(P)
+    got = api.hasher.hash_or_noop(rows)
+    assert got.tolist() == oracle.hash_or_noop_rows(rows).tolist()
+    key = "hash_no_pad_range_%d" % w
+    if key in golden["derived_unpinned"]:
+        assert got[0].tolist() == golden["derived_unpinned"][key]
+    if w <= 4:  # the no-op rule (simple_merkle_tree.rs:210): never permuted, only canonicalised
+        assert got[0, :w].tolist() == list(range(w)) and got[1, :w].tolist() == [2**32 - 2] * w and got[2].tolist() == [0] * 4
+        assert api.hasher.hash_no_pad(rows)[0].tolist() == oracle.hash_no_pad(rows[0]).tolist()
+
+
+def test_empty_batches(api):
+    assert api.hasher.two_to_one(np.zeros((0, 4), np.uint64), np.zeros((0, 4), np.uint64)).shape == (0, 4)
+    assert api.hasher.permute(np.zeros((0, 12), np.uint64)).shape == (0, 12)
+
+
+# ---- simple tree ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["test_build_merkle_tree_4_leaves", "test_build_merkle_tree_16_leaves"])
+def test_simple_tree_reference_vectors(api, golden, name):
+    g = golden["reference"]["simple_tree"][name]
+    t = api.smt.MerkleTree.build(g["leaves"])
+    assert t.count_levels == len(g["levels"])
+    for got, want in zip(t.tree, g["levels"]):
+        assert got.tolist() == want
+    assert t.root.tolist() == g["root"]
+
+
+def test_simple_tree_asserted_proof(api, golden):
+    g = golden["reference"]["simple_tree"]["test_merkle_proof_small_tree"]
+    t = api.smt.MerkleTree.build(g["leaves"])
+    proof = t.get_merkle_proof(0)
+    assert proof.tolist() == g["proof"]                      # simple_merkle_tree.rs:210-211
+    assert api.smt.verify_merkle_proof(g["leaves"][0], 0, t.root, proof)
+
+
+def test_simple_tree_verify_roundtrip_and_negatives(api, oracle, golden):
+    leaves = golden["reference"]["simple_tree"]["test_build_merkle_tree_16_leaves"]["leaves"]
+    t = api.smt.MerkleTree.build(leaves)
+    proofs = t.get_merkle_proofs(list(range(16)))
+    assert api.smt.verify_merkle_proofs(leaves, list(range(16)), t.root, proofs).all()
+    for i in range(16):
+        assert oracle.simple_tree_verify(leaves[i], i, t.root, proofs[i])
+        assert t.get_in_between_hashes(i).tolist() == oracle.simple_tree_in_between(np.concatenate(t.tree), t.root, 16, i).tolist()
+    p3 = proofs[3]
+    assert not api.smt.verify_merkle_proof(leaves[4], 3, t.root, p3)          # wrong leaf  (:298)
+    assert not api.smt.verify_merkle_proof(leaves[3], 2, t.root, p3)          # wrong index (:300)
+    bad = p3.copy(); bad[1, 0] ^= np.uint64(1)
+    assert not api.smt.verify_merkle_proof(leaves[3], 3, t.root, bad)         # wrong proof (:303)
+    assert not api.smt.verify_merkle_proof(leaves[3], 3, t.tree[0][0], p3)    # wrong root  (:306)
+    with pytest.raises(IndexError):
+        t.get_merkle_proof(16)
+    from plonky2_merkle_trees_b200 import PmtError
+    with pytest.raises(PmtError):
+        api.smt.MerkleTree.build([1, 2, 3])
+    with pytest.raises(PmtError):
+        api.smt.MerkleTree.build([1])
+
+
+@pytest.mark.parametrize("lg", [1, 2, 5, 8, 9, 10, 13])
+def test_simple_tree_vs_oracle(api, oracle, lg):
+    n = 1 << lg
+    leaves = splitmix_felts(100 + lg, n)
+    leaves[:min(n, 8)] = u64(EDGE)[:min(n, 8)]
+    t = api.smt.MerkleTree.build(leaves)
+    levels, root = oracle.simple_tree_build(leaves)
+    assert np.array_equal(np.concatenate(t.tree), levels)
+    assert np.array_equal(t.root, root)
+    idx = sorted({0, 1, n // 2, n - 1})
+    proofs = t.get_merkle_proofs(idx)
+    for i, pr in zip(idx, proofs):
+        assert np.array_equal(pr, oracle.simple_tree_proof(levels, n, i))
+
+
+def test_simple_tree_host_buffer_abi(ctx, oracle):
+    from plonky2_merkle_trees_b200._lib import ptr
+    n = 1 << 10  # BASELINE config C1
+    leaves = splitmix_felts(0x706d745f62323030, n)
+    levels = np.zeros((2 * n - 2, 4), np.uint64); root = np.zeros(4, np.uint64)
+    ctx.call("pmt_simple_tree_build", ptr(leaves), n, ptr(levels), ptr(root))
+    ol, orr = oracle.simple_tree_build(leaves)
+    assert np.array_equal(levels, ol) and np.array_equal(root, orr)
+
+
+# ---- plonky2 MerkleTree::new ----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("lg,w,h", [(0, 4, 0), (1, 1, 0), (1, 4, 1), (3, 4, 0), (4, 5, 2), (5, 9, 5), (6, 135, 4), (6, 3, 0),
+                                    (10, 4, 0), (11, 7, 3), (9, 135, 4), (12, 1, 0), (12, 4, 12)])
+def test_merkle_tree_new_vs_oracle(api, oracle, lg, w, h):
+    n = 1 << lg
+    rows = splitmix_felts(7 * lg + w, n * w).reshape(n, w)
+    rows[0, :] = np.uint64(2**64 - 1)
+    t = api.mt.MerkleTree.new(rows, h)
+    dg, cap = oracle.merkle_tree_new(rows, h, threads=4, fast=True)
+    assert np.array_equal(t.digests, dg)
+    assert np.array_equal(t.cap, cap)
+    idx = sorted({0, n // 3, n - 1})
+    proofs = t.prove_batch(idx)
+    for i, pr in zip(idx, proofs):
+        assert np.array_equal(pr, oracle.merkle_prove(dg, n, h, i))
+    ok = api.mt.verify_merkle_proofs_to_cap(rows[idx], idx, cap, h, proofs)
+    assert ok.all()
+    if proofs.shape[1]:
+        bad = proofs.copy(); bad[0, 0, 0] ^= np.uint64(1)
+        assert not api.mt.verify_merkle_proofs_to_cap(rows[idx], idx, cap, h, bad)[0]
+    wrong_row = rows[idx].copy(); wrong_row[0, 0] ^= np.uint64(1)
+    assert not api.mt.verify_merkle_proofs_to_cap(wrong_row, idx, cap, h, proofs)[0]
+
+
+def test_merkle_tree_errors(api):
+    from plonky2_merkle_trees_b200 import PmtError
+    with pytest.raises(PmtError):
+        api.mt.MerkleTree.new(np.zeros((3, 4), np.uint64), 0)
+    with pytest.raises(PmtError):
+        api.mt.MerkleTree.new(np.zeros((4, 4), np.uint64), 3)
+
+
+def test_merkle_tree_host_buffer_abi(ctx, oracle):
+    from plonky2_merkle_trees_b200._lib import ptr
+    n, w, h = 1 << 9, 135, 4
+    rows = splitmix_felts(3, n * w).reshape(n, w)
+    dg = np.zeros((2 * (n - 16), 4), np.uint64); cap = np.zeros((16, 4), np.uint64)
+    ctx.call("pmt_merkle_tree_build", ptr(rows), n, w, h, ptr(dg), ptr(cap))
+    odg, ocap = oracle.merkle_tree_new(rows, h, threads=4, fast=True)
+    assert np.array_equal(dg, odg) and np.array_equal(cap, ocap)
+
+
+def test_full_size_properties_2p20(api, oracle):
+    """BASELINE C2 (2^20 x 4, cap 0) at full size: structure checks that do not need a full CPU rebuild."""
+    n, w = 1 << 20, 4
+    rows = splitmix_felts(0x706d745f62323030, n * w).reshape(n, w)
+    t0 = api.mt.MerkleTree.new(rows, 0)
+    t4 = api.mt.MerkleTree.new(rows, 4)
+    # (1) the 16 cap entries of the cap-4 tree hash up to the cap-0 root
+    lvl = t4.cap
+    while lvl.shape[0] > 1:
+        lvl = api.hasher.two_to_one(lvl[0::2], lvl[1::2])
+    assert np.array_equal(lvl[0], t0.cap[0])
+    # (2) leaf digests are the canonical no-op copy, at digest positions 4j, 4j+1
+    d = t0.digests
+    assert np.array_equal(d[0::4][:n // 2], rows[0::2]) and np.array_equal(d[1::4][:n // 2], rows[1::2])
+    # (3) one random cap-4 subtree (2^16 leaves) rebuilt by the multi-threaded oracle is byte-identical
+    c = 11
+    sub = rows[c << 16:(c + 1) << 16]
+    odg, ocap = oracle.merkle_tree_new(sub, 0, threads=oracle.max_threads(), fast=True)
+    per = t4.digests.shape[0] // 16
+    assert np.array_equal(t4.digests[c * per:(c + 1) * per], odg) and np.array_equal(t4.cap[c], ocap[0])
+    # (4) 1024 proofs verify against the cap; a corrupted one does not
+    idx = (splitmix_felts(5, 1024) % np.uint64(n)).astype(np.uint64)
+    proofs = t0.prove_batch(idx)
+    assert api.mt.verify_merkle_proofs_to_cap(rows[idx.astype(np.int64)], idx, t0.cap, 0, proofs).all()
+
+
+# ---- MMR -------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", list(range(1, 36)) + [63, 64, 65, 70, 100, 255, 1000, 4097])
+def test_mmr_extend_vs_sequential_add_leaf(api, oracle, n):
+    leaves = splitmix_felts(1000 + n, n)
+    m = api.mmr.MMR.new()
+    m.extend(leaves)
+    want = oracle.mmr_extend(None, leaves)
+    assert len(m) == want.shape[0] == 2 * n - bin(n).count("1")
+    assert np.array_equal(m.elements, want)
+    assert np.array_equal(m.get_peaks(), oracle.mmr_peaks(want))
+    assert np.array_equal(m.bagging_the_peaks(), oracle.mmr_bag(want))
+
+
+def test_mmr_incremental_and_add_leaf(api, oracle):
+    leaves = splitmix_felts(77, 300)
+    m = api.mmr.MMR.new()
+    cuts = [0, 1, 2, 5, 6, 64, 65, 130, 299, 300]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        m.extend(leaves[a:b])
+        assert np.array_equal(m.elements, oracle.mmr_extend(None, leaves[:b]))
+    m2 = api.mmr.MMR.new()
+    for x in leaves[:20]:
+        m2.add_leaf(int(x))
+    assert np.array_equal(m2.elements, oracle.mmr_extend(None, leaves[:20]))
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 8, 13, 16, 22, 31, 70, 1031])
+def test_mmr_proofs_and_verify(api, oracle, n):
+    leaves = splitmix_felts(2000 + n, n)
+    m = api.mmr.MMR.new()
+    m.extend(leaves)
+    el = oracle.mmr_extend(None, leaves)
+    root = m.bagging_the_peaks()
+    peaks = m.get_peaks()
+    idx = list(range(n)) if n <= 70 else [0, 1, 511, 512, 1023, 1024, 1027, 1028, 1029, 1030]
+    sib, left, ln = m.prove_batch(idx)
+    for q, i in enumerate(idx):
+        osib, oleft = oracle.mmr_subtree_proof(el, api.mmr.get_mmr_index(i))
+        assert int(ln[q]) == osib.shape[0]
+        assert np.array_equal(sib[q, :ln[q]], osib) and np.array_equal(left[q, :ln[q]], oleft)
+    st = api.mmr.verify_batch(leaves[idx], sib, left, ln, peaks, root)
+    assert (st == 1).all()
+    assert (api.mmr.verify_batch(leaves[idx] ^ np.uint64(1), sib, left, ln, peaks, root) == -1).all()   # assert! :245
+    assert (api.mmr.verify_batch(leaves[idx], sib, left, ln, peaks, root ^ np.uint64(1)) == 0).all()
+    # the reference-shaped single-proof API
+    pr = m.get_proof(api.mmr.get_mmr_index(idx[-1]))
+    assert pr.mmr_size == el.shape[0] and pr.verify(int(leaves[idx[-1]]), root)
+    with pytest.raises(AssertionError):
+        pr.verify(int(leaves[idx[-1]]) ^ 1, root)
+    assert oracle.mmr_verify(leaves[idx[-1]], root, np.array([d for d, _ in pr.merkle_proof]).reshape(-1, 4),
+                             [int(b) for _, b in pr.merkle_proof], pr.peaks) == 1
+
+
+def test_mmr_host_buffer_abi(ctx, oracle):
+    from plonky2_merkle_trees_b200._lib import ptr
+    lib = ctx.lib
+    n0, m = 37, 100
+    leaves = splitmix_felts(9, n0 + m)
+    el = np.zeros((lib.pmt_mmr_size(n0 + m), 4), np.uint64)
+    ctx.call("pmt_mmr_extend", ptr(el), 0, ptr(leaves[:n0]), n0)
+    ctx.call("pmt_mmr_extend", ptr(el), n0, ptr(leaves[n0:]), m)
+    want = oracle.mmr_extend(None, leaves)
+    assert np.array_equal(el, want)
+    root = np.zeros(4, np.uint64); peaks = np.zeros((64, 4), np.uint64); k = C.c_uint32(0)
+    ctx.call("pmt_mmr_bag", ptr(el), n0 + m, ptr(root))
+    ctx.call("pmt_mmr_peaks", ptr(el), n0 + m, ptr(peaks), C.byref(k))
+    assert np.array_equal(root, oracle.mmr_bag(want)) and np.array_equal(peaks[:k.value], oracle.mmr_peaks(want))
+    assert lib.pmt_mmr_index(15) == 26
+
+
+def test_mmr_2p20_against_tree(api):
+    """an MMR with 2^20 leaves is one mountain: its nodes are the simple tree's levels in post-order (size check)."""
+    n = 1 << 20
+    leaves = splitmix_felts(0x706d745f62323030, n)
+    m = api.mmr.MMR.new(); m.extend(leaves)
+    t = api.smt.MerkleTree.build(leaves)
+    assert np.array_equal(m.bagging_the_peaks(), t.root)      # 1 peak => bag = identity
+    el = m.elements
+    assert np.array_equal(el[-1], t.root)
+    pos = lambda h, k: 2 * (((k + 1) << h) - 1) - bin(((k + 1) << h) - 1).count("1") + h
+    for h in (0, 1, 7, 19):
+        ks = [0, 1, (n >> h) - 1]
+        for k in ks:
+            assert np.array_equal(el[pos(h, k)], t.tree[h][k])
+    # ragged: 2^20 - 1 leaves => 20 peaks, multi-block sponge bag; proofs for random leaves verify
+    m2 = api.mmr.MMR.new(); m2.extend(leaves[:n - 1])
+    assert m2.get_peaks().shape[0] == 20
+    idx = (splitmix_felts(6, 64) % np.uint64(n - 1)).astype(np.uint64)
+    sib, left, ln = m2.prove_batch(idx)
+    st = api.mmr.verify_batch(leaves[idx.astype(np.int64)], sib, left, ln, m2.get_peaks(), m2.bagging_the_peaks())
+    assert (st == 1).all()
+
+
+# ---- sharded build (virtual ranks on one GPU) ---------------------------------------------------------------------------
+@pytest.mark.parametrize("lg,w,h,G", [(10, 4, 0, 8), (10, 4, 1, 4), (9, 135, 4, 8), (8, 4, 3, 8), (6, 1, 0, 2)])
+def test_sharded_virtual_ranks(ctx, api, oracle, lg, w, h, G):
+    from plonky2_merkle_trees_b200 import sharded
+    from plonky2_merkle_trees_b200.device import to_device, to_host
+    n = 1 << lg
+    rows = splitmix_felts(31 * lg + G, n * w).reshape(n, w)
+    eng = sharded.CudaEngine(ctx)
+    g = G.bit_length() - 1
+    chunks, caps = [], []
+    for r in range(G):
+        s, c = sharded.shard_range(n, G, r)
+        dg, cp = eng.build_local(to_device(rows[s:s + c], eng.device), max(h - g, 0))
+        eng.sync()
+        chunks.append(to_host(dg)); caps.append(to_host(cp))
+    gathered = np.concatenate(caps)
+    odg, ocap = oracle.merkle_tree_new(rows, h, threads=4, fast=True)
+    if h >= g:
+        t = sharded.ShardedMerkleTree(n, w, h, G, 0, None, None, None, gathered)
+        assert np.array_equal(gathered, ocap)
+    else:
+        d_top = eng.top_levels(to_device(gathered, eng.device), h)
+        eng.sync()   # the ctx stream is non-blocking with respect to torch's stream: sync before the D2H copy
+        top = to_host(d_top)
+        t = sharded.ShardedMerkleTree(n, w, h, G, 0, None, gathered, top, top[top.shape[0] - (1 << h):])
+        assert np.array_equal(t.cap, ocap)
+    assert np.array_equal(t.assemble_global(chunks), odg)

@@ -227,6 +227,7 @@ def poseidon_fast(state, rc, fp):
 # emit
 # ----------------------------------------------------------------------------------------------
 def _fmt_u64_table(name, vals, per_line=4, qual="static const uint64_t"):
+    qual = _QUAL[0]
     lines = ["%s %s[%d] = {" % (qual, name, len(vals))]
     for i in range(0, len(vals), per_line):
         lines.append("  " + ", ".join("0x%016xULL" % x for x in vals[i:i + per_line]) + ",")
@@ -234,7 +235,12 @@ def _fmt_u64_table(name, vals, per_line=4, qual="static const uint64_t"):
     return "\n".join(lines)
 
 
+_QUAL = ["static const uint64_t"]
+
+
 def emit(path, guard, rc, fp, cuda):
+    # CUDA: tables live in constant bank 3; with unrolled rounds ptxas folds them into c[0x3][imm] operands
+    _QUAL[0] = "static __device__ __constant__ uint64_t" if cuda else "static const uint64_t"
     flat = lambda mm: [x for row in mm for x in row]
     init_rest = [fp["init_m"][r][c] for r in range(1, WIDTH) for c in range(1, WIDTH)]
     out = []
@@ -247,10 +253,15 @@ def emit(path, guard, rc, fp, cuda):
     out.append("#ifndef %s\n#define %s\n#include <stdint.h>\n" % (guard, guard))
     out.append("#define PMT_P 0xFFFFFFFF00000001ULL")
     out.append("#define PMT_WIDTH 12\n#define PMT_FULL_HALF 4\n#define PMT_PARTIAL 22\n#define PMT_ROUNDS 30\n")
+    if cuda:
+        out.append("// MDS coefficients as 32-bit words in constant memory ON PURPOSE: as immediates ptxas strength-reduces the")
+        out.append("// power-of-two ones into shift/mask sequences; as opaque uniform operands every MAC is one IMAD.WIDE.U32.")
+        out.append("// index 12 = CIRC[0] + DIAG[0] (the lane-0 diagonal term)")
+        out.append("static __device__ __constant__ uint32_t PMT_MDS_CIRC32[13] = {%s};" % ", ".join(str(x) for x in MDS_CIRC + [MDS_CIRC[0] + MDS_DIAG[0]]))
     out.append(_fmt_u64_table("PMT_MDS_CIRC", MDS_CIRC, 12))
     out.append(_fmt_u64_table("PMT_MDS_DIAG", MDS_DIAG, 12))
-    out.append("// ALL_ROUND_CONSTANTS[12*r + lane]")
-    out.append(_fmt_u64_table("PMT_RC", rc))
+    out.append("// ALL_ROUND_CONSTANTS[12*r + lane]" + ("; row 30 = zeros (added after the last MDS layer)" if cuda else ""))
+    out.append(_fmt_u64_table("PMT_RC", rc + ([0] * WIDTH if cuda else [])))
     out.append("// fast partial rounds (derived; see tools/gen_constants.py::derive_fast_partial)")
     out.append(_fmt_u64_table("PMT_FP_FIRST_RC", fp["first"]))
     out.append("// INIT_M rows 1..11, cols 1..11 (row 0 / col 0 are e0): PMT_FP_INIT[11*(r-1) + (c-1)]")
@@ -260,6 +271,31 @@ def emit(path, guard, rc, fp, cuda):
     out.append("// PMT_FP_W_HAT[11*r + (i-1)], PMT_FP_V[11*r + (i-1)]")
     out.append(_fmt_u64_table("PMT_FP_W_HAT", flat(fp["w_hat"])))
     out.append(_fmt_u64_table("PMT_FP_V", flat(fp["v"])))
+    if cuda:
+        out.append("// constants added by the MDS layer that ends full round j (j = 0..7 over both halves): the next round's")
+        out.append("// constants, the fast-partial FIRST_RC after the 4th full round, zeros after the last round.")
+        nxt = rc[12:48] + fp["first"] + rc[12 * 27:12 * 30] + [0] * 12
+        out.append(_fmt_u64_table("PMT_RC_AFTER_FULL", nxt))
+        out.append("// the same constants split 22/21/21 bits for the limb-form MDS layer (poseidon.cuh mds_layer_limb3): [round][lane][limb]")
+        nl = []
+        for x in nxt:
+            nl += [x & 0x3FFFFF, (x >> 22) & 0x1FFFFF, x >> 43]
+        out.append("static __device__ __constant__ uint32_t PMT_RC_AFTER_FULL_L[%d] = {%s};" % (len(nl), ", ".join(map(str, nl))))
+        def limbs(x):
+            return [x & 0x3FFFFF, (x >> 22) & 0x3FFFFF, x >> 44]
+        out.append("// 64-bit constants of the dense/sparse partial-round matrices split into 22/22/20-bit limbs: a 32-bit state half")
+        out.append("// times a limb is < 2^54, so 12-term dot products accumulate in 64 bits without carries (poseidon.cuh dot_limbs).")
+        out.append("// layout: [term][limb], term-major; W_HAT rows are prefixed by M00 (the lane-0 coefficient).")
+        wl = []
+        for r in range(N_PARTIAL):
+            for x in [fp["m00"]] + fp["w_hat"][r]:
+                wl += limbs(x)
+        out.append("static __device__ __constant__ uint32_t PMT_FP_W_HAT_L[%d] = {%s};" % (len(wl), ", ".join(map(str, wl))))
+        il = []
+        for r in range(1, WIDTH):
+            for c in range(WIDTH):
+                il += limbs(fp["init_m"][r][c])   # column 0 is zero: rows are 12 terms so INIT shares dot12_limbs
+        out.append("static __device__ __constant__ uint32_t PMT_FP_INIT_L[%d] = {%s};" % (len(il), ", ".join(map(str, il))))
     out.append("\n#endif")
     os.makedirs(os.path.dirname(path), exist_ok=True)
     with open(path, "w") as f:

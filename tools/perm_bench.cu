@@ -1,0 +1,206 @@
+// perm_bench.cu -- tuning harness (not part of the product library): integer-pipe peak microbenchmarks and
+// raw permutation throughput on one GPU.  Build: see tools/build_perm_bench.sh.  Prints one JSON object per line.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <cuda_runtime.h>
+
+#include "../plonky2_merkle_trees_b200/csrc/poseidon.cuh"
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "CUDA %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
+
+// ---------------------------------------------------------------------------------------------------------------
+// pipe peaks: ILP independent chains per thread, ITER iterations, counted ops = threads * ILP * ITER
+// ---------------------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) k_pipe(uint64_t* out, uint32_t a, uint32_t b, int iters) {
+  constexpr int ILP = 8;
+  uint64_t acc[ILP];
+  uint32_t x[ILP], y[ILP], z[ILP];
+  double dx[ILP];
+  const double dk = (double)a * 1e-9;
+#pragma unroll
+  for (int j = 0; j < ILP; j++) { acc[j] = threadIdx.x + j; x[j] = threadIdx.x * 7 + j; y[j] = x[j] + 1; z[j] = j; dx[j] = 1.0 + j + threadIdx.x; }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+#pragma unroll
+      for (int j = 0; j < ILP; j++) {
+        if (MODE == 0) {  // IMAD.WIDE.U32 acc += a * b'
+          asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(a), "r"(x[j]));
+        } else if (MODE == 1) {  // IMAD (32-bit lo)
+          asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(x[j]) : "r"(a), "r"(b));
+        } else if (MODE == 2) {  // IADD3
+          asm volatile("add.u32 %0, %0, %1;" : "+r"(x[j]) : "r"(a));
+        } else if (MODE == 3) {  // LOP3
+          asm volatile("xor.b32 %0, %0, %1;" : "+r"(x[j]) : "r"(a));
+        } else if (MODE == 4) {  // IMAD.WIDE + IADD3 interleaved (both counted)
+          asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(a), "r"(b));
+          asm volatile("add.u32 %0, %0, %1;" : "+r"(x[j]) : "r"(a));
+        } else if (MODE == 5) {  // carry chain: add.cc / addc (IADD3 + IADD3.X), counted as 2
+          uint32_t lo = (uint32_t)acc[j], hi = (uint32_t)(acc[j] >> 32);
+          asm volatile("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, %1, %3;" : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
+          acc[j] = ((uint64_t)hi << 32) | lo;
+        } else if (MODE == 6) {  // IMAD.WIDE + 2x IADD3 (1:2 mix)
+          asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(a), "r"(b));
+          asm volatile("add.u32 %0, %0, %1;" : "+r"(x[j]) : "r"(a));
+          asm volatile("xor.b32 %0, %0, %1;" : "+r"(x[j]) : "r"(b));
+        } else if (MODE == 7) {  // SHF (funnel shift)
+          asm volatile("shf.l.wrap.b32 %0, %0, %1, 7;" : "+r"(x[j]) : "r"(a));
+        } else if (MODE == 8) {  // IADD3, operands that cannot be folded
+          asm volatile("add.u32 %0, %0, %1;" : "+r"(x[j]) : "r"(x[(j + 1) % ILP]));
+        } else if (MODE == 9) {  // IMAD.HI.U32 with accumulate
+          asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(x[j]) : "r"(a), "r"(x[(j + 1) % ILP]));
+        } else if (MODE == 10) {  // IMAD.WIDE.U32 with carry-out + carry accumulate (counted as 2)
+          uint32_t lo = (uint32_t)acc[j], hi = (uint32_t)(acc[j] >> 32);
+          asm volatile("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;"
+                       : "+r"(lo), "+r"(hi), "+r"(x[j]) : "r"(a), "r"(x[(j + 1) % ILP]));
+          acc[j] = ((uint64_t)hi << 32) | lo;
+        } else if (MODE == 11) {  // chained IMAD.WIDE.U32 with immediate coefficient (the MDS form)
+          uint32_t lo = (uint32_t)acc[j], hi = (uint32_t)(acc[j] >> 32);
+          asm volatile("mad.lo.cc.u32 %0, %2, 41, %0;\n\tmadc.hi.u32 %1, %2, 41, %1;" : "+r"(lo), "+r"(hi) : "r"(x[j]));
+          acc[j] = ((uint64_t)hi << 32) | lo;
+        } else if (MODE == 12) {  // LOP3 unfoldable
+          asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[j]) : "r"(x[(j + 1) % ILP]), "r"(a));
+        } else if (MODE == 14) {  // DFMA (fp64 pipe), dependent accumulate
+          double d = __longlong_as_double((long long)acc[j]);
+          asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(d) : "d"(dk), "d"(dx[j]));
+          acc[j] = (uint64_t)__double_as_longlong(d);
+        } else if (MODE == 15) {  // DFMA + chained IMAD.WIDE (accumulate form) in parallel (counted as 2)
+          double d = __longlong_as_double((long long)acc[j]);
+          asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(d) : "d"(dk), "d"(dx[j]));
+          acc[j] = (uint64_t)__double_as_longlong(d);
+          asm volatile("mad.lo.cc.u32 %0, %2, 41, %0;\n\tmadc.hi.u32 %1, %2, 41, %1;" : "+r"(y[j]), "+r"(z[j]) : "r"(x[j]));
+        } else if (MODE == 16) {  // DFMA + IMAD.WIDE acc + IADD3 (counted as 3)
+          double d = __longlong_as_double((long long)acc[j]);
+          asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(d) : "d"(dk), "d"(dx[j]));
+          acc[j] = (uint64_t)__double_as_longlong(d);
+          asm volatile("mad.lo.cc.u32 %0, %2, 41, %0;\n\tmadc.hi.u32 %1, %2, 41, %1;" : "+r"(y[j]), "+r"(z[j]) : "r"(x[j]));
+          asm volatile("add.u32 %0, %0, %1;" : "+r"(x[j]) : "r"(x[(j + 1) % ILP]));
+        } else if (MODE == 17) {  // DADD
+          double d = __longlong_as_double((long long)acc[j]);
+          asm volatile("add.rn.f64 %0, %0, %1;" : "+d"(d) : "d"(dk));
+          acc[j] = (uint64_t)__double_as_longlong(d);
+        } else if (MODE == 13) {  // SEL
+          asm volatile("{ .reg .pred p; setp.lt.u32 p, %0, %1; selp.u32 %0, %1, %2, p; }" : "+r"(x[j]) : "r"(x[(j + 1) % ILP]), "r"(a));
+        }
+      }
+    }
+  }
+  uint64_t r = 0;
+#pragma unroll
+  for (int j = 0; j < ILP; j++) r += acc[j] + x[j] + y[j] + z[j];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// permutation throughput: each thread runs `chain` dependent permutations on its own state
+// ---------------------------------------------------------------------------------------------------------------
+template <int VARIANT>
+__global__ void __launch_bounds__(128) k_perm(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, int chain) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t s[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[i] = in[t * 12 + i];
+  for (int c = 0; c < chain; c++) {
+    if (VARIANT == 0) poseidon::permute_naive<false>(s);
+    if (VARIANT == 1) poseidon::permute_fast<false, false>(s);
+    if (VARIANT == 2) poseidon::permute_fast<true, false>(s);
+    if (VARIANT == 3) poseidon::permute_fast<true, true>(s);
+    if (VARIANT == 4) poseidon::permute_naive<true>(s);
+    if (VARIANT == 5) poseidon::permute_fast<true, true, true>(s);
+    if (VARIANT == 6) poseidon::permute_fast<false, false, true>(s);
+  }
+#pragma unroll
+  for (int i = 0; i < 12; i++) out[t * 12 + i] = gl::canonical(s[i]);
+}
+
+static float time_ms(cudaEvent_t a, cudaEvent_t b) { float ms; CK(cudaEventElapsedTime(&ms, a, b)); return ms; }
+
+template <int MODE>
+static void run_pipe(const char* name, double ops_per_inner, int sms) {
+  const int threads = 256, blocks = sms * 8, iters = 4096;
+  uint64_t* d; CK(cudaMalloc(&d, sizeof(uint64_t) * threads * blocks));
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  k_pipe<MODE><<<blocks, threads>>>(d, 12345u, 6789u, 16);
+  CK(cudaDeviceSynchronize());
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; rep++) {
+    CK(cudaEventRecord(e0));
+    k_pipe<MODE><<<blocks, threads>>>(d, 12345u, 6789u, iters);
+    CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+    float ms = time_ms(e0, e1); if (ms < best) best = ms;
+  }
+  double ops = (double)threads * blocks * 8 * 4 * iters * ops_per_inner;
+  printf("{\"bench\": \"pipe\", \"name\": \"%s\", \"ms\": %.4f, \"Gops_per_s\": %.1f, \"ops_per_clk_per_sm_at_1965MHz\": %.2f}\n",
+         name, best, ops / best * 1e-6, ops / (best * 1e-3) / 1.965e9 / sms);
+  CK(cudaFree(d));
+}
+
+template <int VARIANT>
+static void run_perm(const char* name, int sms, int blocks_per_sm, int chain, bool check) {
+  const int threads = 128;
+  const size_t n = (size_t)threads * sms * blocks_per_sm;
+  std::vector<uint64_t> h(n * 12);
+  for (size_t i = 0; i < n * 12; i++) h[i] = i < 12 ? i : (i * 0x9E3779B97F4A7C15ull) ^ (i >> 7);
+  uint64_t *din, *dout; CK(cudaMalloc(&din, n * 96)); CK(cudaMalloc(&dout, n * 96));
+  CK(cudaMemcpy(din, h.data(), n * 96, cudaMemcpyHostToDevice));
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  k_perm<VARIANT><<<(unsigned)(n / threads), threads>>>(din, dout, 1);
+  CK(cudaDeviceSynchronize());
+  if (check) {
+    uint64_t r[4]; CK(cudaMemcpy(r, dout, 32, cudaMemcpyDeviceToHost));
+    const uint64_t want[4] = {0xd64e1e3efc5b8e9eull, 0x53666633020aaa47ull, 0xd40285597c6a8825ull, 0x613a4f81e81231d2ull};
+    printf("{\"bench\": \"kat\", \"name\": \"%s\", \"ok\": %s, \"got0\": \"%016llx\"}\n", name,
+           memcmp(r, want, 32) == 0 ? "true" : "false", (unsigned long long)r[0]);
+  }
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; rep++) {
+    CK(cudaEventRecord(e0));
+    k_perm<VARIANT><<<(unsigned)(n / threads), threads>>>(din, dout, chain);
+    CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+    float ms = time_ms(e0, e1); if (ms < best) best = ms;
+  }
+  printf("{\"bench\": \"perm\", \"name\": \"%s\", \"blocks_per_sm\": %d, \"threads\": %d, \"chain\": %d, \"ms\": %.4f, \"Gperm_per_s\": %.4f}\n",
+         name, blocks_per_sm, threads, chain, best, (double)n * chain / best * 1e-6);
+  CK(cudaFree(din)); CK(cudaFree(dout));
+}
+
+int main(int argc, char** argv) {
+  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
+  int sms = prop.multiProcessorCount;
+  printf("{\"bench\": \"device\", \"name\": \"%s\", \"sms\": %d, \"clock_khz\": %d}\n", prop.name, sms, prop.clockRate);
+  bool pipes = argc < 2 || strstr(argv[1], "pipe");
+  bool perms = argc < 2 || strstr(argv[1], "perm");
+  if (pipes) {
+    run_pipe<0>("imad_wide_u32", 1, sms);
+    run_pipe<1>("imad_lo_u32", 1, sms);
+    run_pipe<2>("iadd3", 1, sms);
+    run_pipe<3>("lop3", 1, sms);
+    run_pipe<7>("shf", 1, sms);
+    run_pipe<4>("imad_wide+iadd3 (1:1)", 2, sms);
+    run_pipe<6>("imad_wide+2alu (1:2)", 3, sms);
+    run_pipe<5>("iadd3.cc+iadd3.x", 2, sms);
+    run_pipe<8>("iadd3_unfoldable", 1, sms);
+    run_pipe<12>("lop3_unfoldable", 1, sms);
+    run_pipe<13>("setp+selp", 2, sms);
+    run_pipe<9>("imad_hi_u32", 1, sms);
+    run_pipe<10>("imad_wide.cc+addc", 2, sms);
+    run_pipe<11>("imad_wide_imm_chain", 1, sms);
+    run_pipe<14>("dfma", 1, sms);
+    run_pipe<17>("dadd", 1, sms);
+    run_pipe<15>("dfma+imad_wide_acc (1:1)", 2, sms);
+    run_pipe<16>("dfma+imad_wide_acc+iadd3 (1:1:1)", 3, sms);
+  }
+  if (perms) {
+    int only_bps = argc > 2 ? atoi(argv[2]) : 0;
+    for (int bps : {1, 2, 4, 8}) if (!only_bps || bps == only_bps) run_perm<0>("naive", sms, bps, 16, true);
+    for (int bps : {2, 4, 8}) if (!only_bps || bps == only_bps) run_perm<1>("fast", sms, bps, 16, true);
+    for (int bps : {2, 4, 8}) if (!only_bps || bps == only_bps) run_perm<2>("fast_sboxalu", sms, bps, 16, true);
+    for (int bps : {2, 4, 8}) if (!only_bps || bps == only_bps) run_perm<3>("fast_allalu", sms, bps, 16, true);
+    for (int bps : {2, 4, 8}) if (!only_bps || bps == only_bps) run_perm<5>("fast_allalu_limbmds", sms, bps, 16, true);
+    for (int bps : {2, 4, 8}) if (!only_bps || bps == only_bps) run_perm<6>("fast_limbmds", sms, bps, 16, true);
+  }
+  return 0;
+}
