@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO = os.path.join(HERE, "libpmt.so")
+SO = os.environ.get("PMT_SO", os.path.join(HERE, "libpmt.so"))  # PMT_SO: A/B testing of kernel builds
 
 PMT_OK, PMT_E_INVALID_ARG, PMT_E_NOT_POW2, PMT_E_OOM, PMT_E_CUDA, PMT_E_RANGE = 0, -1, -2, -3, -4, -5
 

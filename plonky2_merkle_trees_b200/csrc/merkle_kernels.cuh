@@ -18,7 +18,14 @@ namespace pmt {
 using poseidon::WIDTH;
 
 // the production permutation (see DESIGN.md "Permutation variants" for the measurements behind this choice)
-__device__ __forceinline__ void permute(uint64_t (&s)[WIDTH]) { poseidon::permute_fast<false, false>(s); }
+__device__ __forceinline__ void permute(uint64_t (&s)[WIDTH]) { poseidon::permute_fast<true, true, 2>(s); }
+// two_to_one: zero capacity lanes on entry, only the digest lanes are read afterwards
+#ifndef PMT_COMPRESS_SPECIALISED
+#define PMT_COMPRESS_SPECIALISED 0  // A/B on B200: the specialised body is 2.6 % slower inside k_level (larger loop body)
+#endif
+__device__ __forceinline__ void permute_compress(uint64_t (&s)[WIDTH]) {
+  poseidon::permute_fast<true, true, 2, PMT_COMPRESS_SPECIALISED != 0, PMT_COMPRESS_SPECIALISED != 0>(s);
+}
 
 struct Digest { uint64_t v[4]; };
 
@@ -36,7 +43,7 @@ __device__ __forceinline__ void store_digest(uint64_t* __restrict__ p, const Dig
 // [UPSTREAM hash/hashing.rs compress]: perm(l || r || 0^4)[0..4)
 __device__ __forceinline__ Digest two_to_one(const Digest& l, const Digest& r) {
   uint64_t s[WIDTH] = {l.v[0], l.v[1], l.v[2], l.v[3], r.v[0], r.v[1], r.v[2], r.v[3], 0, 0, 0, 0};
-  permute(s);
+  permute_compress(s);
   Digest d;
 #pragma unroll
   for (int i = 0; i < 4; i++) d.v[i] = gl::canonical(s[i]);
@@ -159,6 +166,78 @@ __global__ void __launch_bounds__(TOP_BLOCK) k_top(Layout lay, int l0, int l1, s
     __threadfence_block();
     __syncthreads();
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// cooperative (16 lanes per permutation) kernels for levels too small to fill the GPU with one thread per node
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int COOP_BLOCK = 256;          // 16 permutations in flight per block
+constexpr int COOP_GROUPS = COOP_BLOCK / 16;
+
+__device__ __forceinline__ void coop_stage_constants(uint64_t* rc_smem) {
+  for (int i = threadIdx.x; i < WIDTH * (PMT_ROUNDS + 1); i += blockDim.x) rc_smem[i] = PMT_RC[i];
+  __syncthreads();
+}
+
+// one two_to_one by a 16-lane group; `active` = this group has a node (inactive groups still run the shuffles)
+template <class Layout>
+__device__ __forceinline__ void coop_node(const Layout& lay, int l, size_t k, bool active, const uint64_t* rc_smem,
+                                          unsigned g, unsigned base_lane) {
+  uint64_t v = 0;
+  if (active && g < 8) {
+    const uint64_t *a, *b;
+    lay.children(l, k, a, b);
+    v = g < 4 ? a[g] : b[g - 4];
+  }
+  v = poseidon::permute_coop(v, rc_smem, g, base_lane);
+  if (active && g < 4) lay.at(l, k)[g] = gl::canonical(v);
+}
+
+template <class Layout>
+__global__ void __launch_bounds__(COOP_BLOCK) k_level_coop(Layout lay, int l, size_t k0, size_t count) {
+  __shared__ uint64_t rc_smem[WIDTH * (PMT_ROUNDS + 1)];
+  coop_stage_constants(rc_smem);
+  const unsigned g = threadIdx.x & 15, base_lane = threadIdx.x & 16;
+  const size_t group = (size_t)blockIdx.x * COOP_GROUPS + (threadIdx.x >> 4);
+  const size_t stride = (size_t)gridDim.x * COOP_GROUPS;
+  // trip count is uniform across the block so every warp executes the same shuffles
+  for (size_t base = 0; base < count; base += stride) {
+    const size_t i = base + group;
+    coop_node(lay, l, k0 + i, i < count, rc_smem, g, base_lane);
+  }
+}
+
+// fused upper levels in ONE block of 1024 threads (64 groups): levels l0 .. l1, level l has count0 >> (l - l0) nodes
+template <class Layout>
+__global__ void __launch_bounds__(1024) k_top_coop(Layout lay, int l0, int l1, size_t count0) {
+  __shared__ uint64_t rc_smem[WIDTH * (PMT_ROUNDS + 1)];
+  coop_stage_constants(rc_smem);
+  const unsigned g = threadIdx.x & 15, base_lane = threadIdx.x & 16;
+  const size_t group = threadIdx.x >> 4, groups = blockDim.x >> 4;
+  size_t count = count0;
+  for (int l = l0; l <= l1; l++, count >>= 1) {
+    for (size_t base = 0; base < count; base += groups) coop_node(lay, l, base + group, base + group < count, rc_smem, g, base_lane);
+    __threadfence_block();
+    __syncthreads();
+  }
+}
+
+// hash_or_noop of ONE row by one 16-lane group (bagging the peaks): the sponge's permutations are sequential, so the
+// cooperative form cuts the latency by ~10x
+__global__ void __launch_bounds__(32) k_hash_one_coop(const uint64_t* __restrict__ felts, size_t w, uint64_t* __restrict__ out) {
+  __shared__ uint64_t rc_smem[WIDTH * (PMT_ROUNDS + 1)];
+  coop_stage_constants(rc_smem);
+  const unsigned g = threadIdx.x & 15, base_lane = threadIdx.x & 16;
+  if (w <= 4) {
+    if (threadIdx.x < 4) out[threadIdx.x] = threadIdx.x < w ? gl::canonical(felts[threadIdx.x]) : 0ull;
+    return;
+  }
+  uint64_t v = 0;
+  for (size_t off = 0; off < w; off += 8) {
+    if (g < 8 && off + g < w) v = felts[off + g];      // overwrite mode: lanes past the chunk keep their state
+    v = poseidon::permute_coop(v, rc_smem, g, base_lane);
+  }
+  if (threadIdx.x < 4) out[threadIdx.x] = gl::canonical(v);
 }
 
 // generic batches (parity hooks of the Hasher trait)

@@ -28,6 +28,9 @@ struct pmt_ctx {
   bool profiling = false;
   std::vector<Rec> recs;
   bool rec_open = false;
+  // copy streams + events of the pipelined host-buffer tree build (created on first use)
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;
+  std::vector<cudaEvent_t> ev;
 };
 
 static inline void prof_begin(pmt_ctx* c, const char* name, double units) {
@@ -113,20 +116,38 @@ int arena_get(pmt_ctx* c, int slot, size_t bytes, void** out) {
   return PMT_OK;
 }
 
-// levels l0 .. top of a perfect tree whose level l0 has `count` nodes starting at node 0: big levels one launch each,
-// the last levels (<= TOP_BLOCK nodes) fused into one single-block launch.
+// One tree level of `count` nodes starting at node k0.  Big levels: one thread per node.  Levels that cannot fill the
+// GPU that way (<= COOP_MAX nodes) are latency-bound: they run the cooperative 16-lanes-per-permutation kernel.
+constexpr size_t COOP_MAX = (size_t)1 << 15;
+constexpr size_t TOP_FUSE = 64;   // levels with <= 64 nodes are fused into one block (k_top_coop)
+
+template <class Layout>
+int launch_level(pmt_ctx* c, const Layout& lay, int l, size_t k0, size_t count) {
+  if (count == 0) return PMT_OK;
+  if (count > COOP_MAX) {
+    TAG(c, "k_level", count);
+    k_level<Layout><<<grid_for(c, count), BLOCK, 0, c->stream>>>(lay, l, k0, count);
+  } else {
+    size_t blocks = (count + COOP_GROUPS - 1) / COOP_GROUPS;
+    const size_t cap = (size_t)c->sms * 8;
+    if (blocks > cap) blocks = cap;
+    TAG(c, "k_level_coop", count);
+    k_level_coop<Layout><<<(unsigned)blocks, COOP_BLOCK, 0, c->stream>>>(lay, l, k0, count);
+  }
+  CHECK_LAUNCH(c);
+  return PMT_OK;
+}
+
+// levels l0 .. top of a perfect tree whose level l0 has `count` nodes starting at node 0; the last levels
+// (<= TOP_FUSE nodes) are fused into one single-block launch.
 template <class Layout>
 int run_levels(pmt_ctx* c, const Layout& lay, int l0, int top, size_t count) {
   int l = l0;
-  for (; l <= top && count > (size_t)TOP_BLOCK; l++, count >>= 1) {
-    TAG(c, "k_level", count);
-    k_level<Layout><<<grid_for(c, count), BLOCK, 0, c->stream>>>(lay, l, 0, count);
-    CHECK_LAUNCH(c);
-  }
+  for (; l <= top && count > TOP_FUSE; l++, count >>= 1)
+    if (int rc = launch_level(c, lay, l, 0, count)) return rc;
   if (l <= top) {
-    unsigned threads = (unsigned)(count < 32 ? 32 : count);
-    TAG(c, "k_top", 2 * count - 1);
-    k_top<Layout><<<1, threads, 0, c->stream>>>(lay, l, top, count);
+    TAG(c, "k_top_coop", 2 * count - 1);
+    k_top_coop<Layout><<<1, 1024, 0, c->stream>>>(lay, l, top, count);
     CHECK_LAUNCH(c);
   }
   return PMT_OK;
@@ -169,6 +190,9 @@ void pmt_destroy(pmt_ctx* c) {
   for (void* p : c->arena) if (p) cudaFree(p);
   for (void* p : c->user_allocs) cudaFree(p);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  if (c->copy_in) cudaStreamDestroy(c->copy_in);
+  if (c->copy_out) cudaStreamDestroy(c->copy_out);
+  for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
   delete c;
 }
 
@@ -348,13 +372,8 @@ int pmt_merkle_tree_build_dev(pmt_ctx* c, const uint64_t* d_leaves, size_t n, si
   k_leaves<Plonky2><<<grid_for(c, n), BLOCK, 0, c->stream>>>(lay, d_leaves, w, 0, n);
   CHECK_LAUNCH(c);
   // levels 1 .. L over all subtrees at once: level l has n >> l nodes (2^h subtrees x 2^(L-l))
-  size_t count = n / 2;
-  for (int l = 1; l <= L; l++, count >>= 1) {
-    TAG(c, "k_level", count);
-    k_level<Plonky2><<<grid_for(c, count), BLOCK, 0, c->stream>>>(lay, l, 0, count);
-    CHECK_LAUNCH(c);
-  }
-  return PMT_OK;
+  if (L == 0) return PMT_OK;
+  return run_levels(c, lay, 1, L, n / 2);
 }
 
 int pmt_merkle_prove_dev(pmt_ctx* c, const uint64_t* d_digests, size_t n, uint32_t cap_height, const uint64_t* d_idx,
@@ -414,11 +433,8 @@ int pmt_mmr_extend_dev(pmt_ctx* c, uint64_t* d_elements, size_t n0, const uint64
   for (int l = 1; l < 40; l++) {
     const size_t k0 = n0 >> l, k1 = (n0 + m) >> l;
     if (k1 == 0) break;
-    if (k1 > k0) {
-      TAG(c, "k_level", k1 - k0);
-      k_level<Mmr><<<grid_for(c, k1 - k0), BLOCK, 0, c->stream>>>(lay, l, k0, k1 - k0);
-      CHECK_LAUNCH(c);
-    }
+    if (k1 > k0)
+      if (int rc = launch_level(c, lay, l, k0, k1 - k0)) return rc;
   }
   return PMT_OK;
 }
@@ -443,7 +459,8 @@ int pmt_mmr_bag_dev(pmt_ctx* c, const uint64_t* d_elements, size_t n_leaves, uin
   if (int rc = arena_get(c, 2, 64 * 32 + 64, &peaks)) return rc;
   uint32_t k = 0;
   if (int rc = pmt_mmr_peaks_dev(c, d_elements, n_leaves, (uint64_t*)peaks, &k)) return rc;
-  k_hash_one<<<1, 32, 0, c->stream>>>((const uint64_t*)peaks, (size_t)4 * k, d_root);
+  TAG(c, "k_hash_one_coop", (4 * k + 7) / 8);
+  k_hash_one_coop<<<1, 32, 0, c->stream>>>((const uint64_t*)peaks, (size_t)4 * k, d_root);
   CHECK_LAUNCH(c);
   return PMT_OK;
 }
@@ -471,7 +488,8 @@ int pmt_mmr_verify_dev(pmt_ctx* c, const uint64_t* d_leaves, size_t n_idx, const
   void* bag = nullptr;
   if (int rc = arena_get(c, 2, 64 * 32 + 64, &bag)) return rc;
   uint64_t* d_bag = (uint64_t*)bag + 64 * 4;
-  k_hash_one<<<1, 32, 0, c->stream>>>(d_peaks, (size_t)4 * n_peaks, d_bag);
+  TAG(c, "k_hash_one_coop", (4 * n_peaks + 7) / 8);
+  k_hash_one_coop<<<1, 32, 0, c->stream>>>(d_peaks, (size_t)4 * n_peaks, d_bag);
   CHECK_LAUNCH(c);
   k_mmr_verify<<<(unsigned)((n_idx + BLOCK - 1) / BLOCK), BLOCK, 0, c->stream>>>(d_leaves, n_idx, d_sib, d_left, d_len, d_peaks,
                                                                                 n_peaks, d_bag, d_root, d_status);
@@ -548,6 +566,17 @@ int pmt_simple_tree_build(pmt_ctx* c, const uint64_t* leaves, size_t n, uint64_t
   return PMT_OK;
 }
 
+// host index of node (l, k) in upstream's `digests` (same formula as Plonky2::at on the device)
+static size_t plonky2_index(int L, int l, size_t k) {
+  const int per = L - l;
+  const size_t c = k >> per, kk = k & (((size_t)1 << per) - 1);
+  return c * (((size_t)2 << L) - 2) + 2 * (((kk >> 1) << (l + 1)) + ((size_t)1 << l) - 1) + (kk & 1);
+}
+
+// Host-buffer MerkleTree::new.  Large trees are built as a 3-stage pipeline over 16 leaf chunks: chunk i's leaves go up
+// on the copy-in stream while chunk i-1's subtree is hashed on the compute stream and chunk i-2's digests (one
+// contiguous slice of upstream's layout) go down on the copy-out stream, so PCIe traffic in both directions hides
+// behind the permutations.  The few digests above the chunk roots are finished and downloaded at the end.
 int pmt_merkle_tree_build(pmt_ctx* c, const uint64_t* leaves, size_t n, size_t w, uint32_t cap_height,
                           uint64_t* digests_out, uint64_t* cap_out) {
   if (int rc = bind(c)) return rc;
@@ -560,11 +589,60 @@ int pmt_merkle_tree_build(pmt_ctx* c, const uint64_t* leaves, size_t n, size_t w
   void *a, *b;
   if (int rc = arena_get(c, 0, n * w * 8, &a)) return rc;
   if (int rc = arena_get(c, 1, (n_dig + n_cap) * 32, &b)) return rc;
+  uint64_t* d_leaves = (uint64_t*)a;
   uint64_t* d_dig = (uint64_t*)b; uint64_t* d_cap = d_dig + 4 * n_dig;
-  H2D(c, a, leaves, n * w * 8);
-  if (int rc = pmt_merkle_tree_build_dev(c, (uint64_t*)a, n, w, cap_height, d_dig, d_cap)) return rc;
-  if (n_dig) D2H(c, digests_out, d_dig, n_dig * 32);
+  const int L = lg - (int)cap_height;
+  int cb = lg - 4;                 // log2(leaves per chunk): 16 chunks
+  if (cb > L) cb = L;
+  if (cb < 12 || n * w * 8 < ((size_t)8 << 20)) {   // small: one shot
+    H2D(c, d_leaves, leaves, n * w * 8);
+    if (int rc = pmt_merkle_tree_build_dev(c, d_leaves, n, w, cap_height, d_dig, d_cap)) return rc;
+    if (n_dig) D2H(c, digests_out, d_dig, n_dig * 32);
+    D2H(c, cap_out, d_cap, n_cap * 32);
+    FINISH(c);
+    return PMT_OK;
+  }
+  if (!c->copy_in) CU(c, cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
+  if (!c->copy_out) CU(c, cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
+  const size_t chunks = n >> cb, chunk = (size_t)1 << cb;
+  while (c->ev.size() < 2 * chunks + 2) {
+    cudaEvent_t e;
+    CU(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->ev.push_back(e);
+  }
+  // the copy streams must not start before earlier work on the compute stream that used the arenas has finished
+  CU(c, cudaEventRecord(c->ev[2 * chunks], c->stream));
+  CU(c, cudaStreamWaitEvent(c->copy_in, c->ev[2 * chunks], 0));
+  CU(c, cudaStreamWaitEvent(c->copy_out, c->ev[2 * chunks], 0));
+  Plonky2 lay{d_dig, d_cap, L};
+  for (size_t i = 0; i < chunks; i++) {
+    CU(c, cudaMemcpyAsync(d_leaves + i * chunk * w, leaves + i * chunk * w, chunk * w * 8, cudaMemcpyHostToDevice, c->copy_in));
+    CU(c, cudaEventRecord(c->ev[2 * i], c->copy_in));
+    CU(c, cudaStreamWaitEvent(c->stream, c->ev[2 * i], 0));
+    TAG(c, "k_leaves", w <= 4 ? 0 : chunk * ((w + 7) / 8));
+    k_leaves<Plonky2><<<grid_for(c, chunk), BLOCK, 0, c->stream>>>(lay, d_leaves + i * chunk * w, w, i * chunk, chunk);
+    CHECK_LAUNCH(c);
+    for (int l = 1; l <= cb; l++) {
+      const size_t cnt = chunk >> l;
+      if (int rc = launch_level(c, lay, l, i * cnt, cnt)) return rc;
+    }
+    CU(c, cudaEventRecord(c->ev[2 * i + 1], c->stream));
+    CU(c, cudaStreamWaitEvent(c->copy_out, c->ev[2 * i + 1], 0));
+    if (cb >= 1) {
+      const size_t start = plonky2_index(L, 0, i * chunk), len = 2 * chunk - 2;   // the chunk's subtree is contiguous
+      CU(c, cudaMemcpyAsync(digests_out + 4 * start, d_dig + 4 * start, len * 32, cudaMemcpyDeviceToHost, c->copy_out));
+    }
+  }
+  if (cb < L)
+    if (int rc = run_levels(c, lay, cb + 1, L, n >> (cb + 1))) return rc;
+  // digests of levels cb .. L-1 (the chunk roots and everything above them, below the cap): sibling pairs are adjacent
+  for (int l = cb; l < L; l++)
+    for (size_t k = 0; k < (n >> l); k += 2) {
+      const size_t pos = plonky2_index(L, l, k);
+      D2H(c, digests_out + 4 * pos, d_dig + 4 * pos, 64);
+    }
   D2H(c, cap_out, d_cap, n_cap * 32);
+  CU(c, cudaStreamSynchronize(c->copy_out));
   FINISH(c);
   return PMT_OK;
 }

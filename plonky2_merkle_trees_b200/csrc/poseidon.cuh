@@ -87,6 +87,42 @@ __device__ __forceinline__ void mds_layer_limb3(uint64_t (&s)[WIDTH], const uint
   }
 }
 
+// fp64 form of the same layer.  A DFMA is a multiply-accumulate in ONE fma-pipe slot (the accumulate form of
+// IMAD.WIDE.U32 takes two), and integers below 2^52 are exact in a double: the 32-bit halves are converted with the
+// 2^52 magic-number trick (pair the word with 0x43300000, subtract 2^52), the 12-term column sums stay below 2^42, and
+// adding 2^52 back leaves the integer in the mantissa.  add_d = constants as (lo, hi) doubles.
+// rows_4_only (warp-uniform): compute output lanes 0..3 only -- the last layer of a permutation whose caller keeps just
+// the digest (two_to_one, last sponge block); lanes 4..11 are left undefined.
+__device__ __forceinline__ void mds_layer_dfma(uint64_t (&s)[WIDTH], const double* __restrict__ add_d,
+                                               bool rows_4_only = false) {
+  const double MAGIC = 4503599627370496.0;  // 2^52
+  double dlo[WIDTH], dhi[WIDTH], coef[WIDTH];
+#pragma unroll
+  for (int i = 0; i < WIDTH; i++) {
+    dlo[i] = __hiloint2double(0x43300000, (int)gl::lo32(s[i])) - MAGIC;
+    dhi[i] = __hiloint2double(0x43300000, (int)gl::hi32(s[i])) - MAGIC;
+    coef[i] = PMT_MDS_CIRC_D[i];
+  }
+  const double coef00 = PMT_MDS_CIRC_D[12];
+  uint64_t out[WIDTH];
+#pragma unroll
+  for (int r = 0; r < WIDTH; r++) {
+    if (r == 4 && rows_4_only) break;
+    double L = add_d[2 * r], H = add_d[2 * r + 1];
+#pragma unroll
+    for (int i = 0; i < WIDTH; i++) {
+      const double c = (r == 0 && i == 0) ? coef00 : coef[i];
+      L = fma(dlo[(i + r) % WIDTH], c, L);
+      H = fma(dhi[(i + r) % WIDTH], c, H);
+    }
+    const uint64_t li = (uint64_t)__double_as_longlong(L + MAGIC) & 0x000FFFFFFFFFFFFFull;
+    const uint64_t hi = (uint64_t)__double_as_longlong(H + MAGIC) & 0x000FFFFFFFFFFFFFull;
+    out[r] = gl::combine_halves(li, hi);
+  }
+#pragma unroll
+  for (int r = 0; r < WIDTH; r++) s[r] = out[r];
+}
+
 // Specification form: 30 x (add constants, x^7 on all lanes / lane 0, MDS).  Output lanes are NOT canonicalised.
 // One rolled loop over the rounds: the body (12 s-boxes + 1 s-box + one MDS layer, ~1.2k SASS instructions = 19 KB)
 // stays inside the 32 KB L1.5 instruction cache; a fully unrolled permutation (~290 KB) would be fetch-bound.
@@ -148,17 +184,44 @@ __device__ __forceinline__ uint64_t dot12_limbs(const uint64_t (&s)[WIDTH], cons
   return dot12_limbs(s[0], s[1], s[2], s[3], s[4], s[5], s[6], s[7], s[8], s[9], s[10], s[11], kl);
 }
 
-template <bool SBOX_ALU = false, bool PART_ALU = false, bool MDS_LIMB = false>
+// x^7 on four lanes as ONE shared routine (3 calls per full round): the unrolled 12-lane S-box layer is 12 KB of SASS,
+// this is 4 KB, which keeps the hot loops inside the instruction cache.  SBOX_CALL selects it.
+template <bool ALU>
+__device__ __noinline__ void pow7_x4(uint64_t& a, uint64_t& b, uint64_t& c, uint64_t& d) {
+  a = gl::pow7<ALU>(a); b = gl::pow7<ALU>(b); c = gl::pow7<ALU>(c); d = gl::pow7<ALU>(d);
+}
+
+// MDS_MODE: 0 = 64-bit column sums (IMAD.WIDE), 1 = 22/21/21-bit limbs (32-bit IMAD), 2 = fp64 column sums (DFMA)
+// CAP_ZERO: the caller guarantees lanes 8..11 are zero on entry (two_to_one): their first S-box is a table lookup.
+// OUT4: the caller only reads lanes 0..3 afterwards: the last MDS layer computes 4 rows (MDS_MODE 2 only).
+template <bool SBOX_ALU = false, bool PART_ALU = false, int MDS_MODE = 0, bool CAP_ZERO = false, bool OUT4 = false,
+          bool SBOX_CALL = false>
 __device__ __forceinline__ void permute_fast(uint64_t (&s)[WIDTH]) {
 #pragma unroll
-  for (int i = 0; i < WIDTH; i++) s[i] = gl::add_canonical(s[i], PMT_RC[i]);
+  for (int i = 0; i < (CAP_ZERO ? 8 : WIDTH); i++) s[i] = gl::add_canonical(s[i], PMT_RC[i]);
 #pragma unroll 1
   for (int half = 0; half < 2; half++) {
 #pragma unroll 1
     for (int r = 0; r < PMT_FULL_HALF; r++) {
+      if (SBOX_CALL) {
+        pow7_x4<SBOX_ALU>(s[0], s[1], s[2], s[3]);
+        pow7_x4<SBOX_ALU>(s[4], s[5], s[6], s[7]);
+      } else {
 #pragma unroll
-      for (int i = 0; i < WIDTH; i++) s[i] = gl::pow7<SBOX_ALU>(s[i]);
-      if (MDS_LIMB) mds_layer_limb3(s, &PMT_RC_AFTER_FULL_L[3 * WIDTH * (PMT_FULL_HALF * half + r)]);
+        for (int i = 0; i < 8; i++) s[i] = gl::pow7<SBOX_ALU>(s[i]);
+      }
+      if (SBOX_CALL && !CAP_ZERO) {
+        pow7_x4<SBOX_ALU>(s[8], s[9], s[10], s[11]);
+      } else if (CAP_ZERO && half == 0 && r == 0) {
+#pragma unroll
+        for (int i = 8; i < WIDTH; i++) s[i] = PMT_SBOX_RC_CAP[i - 8];
+      } else {
+#pragma unroll
+        for (int i = 8; i < WIDTH; i++) s[i] = gl::pow7<SBOX_ALU>(s[i]);
+      }
+      if (MDS_MODE == 1) mds_layer_limb3(s, &PMT_RC_AFTER_FULL_L[3 * WIDTH * (PMT_FULL_HALF * half + r)]);
+      else if (MDS_MODE == 2) mds_layer_dfma(s, &PMT_RC_AFTER_FULL_D[2 * WIDTH * (PMT_FULL_HALF * half + r)],
+                                             OUT4 && half == 1 && r == PMT_FULL_HALF - 1);
       else mds_layer(s, &PMT_RC_AFTER_FULL[WIDTH * (PMT_FULL_HALF * half + r)]);
     }
     if (half == 0) {
@@ -185,6 +248,41 @@ __device__ __forceinline__ void permute_fast(uint64_t (&s)[WIDTH]) {
       for (int i = 0; i < WIDTH; i++) s[i] = gl::add_canonical(s[i], PMT_RC[WIDTH * (PMT_FULL_HALF + PMT_PARTIAL) + i]);
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Cooperative form for the latency-bound levels: 16 lanes share ONE state (lane g < 12 holds element g, lanes 12..15
+// idle).  A lone warp needs ~58 us for a thread-per-state permutation (25 k dependent-ish instructions); here the 12
+// S-boxes of a round run side by side and the MDS row of every lane is 11 pairs of warp shuffles + 24 IMAD.WIDE, so a
+// permutation is ~3.8 k instructions per warp and ~5 us.  Specification form (30 x constants, S-box, MDS): in the
+// partial rounds every lane computes the S-box (SIMT) and only lane 0 keeps it.
+// rc: the 372-entry table PMT_RC staged in SHARED memory (lane-indexed reads from constant memory would serialise).
+// All 32 lanes of the warp must call this together.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t permute_coop(uint64_t v, const uint64_t* __restrict__ rc, unsigned g,
+                                                 unsigned group_base_lane) {
+  constexpr uint32_t CIRC[WIDTH] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+  const unsigned gg = g < WIDTH ? g : 0;
+  const uint32_t c0 = g == 0 ? 25u : 17u;  // CIRC[0] + DIAG[0] on lane 0
+  v = gl::add_canonical(v, rc[gg]);
+#pragma unroll 1
+  for (int r = 0; r < PMT_ROUNDS; r++) {
+    const bool full = r < PMT_FULL_HALF || r >= PMT_FULL_HALF + PMT_PARTIAL;
+    const uint64_t p = gl::pow7<true>(v);
+    v = (full || g == 0) ? p : v;
+    const uint32_t lo = gl::lo32(v), hi = gl::hi32(v);
+    uint64_t L = gl::mad_wide(lo, c0, rc[WIDTH * (r + 1) + gg]);   // constants < 2^64 - 2^48, sums < 2^42: no overflow
+    uint64_t H = (uint64_t)hi * c0;
+#pragma unroll
+    for (int i = 1; i < WIDTH; i++) {
+      const unsigned idx = gg + i;
+      const unsigned src = group_base_lane + (idx >= WIDTH ? idx - WIDTH : idx);
+      L = gl::mad_wide(__shfl_sync(0xffffffffu, lo, src), CIRC[i], L);
+      H = gl::mad_wide(__shfl_sync(0xffffffffu, hi, src), CIRC[i], H);
+    }
+    v = gl::combine_halves(L, H);
+  }
+  return v;
 }
 
 }  // namespace poseidon

@@ -198,6 +198,26 @@ def test_merkle_tree_host_buffer_abi(ctx, oracle):
     assert np.array_equal(dg, odg) and np.array_equal(cap, ocap)
 
 
+@pytest.mark.parametrize("lg,w,h", [(18, 4, 0), (18, 4, 3), (16, 135, 4), (19, 5, 17)])
+def test_merkle_tree_host_buffer_pipelined_path(ctx, api, oracle, lg, w, h):
+    """large host-buffer builds take the chunked H2D / hash / D2H pipeline: must equal the one-shot device build + oracle"""
+    from plonky2_merkle_trees_b200._lib import ptr
+    n = 1 << lg
+    rows = splitmix_felts(lg + w + h, n * w).reshape(n, w)
+    ncap = 1 << h
+    dg = np.zeros((2 * (n - ncap), 4), np.uint64); cap = np.zeros((ncap, 4), np.uint64)
+    ctx.call("pmt_merkle_tree_build", ptr(rows), n, w, h, ptr(dg), ptr(cap))
+    t = api.mt.MerkleTree.new(rows, h)
+    assert np.array_equal(dg, t.digests) and np.array_equal(cap, t.cap)
+    if lg <= 18:
+        odg, ocap = oracle.merkle_tree_new(rows, h, threads=oracle.max_threads(), fast=True)
+        assert np.array_equal(dg, odg) and np.array_equal(cap, ocap)
+    # a second call reuses the arenas and streams
+    dg2 = np.zeros_like(dg); cap2 = np.zeros_like(cap)
+    ctx.call("pmt_merkle_tree_build", ptr(rows), n, w, h, ptr(dg2), ptr(cap2))
+    assert np.array_equal(dg, dg2) and np.array_equal(cap, cap2)
+
+
 def test_full_size_properties_2p20(api, oracle):
     """BASELINE C2 (2^20 x 4, cap 0) at full size: structure checks that do not need a full CPU rebuild."""
     n, w = 1 << 20, 4

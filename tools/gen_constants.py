@@ -281,6 +281,15 @@ def emit(path, guard, rc, fp, cuda):
         for x in nxt:
             nl += [x & 0x3FFFFF, (x >> 22) & 0x1FFFFF, x >> 43]
         out.append("static __device__ __constant__ uint32_t PMT_RC_AFTER_FULL_L[%d] = {%s};" % (len(nl), ", ".join(map(str, nl))))
+        out.append("// two_to_one starts from a zero capacity: after the first constant layer lanes 8..11 hold RC[8..11], so their first")
+        out.append("// S-box output is a constant: (RC[i])^7")
+        out.append(_fmt_u64_table("PMT_SBOX_RC_CAP", [pow(rc[i], 7, P) for i in range(8, 12)]))
+        out.append("// the same constants as exact doubles (low 32 bits, high 32 bits) for the DFMA-form MDS layer: [round][lane][lo, hi]")
+        nd = []
+        for x in nxt:
+            nd += ["%d.0" % (x & 0xFFFFFFFF), "%d.0" % (x >> 32)]
+        out.append("static __device__ __constant__ double PMT_RC_AFTER_FULL_D[%d] = {%s};" % (len(nd), ", ".join(nd)))
+        out.append("static __device__ __constant__ double PMT_MDS_CIRC_D[13] = {%s};" % ", ".join("%d.0" % x for x in MDS_CIRC + [MDS_CIRC[0] + MDS_DIAG[0]]))
         def limbs(x):
             return [x & 0x3FFFFF, (x >> 22) & 0x3FFFFF, x >> 44]
         out.append("// 64-bit constants of the dense/sparse partial-round matrices split into 22/22/20-bit limbs: a 32-bit state half")

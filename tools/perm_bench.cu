@@ -97,8 +97,11 @@ __global__ void __launch_bounds__(256) k_pipe(uint64_t* out, uint32_t a, uint32_
 // ---------------------------------------------------------------------------------------------------------------
 // permutation throughput: each thread runs `chain` dependent permutations on its own state
 // ---------------------------------------------------------------------------------------------------------------
+#ifndef MINB
+#define MINB 1
+#endif
 template <int VARIANT>
-__global__ void __launch_bounds__(128) k_perm(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, int chain) {
+__global__ void __launch_bounds__(128, MINB) k_perm(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, int chain) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint64_t s[12];
 #pragma unroll
@@ -109,8 +112,12 @@ __global__ void __launch_bounds__(128) k_perm(const uint64_t* __restrict__ in, u
     if (VARIANT == 2) poseidon::permute_fast<true, false>(s);
     if (VARIANT == 3) poseidon::permute_fast<true, true>(s);
     if (VARIANT == 4) poseidon::permute_naive<true>(s);
-    if (VARIANT == 5) poseidon::permute_fast<true, true, true>(s);
-    if (VARIANT == 6) poseidon::permute_fast<false, false, true>(s);
+    if (VARIANT == 5) poseidon::permute_fast<true, true, 1>(s);
+    if (VARIANT == 6) poseidon::permute_fast<false, false, 1>(s);
+    if (VARIANT == 7) poseidon::permute_fast<false, false, 2>(s);
+    if (VARIANT == 8) poseidon::permute_fast<true, true, 2>(s);
+    if (VARIANT == 10) poseidon::permute_fast<true, true, 2, false, false, true>(s);
+    if (VARIANT == 9) { s[8] = s[9] = s[10] = s[11] = 0; poseidon::permute_fast<true, true, 2, true, true>(s); }
   }
 #pragma unroll
   for (int i = 0; i < 12; i++) out[t * 12 + i] = gl::canonical(s[i]);
@@ -201,6 +208,10 @@ int main(int argc, char** argv) {
     for (int bps : {2, 4, 8}) if (!only_bps || bps == only_bps) run_perm<3>("fast_allalu", sms, bps, 16, true);
     for (int bps : {2, 4, 8}) if (!only_bps || bps == only_bps) run_perm<5>("fast_allalu_limbmds", sms, bps, 16, true);
     for (int bps : {2, 4, 8}) if (!only_bps || bps == only_bps) run_perm<6>("fast_limbmds", sms, bps, 16, true);
+    for (int bps : {2, 4, 8}) if (!only_bps || bps == only_bps) run_perm<7>("fast_dfmamds", sms, bps, 16, true);
+    for (int bps : {2, 4, 8}) if (!only_bps || bps == only_bps) run_perm<8>("fast_allalu_dfmamds", sms, bps, 16, true);
+    for (int bps : {2, 4, 8}) if (!only_bps || bps == only_bps) run_perm<10>("fast_allalu_dfmamds_sboxcall", sms, bps, 16, true);
+    for (int bps : {2, 4, 8}) if (!only_bps || bps == only_bps) run_perm<9>("compress_allalu_dfmamds", sms, bps, 16, false);
   }
   return 0;
 }
