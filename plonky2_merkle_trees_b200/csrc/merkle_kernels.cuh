@@ -207,16 +207,20 @@ __global__ void __launch_bounds__(COOP_BLOCK) k_level_coop(Layout lay, int l, si
   }
 }
 
-// fused upper levels in ONE block of 1024 threads (64 groups): levels l0 .. l1, level l has count0 >> (l - l0) nodes
+// fused upper levels in ONE block of 256 threads (16 groups): levels l0 .. l1, level l has count0 >> (l - l0) nodes.
+// Warps whose two groups both have no node skip the permutation (shuffles never cross a warp).
 template <class Layout>
-__global__ void __launch_bounds__(1024) k_top_coop(Layout lay, int l0, int l1, size_t count0) {
+__global__ void __launch_bounds__(COOP_BLOCK) k_top_coop(Layout lay, int l0, int l1, size_t count0) {
   __shared__ uint64_t rc_smem[WIDTH * (PMT_ROUNDS + 1)];
   coop_stage_constants(rc_smem);
   const unsigned g = threadIdx.x & 15, base_lane = threadIdx.x & 16;
   const size_t group = threadIdx.x >> 4, groups = blockDim.x >> 4;
   size_t count = count0;
   for (int l = l0; l <= l1; l++, count >>= 1) {
-    for (size_t base = 0; base < count; base += groups) coop_node(lay, l, base + group, base + group < count, rc_smem, g, base_lane);
+    for (size_t base = 0; base < count; base += groups) {
+      const size_t first_of_warp = base + (group & ~(size_t)1);
+      if (first_of_warp < count) coop_node(lay, l, base + group, base + group < count, rc_smem, g, base_lane);
+    }
     __threadfence_block();
     __syncthreads();
   }

@@ -118,8 +118,11 @@ int arena_get(pmt_ctx* c, int slot, size_t bytes, void** out) {
 
 // One tree level of `count` nodes starting at node k0.  Big levels: one thread per node.  Levels that cannot fill the
 // GPU that way (<= COOP_MAX nodes) are latency-bound: they run the cooperative 16-lanes-per-permutation kernel.
-constexpr size_t COOP_MAX = (size_t)1 << 15;
-constexpr size_t TOP_FUSE = 64;   // levels with <= 64 nodes are fused into one block (k_top_coop)
+// Measured on B200 (tools/perm_bench.cu lat): a lone warp needs 38 us per thread-per-state permutation but 6.6 us per
+// cooperative one; per permutation the cooperative form issues 2.4x more instructions, so it only wins while the level
+// is latency-bound: <= 2^13 nodes.
+constexpr size_t COOP_MAX = (size_t)1 << 13;
+constexpr size_t TOP_FUSE = 16;   // levels with <= 16 nodes are fused into one block (k_top_coop)
 
 template <class Layout>
 int launch_level(pmt_ctx* c, const Layout& lay, int l, size_t k0, size_t count) {
@@ -147,7 +150,7 @@ int run_levels(pmt_ctx* c, const Layout& lay, int l0, int top, size_t count) {
     if (int rc = launch_level(c, lay, l, 0, count)) return rc;
   if (l <= top) {
     TAG(c, "k_top_coop", 2 * count - 1);
-    k_top_coop<Layout><<<1, 1024, 0, c->stream>>>(lay, l, top, count);
+    k_top_coop<Layout><<<1, 256, 0, c->stream>>>(lay, l, top, count);
     CHECK_LAUNCH(c);
   }
   return PMT_OK;

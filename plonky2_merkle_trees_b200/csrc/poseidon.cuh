@@ -93,14 +93,20 @@ __device__ __forceinline__ void mds_layer_limb3(uint64_t (&s)[WIDTH], const uint
 // adding 2^52 back leaves the integer in the mantissa.  add_d = constants as (lo, hi) doubles.
 // rows_4_only (warp-uniform): compute output lanes 0..3 only -- the last layer of a permutation whose caller keeps just
 // the digest (two_to_one, last sponge block); lanes 4..11 are left undefined.
+template <bool CVT_I2F = false>
 __device__ __forceinline__ void mds_layer_dfma(uint64_t (&s)[WIDTH], const double* __restrict__ add_d,
                                                bool rows_4_only = false) {
   const double MAGIC = 4503599627370496.0;  // 2^52
   double dlo[WIDTH], dhi[WIDTH], coef[WIDTH];
 #pragma unroll
   for (int i = 0; i < WIDTH; i++) {
-    dlo[i] = __hiloint2double(0x43300000, (int)gl::lo32(s[i])) - MAGIC;
-    dhi[i] = __hiloint2double(0x43300000, (int)gl::hi32(s[i])) - MAGIC;
+    if (CVT_I2F) {   // I2F.F64.U32 runs on the (otherwise idle) conversion pipe instead of MOV + DADD on the fma pipe
+      dlo[i] = (double)gl::lo32(s[i]);
+      dhi[i] = (double)gl::hi32(s[i]);
+    } else {
+      dlo[i] = __hiloint2double(0x43300000, (int)gl::lo32(s[i])) - MAGIC;
+      dhi[i] = __hiloint2double(0x43300000, (int)gl::hi32(s[i])) - MAGIC;
+    }
     coef[i] = PMT_MDS_CIRC_D[i];
   }
   const double coef00 = PMT_MDS_CIRC_D[12];
@@ -153,8 +159,10 @@ __device__ __forceinline__ uint64_t dot_limbs(const uint64_t (&x)[N], const uint
   for (int t = 0; t < N; t++) {
     const uint32_t a0 = gl::lo32(x[t]), a1 = gl::hi32(x[t]);
     const uint32_t b0 = kl[3 * t], b1 = kl[3 * t + 1], b2 = kl[3 * t + 2];
-    t00 += (uint64_t)a0 * b0; t01 += (uint64_t)a0 * b1; t02 += (uint64_t)a0 * b2;
-    t10 += (uint64_t)a1 * b0; t11 += (uint64_t)a1 * b1; t12 += (uint64_t)a1 * b2;
+    // gl::mad_wide (the mad.lo.cc / madc.hi spelling) keeps these as bare chained IMAD.WIDE.U32; the plain C form made
+    // ptxas add one junk VIADD (adding a zero uniform register) per product, all on the bottleneck fma pipe
+    t00 = gl::mad_wide(a0, b0, t00); t01 = gl::mad_wide(a0, b1, t01); t02 = gl::mad_wide(a0, b2, t02);
+    t10 = gl::mad_wide(a1, b0, t10); t11 = gl::mad_wide(a1, b1, t11); t12 = gl::mad_wide(a1, b2, t12);
   }
   // V = G0 + 2^32 G1,  G0 = t00 + 2^22 t01 + 2^44 t02 (< 2^103), G1 likewise.
   // 2^32 G1 = 2^32 g_lo + 2^96 g_hi = 2^32 g_lo - g_hi (mod p); adding 2^40 p keeps the total non-negative.
@@ -191,7 +199,8 @@ __device__ __noinline__ void pow7_x4(uint64_t& a, uint64_t& b, uint64_t& c, uint
   a = gl::pow7<ALU>(a); b = gl::pow7<ALU>(b); c = gl::pow7<ALU>(c); d = gl::pow7<ALU>(d);
 }
 
-// MDS_MODE: 0 = 64-bit column sums (IMAD.WIDE), 1 = 22/21/21-bit limbs (32-bit IMAD), 2 = fp64 column sums (DFMA)
+// MDS_MODE: 0 = 64-bit column sums (IMAD.WIDE), 1 = 22/21/21-bit limbs (32-bit IMAD), 2 = fp64 column sums (DFMA),
+//           3 = fp64 column sums with I2F conversions
 // CAP_ZERO: the caller guarantees lanes 8..11 are zero on entry (two_to_one): their first S-box is a table lookup.
 // OUT4: the caller only reads lanes 0..3 afterwards: the last MDS layer computes 4 rows (MDS_MODE 2 only).
 template <bool SBOX_ALU = false, bool PART_ALU = false, int MDS_MODE = 0, bool CAP_ZERO = false, bool OUT4 = false,
@@ -220,8 +229,10 @@ __device__ __forceinline__ void permute_fast(uint64_t (&s)[WIDTH]) {
         for (int i = 8; i < WIDTH; i++) s[i] = gl::pow7<SBOX_ALU>(s[i]);
       }
       if (MDS_MODE == 1) mds_layer_limb3(s, &PMT_RC_AFTER_FULL_L[3 * WIDTH * (PMT_FULL_HALF * half + r)]);
-      else if (MDS_MODE == 2) mds_layer_dfma(s, &PMT_RC_AFTER_FULL_D[2 * WIDTH * (PMT_FULL_HALF * half + r)],
-                                             OUT4 && half == 1 && r == PMT_FULL_HALF - 1);
+      else if (MDS_MODE == 2) mds_layer_dfma<false>(s, &PMT_RC_AFTER_FULL_D[2 * WIDTH * (PMT_FULL_HALF * half + r)],
+                                                    OUT4 && half == 1 && r == PMT_FULL_HALF - 1);
+      else if (MDS_MODE == 3) mds_layer_dfma<true>(s, &PMT_RC_AFTER_FULL_D[2 * WIDTH * (PMT_FULL_HALF * half + r)],
+                                                   OUT4 && half == 1 && r == PMT_FULL_HALF - 1);
       else mds_layer(s, &PMT_RC_AFTER_FULL[WIDTH * (PMT_FULL_HALF * half + r)]);
     }
     if (half == 0) {

@@ -117,10 +117,24 @@ __global__ void __launch_bounds__(128, MINB) k_perm(const uint64_t* __restrict__
     if (VARIANT == 7) poseidon::permute_fast<false, false, 2>(s);
     if (VARIANT == 8) poseidon::permute_fast<true, true, 2>(s);
     if (VARIANT == 10) poseidon::permute_fast<true, true, 2, false, false, true>(s);
+    if (VARIANT == 11) poseidon::permute_fast<true, true, 3>(s);
+    if (VARIANT == 12) poseidon::permute_fast<false, false, 3>(s);
     if (VARIANT == 9) { s[8] = s[9] = s[10] = s[11] = 0; poseidon::permute_fast<true, true, 2, true, true>(s); }
   }
 #pragma unroll
   for (int i = 0; i < 12; i++) out[t * 12 + i] = gl::canonical(s[i]);
+}
+
+// single-warp latency of the cooperative (16 lanes per state) permutation
+__global__ void __launch_bounds__(256) k_perm_coop(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, int chain) {
+  __shared__ uint64_t rc_smem[12 * 31];
+  for (int i = threadIdx.x; i < 12 * 31; i += blockDim.x) rc_smem[i] = PMT_RC[i];
+  __syncthreads();
+  const unsigned g = threadIdx.x & 15, base_lane = threadIdx.x & 16;
+  const size_t grp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+  uint64_t v = g < 12 ? in[grp * 12 + g] : 0;
+  for (int c = 0; c < chain; c++) v = poseidon::permute_coop(v, rc_smem, g, base_lane);
+  if (g < 12) out[grp * 12 + g] = gl::canonical(v);
 }
 
 static float time_ms(cudaEvent_t a, cudaEvent_t b) { float ms; CK(cudaEventElapsedTime(&ms, a, b)); return ms; }
@@ -174,6 +188,27 @@ static void run_perm(const char* name, int sms, int blocks_per_sm, int chain, bo
   CK(cudaFree(din)); CK(cudaFree(dout));
 }
 
+static void run_latency(int sms) {
+  uint64_t *din, *dout; CK(cudaMalloc(&din, 1 << 20)); CK(cudaMalloc(&dout, 1 << 20));
+  std::vector<uint64_t> h(1 << 17);
+  for (size_t i = 0; i < h.size(); i++) h[i] = i;
+  CK(cudaMemcpy(din, h.data(), 1 << 20, cudaMemcpyHostToDevice));
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  for (int chain : {1, 17}) {
+    for (int rep = 0; rep < 3; rep++) {
+      CK(cudaEventRecord(e0)); k_perm_coop<<<1, 32>>>(din, dout, chain); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+      float a = time_ms(e0, e1);
+      CK(cudaEventRecord(e0)); k_perm<8><<<1, 32>>>(din, dout, chain); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+      float b = time_ms(e0, e1);
+      CK(cudaEventRecord(e0)); k_perm_coop<<<sms, 256>>>(din, dout, chain); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+      float c2 = time_ms(e0, e1);
+      if (rep == 2) printf("{\"bench\": \"latency\", \"chain\": %d, \"coop_1warp_us\": %.2f, \"thread_1warp_us\": %.2f, \"coop_148x256_us\": %.2f}\n", chain, a * 1e3, b * 1e3, c2 * 1e3);
+    }
+  }
+  uint64_t r[4]; CK(cudaMemcpy(r, dout, 32, cudaMemcpyDeviceToHost));
+  CK(cudaFree(din)); CK(cudaFree(dout));
+}
+
 int main(int argc, char** argv) {
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
   int sms = prop.multiProcessorCount;
@@ -200,6 +235,7 @@ int main(int argc, char** argv) {
     run_pipe<15>("dfma+imad_wide_acc (1:1)", 2, sms);
     run_pipe<16>("dfma+imad_wide_acc+iadd3 (1:1:1)", 3, sms);
   }
+  if (argc > 1 && strstr(argv[1], "lat")) run_latency(sms);
   if (perms) {
     int only_bps = argc > 2 ? atoi(argv[2]) : 0;
     for (int bps : {1, 2, 4, 8}) if (!only_bps || bps == only_bps) run_perm<0>("naive", sms, bps, 16, true);
@@ -210,6 +246,8 @@ int main(int argc, char** argv) {
     for (int bps : {2, 4, 8}) if (!only_bps || bps == only_bps) run_perm<6>("fast_limbmds", sms, bps, 16, true);
     for (int bps : {2, 4, 8}) if (!only_bps || bps == only_bps) run_perm<7>("fast_dfmamds", sms, bps, 16, true);
     for (int bps : {2, 4, 8}) if (!only_bps || bps == only_bps) run_perm<8>("fast_allalu_dfmamds", sms, bps, 16, true);
+    for (int bps : {2, 4, 8}) if (!only_bps || bps == only_bps) run_perm<11>("fast_allalu_dfmamds_i2f", sms, bps, 16, true);
+    for (int bps : {2, 4, 8}) if (!only_bps || bps == only_bps) run_perm<12>("fast_dfmamds_i2f", sms, bps, 16, true);
     for (int bps : {2, 4, 8}) if (!only_bps || bps == only_bps) run_perm<10>("fast_allalu_dfmamds_sboxcall", sms, bps, 16, true);
     for (int bps : {2, 4, 8}) if (!only_bps || bps == only_bps) run_perm<9>("compress_allalu_dfmamds", sms, bps, 16, false);
   }
