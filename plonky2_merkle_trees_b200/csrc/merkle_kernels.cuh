@@ -17,14 +17,61 @@ namespace pmt {
 
 using poseidon::WIDTH;
 
-// the production permutation (see DESIGN.md "Permutation variants" for the measurements behind this choice)
-__device__ __forceinline__ void permute(uint64_t (&s)[WIDTH]) { poseidon::permute_fast<true, true, 2>(s); }
-// two_to_one: zero capacity lanes on entry, only the digest lanes are read afterwards
-#ifndef PMT_COMPRESS_SPECIALISED
-#define PMT_COMPRESS_SPECIALISED 0  // A/B on B200: the specialised body is 2.6 % slower inside k_level (larger loop body)
+// the production permutation (see DESIGN.md "Permutation variants" for the measurements behind this choice).
+// PMT_PERM selects the form for A/B runs (tools/ab_level.cu): 0 = permute_fast (sparse partial rounds), 1 = permute_fused,
+// 2 = permute_rounds (30 x S-box + DFMA MDS), 3 = permute_paired (partial rounds in pairs; production).
+#ifndef PMT_PERM
+#define PMT_PERM 3
 #endif
+#ifndef PMT_SBOX_FMA_MASK
+#define PMT_SBOX_FMA_MASK 0
+#endif
+#ifndef PMT_PART_FMA_MASK
+#define PMT_PART_FMA_MASK 0
+#endif
+#ifndef PMT_MULADD_ALU
+#define PMT_MULADD_ALU 1
+#endif
+#ifndef PMT_DOT_ALU
+#define PMT_DOT_ALU 0
+#endif
+#ifndef PMT_CVT_I2F
+#define PMT_CVT_I2F 1   // I2F.F64.U32 (conversion pipe) instead of the 2^52 magic-number subtraction (fma pipe)
+#endif
+#ifndef PMT_COMBINE_ALU
+#define PMT_COMBINE_ALU 1
+#endif
+#ifndef PMT_COLUMN
+#define PMT_COLUMN 0
+#endif
+#ifndef PMT_PIPE
+#define PMT_PIPE 0
+#endif
+#ifndef PMT_PPIPE
+#define PMT_PPIPE 0
+#endif
+#ifndef PMT_COMPRESS_SPECIALISED
+#define PMT_COMPRESS_SPECIALISED 0
+#endif
+template <bool CAP_ZERO, bool OUT4>
+__device__ __forceinline__ void permute_impl(uint64_t (&s)[WIDTH]) {
+#if PMT_PERM == 0
+  poseidon::permute_fast<true, true, 2, CAP_ZERO, OUT4>(s);
+#elif PMT_PERM == 3
+  poseidon::permute_paired<PMT_SBOX_FMA_MASK, PMT_PART_FMA_MASK, PMT_COLUMN != 0, PMT_CVT_I2F != 0, PMT_COMBINE_ALU != 0, CAP_ZERO,
+                           OUT4>(s);
+#elif PMT_PERM == 2
+  poseidon::permute_rounds<PMT_SBOX_FMA_MASK, PMT_PART_FMA_MASK, PMT_COLUMN != 0, PMT_CVT_I2F != 0, PMT_COMBINE_ALU != 0, CAP_ZERO,
+                           OUT4>(s);
+#else
+  poseidon::permute_fused<PMT_SBOX_FMA_MASK, PMT_PART_FMA_MASK, PMT_MULADD_ALU != 0, PMT_DOT_ALU != 0, PMT_CVT_I2F != 0,
+                          PMT_COMBINE_ALU != 0, CAP_ZERO, OUT4, PMT_PIPE, PMT_PPIPE>(s);
+#endif
+}
+__device__ __forceinline__ void permute(uint64_t (&s)[WIDTH]) { permute_impl<false, false>(s); }
+// two_to_one: zero capacity lanes on entry, only the digest lanes are read afterwards
 __device__ __forceinline__ void permute_compress(uint64_t (&s)[WIDTH]) {
-  poseidon::permute_fast<true, true, 2, PMT_COMPRESS_SPECIALISED != 0, PMT_COMPRESS_SPECIALISED != 0>(s);
+  permute_impl<PMT_COMPRESS_SPECIALISED != 0, PMT_COMPRESS_SPECIALISED != 0>(s);
 }
 
 struct Digest { uint64_t v[4]; };
@@ -130,7 +177,13 @@ struct Mmr {
 // kernels.  Block = 128 threads: the permutation needs ~90 registers, so 5 blocks (20 warps) are resident per SM and
 // grids are sized in whole waves of 148 x 5 blocks by the host where the level is large enough.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int BLOCK = 128;
+#ifndef PMT_BLOCK
+#define PMT_BLOCK 128
+#endif
+#ifndef PMT_MINB
+#define PMT_MINB 1   // minimum resident blocks per SM asked of ptxas (register cap); tuned with tools/ab_level.cu
+#endif
+constexpr int BLOCK = PMT_BLOCK;
 
 // level 0: digest(0, k0 + i) = hash_or_noop(row i),  rows row-major count x w
 template <class Layout>
@@ -142,7 +195,7 @@ __global__ void __launch_bounds__(BLOCK) k_leaves(Layout lay, const uint64_t* __
 
 // one level: digest(l, k) = two_to_one(children) for k in [k0, k0 + count)
 template <class Layout>
-__global__ void __launch_bounds__(BLOCK) k_level(Layout lay, int l, size_t k0, size_t count) {
+__global__ void __launch_bounds__(BLOCK, PMT_MINB) k_level(Layout lay, int l, size_t k0, size_t count) {
   for (size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x; i < count; i += (size_t)gridDim.x * BLOCK) {
     const uint64_t *a, *b;
     lay.children(l, k0 + i, a, b);

@@ -91,17 +91,23 @@ int log2_strict(size_t n) {  // plonky2_util::log2_strict: -1 unless n is a powe
   return l;
 }
 
-// grid for `count` independent permutations: whole waves of (SMs x 5 resident 128-thread blocks) when the level is
-// large, otherwise just enough blocks
+// grid for `count` independent permutations: ONE node per thread.  Measured on B200 (tools/ab_level.cu, 2^22 nodes):
+// a persistent grid of resident blocks striding over the level is 7 % slower than count / 128 short-lived blocks, because
+// blocks that start together stay in phase (all warps in the ALU-heavy S-box layer, then all in the DFMA layer), while
+// blocks retiring at different times keep the warps of an SM in different phases so the two issue pipes overlap.
 unsigned grid_for(const pmt_ctx* c, size_t count) {
-  const size_t wave = (size_t)c->sms * 5;
+  (void)c;
   size_t blocks = (count + BLOCK - 1) / BLOCK;
-  if (blocks > wave) {
-    // persistent-style: a multiple of the wave, at most 8 waves; threads stride over the rest
-    size_t waves = (blocks + wave - 1) / wave;
-    if (waves > 8) waves = 8;
-    blocks = waves * wave;
-  }
+  if (blocks > 0x7fffffffu) blocks = 0x7fffffffu;   // threads stride over the rest
+  return (unsigned)(blocks ? blocks : 1);
+}
+
+// grid for the narrow-leaf copy (w <= 4: hash_or_noop is a canonicalising copy, HBM-bound): a few waves of resident
+// blocks striding over the rows (6.5 TB/s measured, against 4.4 TB/s with one row per thread)
+unsigned grid_copy(const pmt_ctx* c, size_t count) {
+  const size_t wave = (size_t)c->sms * 8;
+  size_t blocks = (count + BLOCK - 1) / BLOCK;
+  if (blocks > 8 * wave) blocks = 8 * wave;
   return (unsigned)(blocks ? blocks : 1);
 }
 
@@ -323,7 +329,7 @@ int pmt_simple_tree_build_dev(pmt_ctx* c, const uint64_t* d_leaves, size_t n, ui
   if (!d_leaves || !d_levels || !d_root) return fail(c, PMT_E_INVALID_ARG, "simple tree: null pointer");
   LevelMajor lay{d_levels, d_root, n, lg};
   TAG(c, "k_leaves", 0);
-  k_leaves<LevelMajor><<<grid_for(c, n), BLOCK, 0, c->stream>>>(lay, d_leaves, 1, 0, n);
+  k_leaves<LevelMajor><<<grid_copy(c, n), BLOCK, 0, c->stream>>>(lay, d_leaves, 1, 0, n);
   CHECK_LAUNCH(c);
   return run_levels(c, lay, 1, lg, n / 2);
 }
@@ -372,7 +378,7 @@ int pmt_merkle_tree_build_dev(pmt_ctx* c, const uint64_t* d_leaves, size_t n, si
   const int L = lg - (int)cap_height;
   Plonky2 lay{d_digests, d_cap, L};
   TAG(c, "k_leaves", w <= 4 ? 0 : n * ((w + 7) / 8));
-  k_leaves<Plonky2><<<grid_for(c, n), BLOCK, 0, c->stream>>>(lay, d_leaves, w, 0, n);
+  k_leaves<Plonky2><<<w <= 4 ? grid_copy(c, n) : grid_for(c, n), BLOCK, 0, c->stream>>>(lay, d_leaves, w, 0, n);
   CHECK_LAUNCH(c);
   // levels 1 .. L over all subtrees at once: level l has n >> l nodes (2^h subtrees x 2^(L-l))
   if (L == 0) return PMT_OK;
@@ -431,7 +437,7 @@ int pmt_mmr_extend_dev(pmt_ctx* c, uint64_t* d_elements, size_t n0, const uint64
   if (n0 + m > ((size_t)1 << 30)) return fail(c, PMT_E_RANGE, "mmr extend: more than 2^30 leaves (get_mmr_index is i32, merkle_mountain_ranges.rs:264)");
   Mmr lay{d_elements};
   TAG(c, "k_leaves", 0);
-  k_leaves<Mmr><<<grid_for(c, m), BLOCK, 0, c->stream>>>(lay, d_new, 1, n0, m);
+  k_leaves<Mmr><<<grid_copy(c, m), BLOCK, 0, c->stream>>>(lay, d_new, 1, n0, m);
   CHECK_LAUNCH(c);
   for (int l = 1; l < 40; l++) {
     const size_t k0 = n0 >> l, k1 = (n0 + m) >> l;
@@ -623,7 +629,7 @@ int pmt_merkle_tree_build(pmt_ctx* c, const uint64_t* leaves, size_t n, size_t w
     CU(c, cudaEventRecord(c->ev[2 * i], c->copy_in));
     CU(c, cudaStreamWaitEvent(c->stream, c->ev[2 * i], 0));
     TAG(c, "k_leaves", w <= 4 ? 0 : chunk * ((w + 7) / 8));
-    k_leaves<Plonky2><<<grid_for(c, chunk), BLOCK, 0, c->stream>>>(lay, d_leaves + i * chunk * w, w, i * chunk, chunk);
+    k_leaves<Plonky2><<<w <= 4 ? grid_copy(c, chunk) : grid_for(c, chunk), BLOCK, 0, c->stream>>>(lay, d_leaves + i * chunk * w, w, i * chunk, chunk);
     CHECK_LAUNCH(c);
     for (int l = 1; l <= cb; l++) {
       const size_t cnt = chunk >> l;

@@ -262,6 +262,348 @@ __device__ __forceinline__ void permute_fast(uint64_t (&s)[WIDTH]) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Fused form (production).  ncu on the phase-structured permute_fast showed the two issue pipes taking turns instead
+// of overlapping: the S-box layer is ALU-heavy (carry chains of the reductions), the DFMA MDS layer is pure fma pipe,
+// and with 4 warps per scheduler the phases of different warps rarely complement each other (fma-heavy pipe 61-70 %
+// busy, 0.55 IPC).  Here every phase carries its own mix:
+//   * full round = 12 x { S-box of lane i ; lane i's COLUMN of the MDS matrix: 24 DFMAs into the 12 (lo, hi) row
+//     accumulators }.  The DFMAs of lane i have no consumer until the end of the round, so they fill the fma pipe
+//     while the next lanes' reductions run on the ALU pipe.  The accumulators start at constant + 2^52, so the
+//     integer result is the mantissa (no conversion back), and are recombined on the ALU pipe.
+//   * partial round: everything inline in one basic block (no call ABI moves); the 11-term dot product of the old
+//     lanes does not depend on the S-box of lane 0, so ptxas overlaps the S-box's serial chain with it; lane 0 enters
+//     the dot product with its small coefficient M00 = 25 (2 MACs instead of 6).
+// ---------------------------------------------------------------------------------------------------------------
+// Scheduling fence.  ptxas orders a basic block by critical path: left alone it runs every S-box of a round first and
+// all DFMAs afterwards (and, in the partial rounds, the S-box chain before the dot product), which recreates the
+// phases.  tie(x, after) makes x formally depend on `after` through one LOP3 with a run-time zero (x | (after & 0)), so
+// "lane i+2's S-box may not start before lane i's DFMAs" is a data dependency the scheduler has to respect, and the
+// DFMAs of lane i are left to overlap with the S-box of lane i+1.
+static __device__ __constant__ uint32_t PMT_ZERO32 = 0;   // not const: the compiler must treat it as unknown
+__device__ __forceinline__ uint64_t tie(uint64_t x, uint32_t after, uint32_t zero) {
+  uint32_t lo = gl::lo32(x);
+  asm("lop3.b32 %0, %0, %1, %2, 0xf8;" : "+r"(lo) : "r"(after), "r"(zero));   // lo | (after & zero)
+  return gl::pack(lo, gl::hi32(x));
+}
+__device__ __forceinline__ uint32_t hi_word(double d) { return (uint32_t)__double2hiint(d); }
+
+// 2^52 + l, 2^52 + h (l, h < 2^43) -> u64 congruent to l + 2^32 h, ALU pipe only.
+__device__ __forceinline__ uint64_t combine_magic_alu(double L, double H) {
+  const uint64_t lb = (uint64_t)__double_as_longlong(L), hb = (uint64_t)__double_as_longlong(H);
+  uint32_t w0 = gl::lo32(lb), w1 = gl::lo32(hb), w2 = gl::hi32(hb) & 0xFFFFFu, net;
+  const uint32_t lh = gl::hi32(lb) & 0xFFFFFu;
+  // (w2 : w1 : w0) = l + 2^32 h
+  asm("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, %1, 0;" : "+r"(w1), "+r"(w2) : "r"(lh));
+  // + w2 * (2^32 - 1) = (w2 << 32) - w2; net = carry - borrow is 0 or 1 (a borrow forces the carry, see gl::reduce128_alu)
+  asm("sub.cc.u32 %0, %0, %3;\n\tsubc.cc.u32 %1, %1, 0;\n\tsubc.u32 %2, 0, 0;" : "+r"(w0), "+r"(w1), "=r"(net) : "r"(w2));
+  asm("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, %1, 0;" : "+r"(w1), "+r"(net) : "r"(w2));
+  asm("sub.cc.u32 %0, %0, %2;\n\tsubc.u32 %1, %1, 0;" : "+r"(w0), "+r"(w1) : "r"(net));
+  w1 += net;
+  return gl::pack(w0, w1);
+}
+__device__ __forceinline__ uint64_t combine_magic_fma(double L, double H) {
+  const uint64_t li = (uint64_t)__double_as_longlong(L) & 0x000FFFFFFFFFFFFFull;
+  const uint64_t hi = (uint64_t)__double_as_longlong(H) & 0x000FFFFFFFFFFFFFull;
+  return gl::combine_halves(li, hi);
+}
+
+// x^7 with a per-multiplication choice of reduction: bit j of FMA_MASK = multiplication j (x2, x4, x3, x7) folds with
+// IMAD.WIDE (fma pipe, 6 ALU + 2 IMAD.WIDE) instead of the 13-instruction ALU-only reduction.
+template <int FMA_MASK>
+__device__ __forceinline__ uint64_t pow7_mix(uint64_t x) {
+  const uint64_t x2 = (FMA_MASK & 1) ? gl::sqr<false>(x) : gl::sqr<true>(x);
+  const uint64_t x4 = (FMA_MASK & 2) ? gl::sqr<false>(x2) : gl::sqr<true>(x2);
+  const uint64_t x3 = (FMA_MASK & 4) ? gl::mul<false>(x, x2) : gl::mul<true>(x, x2);
+  return (FMA_MASK & 8) ? gl::mul<false>(x3, x4) : gl::mul<true>(x3, x4);
+}
+
+// one full round: s[] holds the state WITH this round's constants added; add_dm = the next constants as
+// (lo + 2^52, hi + 2^52) doubles.  cap_const / out4 are warp-uniform run-time flags (no code duplication):
+// cap_const: lanes 8..11 hold RC[8..11] (first round of two_to_one), their S-box output is a table constant;
+// out4: only output lanes 0..3 are needed (last round when the caller keeps the digest).
+template <int SBOX_FMA_MASK, bool CVT_I2F, bool COMBINE_ALU, int PIPE>
+__device__ __forceinline__ void full_round_fused(uint64_t (&s)[WIDTH], const double* __restrict__ add_dm, bool cap_const,
+                                                 bool out4) {
+  const double MAGIC = 4503599627370496.0;  // 2^52
+  const uint32_t zero = PMT_ZERO32;
+  double L[WIDTH], H[WIDTH];
+#pragma unroll
+  for (int r = 0; r < WIDTH; r++) { L[r] = add_dm[2 * r]; H[r] = add_dm[2 * r + 1]; }
+#pragma unroll
+  for (int i = 0; i < WIDTH; i++) {
+    uint64_t x;
+    if (PIPE > 0 && i >= PIPE + 1) s[i] = tie(s[i], hi_word(H[WIDTH - 1]), zero);   // after lane (i - PIPE - 1)'s DFMAs
+    if (i >= 8 && cap_const) x = PMT_SBOX_RC_CAP[i - 8];
+    else x = pow7_mix<SBOX_FMA_MASK>(s[i]);
+    double dlo, dhi;
+    if (CVT_I2F) {
+      dlo = (double)gl::lo32(x); dhi = (double)gl::hi32(x);
+    } else {
+      dlo = __hiloint2double(0x43300000, (int)gl::lo32(x)) - MAGIC;
+      dhi = __hiloint2double(0x43300000, (int)gl::hi32(x)) - MAGIC;
+    }
+    if (out4) {
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        const double c = (i == 0 && r == 0) ? PMT_MDS_CIRC_D[12] : PMT_MDS_CIRC_D[(i - r + WIDTH) % WIDTH];
+        L[r] = fma(dlo, c, L[r]); H[r] = fma(dhi, c, H[r]);
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < WIDTH; r++) {
+        const double c = (i == 0 && r == 0) ? PMT_MDS_CIRC_D[12] : PMT_MDS_CIRC_D[(i - r + WIDTH) % WIDTH];
+        L[r] = fma(dlo, c, L[r]); H[r] = fma(dhi, c, H[r]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < WIDTH; r++) s[r] = COMBINE_ALU ? combine_magic_alu(L[r], H[r]) : combine_magic_fma(L[r], H[r]);
+}
+
+// The DFMA MDS layer with the 2^52 folded into the constants (add_dm) and the ALU-only recombination.
+// COLUMN = false: row by row (24 input doubles live, 2 accumulators at a time); true: lane by lane (24 accumulators).
+template <bool COLUMN, bool CVT_I2F, bool COMBINE_ALU>
+__device__ __forceinline__ void mds_layer_dfma2(uint64_t (&s)[WIDTH], const double* __restrict__ add_dm, bool out4) {
+  const double MAGIC = 4503599627370496.0;  // 2^52
+  double dlo[WIDTH], dhi[WIDTH];
+#pragma unroll
+  for (int i = 0; i < WIDTH; i++) {
+    if (CVT_I2F) { dlo[i] = (double)gl::lo32(s[i]); dhi[i] = (double)gl::hi32(s[i]); }
+    else {
+      dlo[i] = __hiloint2double(0x43300000, (int)gl::lo32(s[i])) - MAGIC;
+      dhi[i] = __hiloint2double(0x43300000, (int)gl::hi32(s[i])) - MAGIC;
+    }
+  }
+  if (!COLUMN) {
+    uint64_t out[WIDTH];
+#pragma unroll
+    for (int r = 0; r < WIDTH; r++) {
+      if (r == 4 && out4) break;
+      double L = add_dm[2 * r], H = add_dm[2 * r + 1];
+#pragma unroll
+      for (int i = 0; i < WIDTH; i++) {
+        const double c = (r == 0 && i == 0) ? PMT_MDS_CIRC_D[12] : PMT_MDS_CIRC_D[i];
+        L = fma(dlo[(i + r) % WIDTH], c, L);
+        H = fma(dhi[(i + r) % WIDTH], c, H);
+      }
+      out[r] = COMBINE_ALU ? combine_magic_alu(L, H) : combine_magic_fma(L, H);
+    }
+#pragma unroll
+    for (int r = 0; r < WIDTH; r++) s[r] = out[r];
+  } else {
+    double L[WIDTH], H[WIDTH];
+#pragma unroll
+    for (int r = 0; r < WIDTH; r++) { L[r] = add_dm[2 * r]; H[r] = add_dm[2 * r + 1]; }
+    // lane 0 (the only lane behind an S-box in a partial round) goes last
+#pragma unroll
+    for (int ii = 1; ii <= WIDTH; ii++) {
+      const int i = ii % WIDTH;
+#pragma unroll
+      for (int r = 0; r < WIDTH; r++) {
+        if (r >= 4 && out4) break;
+        const double c = (i == 0 && r == 0) ? PMT_MDS_CIRC_D[12] : PMT_MDS_CIRC_D[(i - r + WIDTH) % WIDTH];
+        L[r] = fma(dlo[i], c, L[r]); H[r] = fma(dhi[i], c, H[r]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < WIDTH; r++) s[r] = COMBINE_ALU ? combine_magic_alu(L[r], H[r]) : combine_magic_fma(L[r], H[r]);
+  }
+}
+
+// Specification form, ONE rolled loop over the 30 rounds (constants, S-box on 12 lanes / lane 0, MDS), with the DFMA
+// MDS layer.  With the MDS layer at 312 fma-pipe slots a partial round costs about what the sparse "fast" form costs
+// (1 S-box + 23 full multiplications), the dense 11 x 11 INIT layer disappears, and the whole permutation is ~21 KB of
+// code.  CAP_ZERO / OUT4 as in permute_fast.
+template <int SBOX_FMA_MASK = 0, int PART_FMA_MASK = 0, bool COLUMN = false, bool CVT_I2F = false, bool COMBINE_ALU = true,
+          bool CAP_ZERO = false, bool OUT4 = false>
+__device__ __forceinline__ void permute_rounds(uint64_t (&s)[WIDTH]) {
+#pragma unroll
+  for (int i = 0; i < (CAP_ZERO ? 8 : WIDTH); i++) s[i] = gl::add_canonical(s[i], PMT_RC[i]);
+#pragma unroll 1
+  for (int r = 0; r < PMT_ROUNDS; r++) {
+    if (r < PMT_FULL_HALF || r >= PMT_FULL_HALF + PMT_PARTIAL) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) s[i] = pow7_mix<SBOX_FMA_MASK>(s[i]);
+      if (CAP_ZERO && r == 0) {
+#pragma unroll
+        for (int i = 8; i < WIDTH; i++) s[i] = PMT_SBOX_RC_CAP[i - 8];
+      } else {
+#pragma unroll
+        for (int i = 8; i < WIDTH; i++) s[i] = pow7_mix<SBOX_FMA_MASK>(s[i]);
+      }
+    } else {
+      s[0] = pow7_mix<PART_FMA_MASK>(s[0]);
+    }
+    mds_layer_dfma2<COLUMN, CVT_I2F, COMBINE_ALU>(s, &PMT_RC_DM[2 * WIDTH * r], OUT4 && r == PMT_ROUNDS - 1);
+  }
+}
+
+// Paired form (production): full rounds as in permute_rounds; the 22 partial rounds as 11 PAIRS.  Lanes 1..11 of the
+// state between the two rounds of a pair never meet an S-box, so (tools/gen_constants.py::derive_paired)
+//     z = A s' + col0(M) x + K,   s' = [sbox(s0), s1..s11],  x = sbox(row0(M) s' + c[0]),  A = M[:,1:] M[1:,:]
+// which is 24 + 288 + 24 DFMAs per PAIR of rounds instead of 2 x 288, one conversion of the state to doubles and one
+// recombination instead of two.  A's entries are < 2^15 and its row sums < 2^17, so the fp64 sums stay exact (< 2^50).
+// The 288 DFMAs of A s' do not depend on the second S-box, whose serial chain they can overlap.
+template <int SBOX_FMA_MASK = 0, int PART_FMA_MASK = 0, bool COLUMN = false, bool CVT_I2F = false, bool COMBINE_ALU = true,
+          bool CAP_ZERO = false, bool OUT4 = false>
+__device__ __forceinline__ void permute_paired(uint64_t (&s)[WIDTH]) {
+  const double MAGIC = 4503599627370496.0;  // 2^52
+#pragma unroll
+  for (int i = 0; i < (CAP_ZERO ? 8 : WIDTH); i++) s[i] = gl::add_canonical(s[i], PMT_RC[i]);
+#pragma unroll 1
+  for (int half = 0; half < 2; half++) {
+#pragma unroll 1
+    for (int q = 0; q < PMT_FULL_HALF; q++) {
+      const int r = half ? PMT_FULL_HALF + PMT_PARTIAL + q : q;
+#pragma unroll
+      for (int i = 0; i < 8; i++) s[i] = pow7_mix<SBOX_FMA_MASK>(s[i]);
+      if (CAP_ZERO && r == 0) {
+#pragma unroll
+        for (int i = 8; i < WIDTH; i++) s[i] = PMT_SBOX_RC_CAP[i - 8];
+      } else {
+#pragma unroll
+        for (int i = 8; i < WIDTH; i++) s[i] = pow7_mix<SBOX_FMA_MASK>(s[i]);
+      }
+      mds_layer_dfma2<COLUMN, CVT_I2F, COMBINE_ALU>(s, &PMT_RC_DM[2 * WIDTH * r], OUT4 && r == PMT_ROUNDS - 1);
+    }
+    if (half == 0) {
+#pragma unroll 1
+      for (int pair = 0; pair < PMT_PARTIAL / 2; pair++) {
+        const int r = PMT_FULL_HALF + 2 * pair;
+        s[0] = pow7_mix<PART_FMA_MASK>(s[0]);
+        double dlo[WIDTH], dhi[WIDTH];
+#pragma unroll
+        for (int i = 0; i < WIDTH; i++) {
+          if (CVT_I2F) { dlo[i] = (double)gl::lo32(s[i]); dhi[i] = (double)gl::hi32(s[i]); }
+          else {
+            dlo[i] = __hiloint2double(0x43300000, (int)gl::lo32(s[i])) - MAGIC;
+            dhi[i] = __hiloint2double(0x43300000, (int)gl::hi32(s[i])) - MAGIC;
+          }
+        }
+        // y0 = row0(M) s' + c_{r+1}[0]
+        double L0 = PMT_RC_DM[2 * WIDTH * r], H0 = PMT_RC_DM[2 * WIDTH * r + 1];
+#pragma unroll
+        for (int i = 0; i < WIDTH; i++) {
+          const double c = i == 0 ? PMT_MDS_CIRC_D[12] : PMT_MDS_CIRC_D[i];
+          L0 = fma(dlo[i], c, L0); H0 = fma(dhi[i], c, H0);
+        }
+        const uint64_t y0 = COMBINE_ALU ? combine_magic_alu(L0, H0) : combine_magic_fma(L0, H0);
+        // z = A s' + K  (independent of the S-box of y0)
+        double L[WIDTH], H[WIDTH];
+        const double* __restrict__ kd = &PMT_PP_K_DM[2 * WIDTH * pair];
+#pragma unroll
+        for (int j = 0; j < WIDTH; j++) {
+          double l = kd[2 * j], h = kd[2 * j + 1];
+#pragma unroll
+          for (int i = 0; i < WIDTH; i++) {
+            const double c = PMT_PP_A_D[WIDTH * j + i];
+            l = fma(dlo[i], c, l); h = fma(dhi[i], c, h);
+          }
+          L[j] = l; H[j] = h;
+        }
+        const uint64_t x = pow7_mix<PART_FMA_MASK>(y0);
+        double xlo, xhi;
+        if (CVT_I2F) { xlo = (double)gl::lo32(x); xhi = (double)gl::hi32(x); }
+        else {
+          xlo = __hiloint2double(0x43300000, (int)gl::lo32(x)) - MAGIC;
+          xhi = __hiloint2double(0x43300000, (int)gl::hi32(x)) - MAGIC;
+        }
+#pragma unroll
+        for (int j = 0; j < WIDTH; j++) {
+          const double c = j == 0 ? PMT_MDS_CIRC_D[12] : PMT_MDS_CIRC_D[(WIDTH - j) % WIDTH];   // M[j][0]
+          L[j] = fma(xlo, c, L[j]); H[j] = fma(xhi, c, H[j]);
+          s[j] = COMBINE_ALU ? combine_magic_alu(L[j], H[j]) : combine_magic_fma(L[j], H[j]);
+        }
+      }
+    }
+  }
+}
+
+// six carry-free column sums of sum_t x[t] * K[t], K as 22/22/20-bit limbs kl[3 t + j]
+struct DotAcc { uint64_t t00, t01, t02, t10, t11, t12; };
+template <int N>
+__device__ __forceinline__ void dot_acc(DotAcc& a, const uint64_t* x, const uint32_t* __restrict__ kl) {
+#pragma unroll
+  for (int t = 0; t < N; t++) {
+    const uint32_t a0 = gl::lo32(x[t]), a1 = gl::hi32(x[t]);
+    const uint32_t b0 = kl[3 * t], b1 = kl[3 * t + 1], b2 = kl[3 * t + 2];
+    a.t00 = gl::mad_wide(a0, b0, a.t00); a.t01 = gl::mad_wide(a0, b1, a.t01); a.t02 = gl::mad_wide(a0, b2, a.t02);
+    a.t10 = gl::mad_wide(a1, b0, a.t10); a.t11 = gl::mad_wide(a1, b1, a.t11); a.t12 = gl::mad_wide(a1, b2, a.t12);
+  }
+}
+template <bool ALU>
+__device__ __forceinline__ uint64_t dot_finish(const DotAcc& a) {
+  // V = G0 + 2^32 G1,  G0 = t00 + 2^22 t01 + 2^44 t02 (< 2^103), G1 likewise;  2^32 G1 = 2^32 g_lo - g_hi (mod p)
+  gl::u128 g0 = (gl::u128)a.t00 + ((gl::u128)a.t01 << 22) + ((gl::u128)a.t02 << 44);
+  gl::u128 g1 = (gl::u128)a.t10 + ((gl::u128)a.t11 << 22) + ((gl::u128)a.t12 << 44);
+  const uint64_t g_lo = (uint64_t)g1, g_hi = (uint64_t)(g1 >> 64);
+  gl::u128 v = g0 + ((gl::u128)g_lo << 32) + (((gl::u128)gl::P << 40) - g_hi);
+  return gl::reduce128<ALU>(v);
+}
+
+// SBOX_FMA_MASK / PART_FMA_MASK: pow7_mix masks of the full / partial rounds; MULADD_ALU, DOT_ALU: reduction pipe of the
+// partial rounds' multiply-adds and dot products.  CAP_ZERO / OUT4 as in permute_fast.
+template <int SBOX_FMA_MASK = 0, int PART_FMA_MASK = 0, bool MULADD_ALU = true, bool DOT_ALU = false, bool CVT_I2F = false,
+          bool COMBINE_ALU = true, bool CAP_ZERO = false, bool OUT4 = false, int PIPE = 0, int PPIPE = 0>
+__device__ __forceinline__ void permute_fused(uint64_t (&s)[WIDTH]) {
+#pragma unroll
+  for (int i = 0; i < (CAP_ZERO ? 8 : WIDTH); i++) s[i] = gl::add_canonical(s[i], PMT_RC[i]);
+#pragma unroll 1
+  for (int half = 0; half < 2; half++) {
+#pragma unroll 1
+    for (int r = 0; r < PMT_FULL_HALF; r++)
+      full_round_fused<SBOX_FMA_MASK, CVT_I2F, COMBINE_ALU, PIPE>(s, &PMT_RC_AFTER_FULL_DM[2 * WIDTH * (PMT_FULL_HALF * half + r)],
+                                                            CAP_ZERO && half == 0 && r == 0,
+                                                            OUT4 && half == 1 && r == PMT_FULL_HALF - 1);
+    if (half == 0) {
+      {  // dense INIT matrix on lanes 1..11 (lane 0 passes through)
+        uint64_t y[WIDTH];
+#pragma unroll 1
+        for (int a = 1; a < WIDTH; a++) {
+          DotAcc acc = {0, 0, 0, 0, 0, 0};
+          dot_acc<WIDTH - 1>(acc, &s[1], &PMT_FP_INIT_L11[3 * (WIDTH - 1) * (a - 1)]);
+          const uint64_t v = dot_finish<DOT_ALU>(acc);
+#pragma unroll
+          for (int i = 1; i < WIDTH; i++) if (i == a) y[i] = v;   // static indexing keeps y[] in registers
+        }
+#pragma unroll
+        for (int i = 1; i < WIDTH; i++) s[i] = y[i];
+      }
+#pragma unroll 1
+      for (int k = 0; k < PMT_PARTIAL; k++) {
+        DotAcc acc = {0, 0, 0, 0, 0, 0};
+        const uint32_t* __restrict__ wl = &PMT_FP_W_HAT_L11[3 * (WIDTH - 1) * k];
+        uint64_t x0;
+        if (PPIPE == 0) {
+          dot_acc<WIDTH - 1>(acc, &s[1], wl);   // independent of the S-box below
+          x0 = gl::add_canonical(pow7_mix<PART_FMA_MASK>(s[0]), PMT_FP_POST_RC[k]);
+        } else {
+          // the S-box's four dependent multiplications are staged against quarters of the dot product
+          const uint32_t zero = PMT_ZERO32;
+          const uint64_t x = s[0];
+          dot_acc<3>(acc, &s[1], wl);
+          const uint64_t x2 = gl::sqr<!(PART_FMA_MASK & 1)>(x);
+          dot_acc<3>(acc, &s[4], wl + 9);
+          const uint64_t x4 = gl::sqr<!(PART_FMA_MASK & 2)>(tie(x2, gl::hi32(acc.t12), zero));
+          dot_acc<3>(acc, &s[7], wl + 18);
+          const uint64_t x3 = gl::mul<!(PART_FMA_MASK & 4)>(x, tie(x2, gl::hi32(acc.t12), zero));
+          dot_acc<2>(acc, &s[10], wl + 27);
+          x0 = gl::add_canonical(gl::mul<!(PART_FMA_MASK & 8)>(x3, tie(x4, gl::hi32(acc.t12), zero)), PMT_FP_POST_RC[k]);
+        }
+        acc.t00 = gl::mad_wide(gl::lo32(x0), (uint32_t)PMT_FP_M00, acc.t00);
+        acc.t10 = gl::mad_wide(gl::hi32(x0), (uint32_t)PMT_FP_M00, acc.t10);
+        const uint64_t d = dot_finish<DOT_ALU>(acc);
+#pragma unroll
+        for (int i = 1; i < WIDTH; i++) s[i] = gl::mul_add<MULADD_ALU>(x0, PMT_FP_V[(WIDTH - 1) * k + (i - 1)], s[i]);
+        s[0] = d;
+      }
+#pragma unroll
+      for (int i = 0; i < WIDTH; i++) s[i] = gl::add_canonical(s[i], PMT_RC[WIDTH * (PMT_FULL_HALF + PMT_PARTIAL) + i]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Cooperative form for the latency-bound levels: 16 lanes share ONE state (lane g < 12 holds element g, lanes 12..15
 // idle).  A lone warp needs ~58 us for a thread-per-state permutation (25 k dependent-ish instructions); here the 12
 // S-boxes of a round run side by side and the MDS row of every lane is 11 pairs of warp shuffles + 24 IMAD.WIDE, so a

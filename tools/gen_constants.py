@@ -224,6 +224,52 @@ def poseidon_fast(state, rc, fp):
 
 
 # ----------------------------------------------------------------------------------------------
+# Paired partial rounds (the form the CUDA permutation executes, poseidon.cuh permute_paired).
+# Two consecutive partial rounds r, r+1 on a state s that already holds c_r:
+#     s' = [sbox(s0), s1..s11];  y = M s' + c_{r+1};  y' = [sbox(y0), y1..y11];  z = M y' + c_{r+2}
+# Lanes 1..11 of y never meet an S-box, so with x = sbox(y0), y0 = row0(M) s' + c_{r+1}[0]:
+#     z = A s' + col0(M) x + K,     A = M[:,1:] M[1:,:]  (12 x 12, entries < 2^15),   K = M[:,1:] c_{r+1}[1:] + c_{r+2}
+# i.e. 24 + 288 + 24 small-coefficient MACs per PAIR of rounds instead of 2 x 288.  A is the same for every pair.
+# ----------------------------------------------------------------------------------------------
+def derive_paired(rc):
+    m = mds_matrix()
+    a = [[sum(m[i][j] * m[j][k] for j in range(1, WIDTH)) for k in range(WIDTH)] for i in range(WIDTH)]   # exact integers
+    ks = []
+    for pair in range(N_PARTIAL // 2):
+        r = N_FULL_HALF + 2 * pair
+        c1 = rc[WIDTH * (r + 1): WIDTH * (r + 2)]
+        c2 = rc[WIDTH * (r + 2): WIDTH * (r + 3)]
+        ks.append([(sum(m[i][j] * c1[j] for j in range(1, WIDTH)) + c2[i]) % P for i in range(WIDTH)])
+    return dict(a=a, k=ks)
+
+
+def poseidon_paired(state, rc, pp):
+    m = mds_matrix()
+    s = [x % P for x in state]
+
+    def full(s, r):   # s holds c_r already; adds c_{r+1} (zeros after the last round)
+        s = [pow(x, 7, P) for x in s]
+        nxt = rc[WIDTH * (r + 1): WIDTH * (r + 2)] if r + 1 < N_ROUNDS else [0] * WIDTH
+        return [(y + c) % P for y, c in zip(mat_vec(m, s), nxt)]
+
+    s = [(s[i] + rc[i]) % P for i in range(WIDTH)]
+    for r in range(N_FULL_HALF):
+        s = full(s, r)
+    for pair in range(N_PARTIAL // 2):
+        r = N_FULL_HALF + 2 * pair
+        sp = [pow(s[0], 7, P)] + s[1:]
+        # the kernel accumulates these sums in fp64: every partial sum must stay an exact integer below 2^52
+        for half in (lambda v: v & 0xFFFFFFFF, lambda v: v >> 32):
+            assert sum(pp["a"][0][k] * 0xFFFFFFFF for k in range(WIDTH)) + 41 * 0xFFFFFFFF + 0xFFFFFFFF < 2 ** 52
+        y0 = (sum(m[0][k] * sp[k] for k in range(WIDTH)) + rc[WIDTH * (r + 1)]) % P
+        x = pow(y0, 7, P)
+        s = [(sum(pp["a"][i][k] * sp[k] for k in range(WIDTH)) + m[i][0] * x + pp["k"][pair][i]) % P for i in range(WIDTH)]
+    for r in range(N_FULL_HALF + N_PARTIAL, N_ROUNDS):
+        s = full(s, r)
+    return s
+
+
+# ----------------------------------------------------------------------------------------------
 # emit
 # ----------------------------------------------------------------------------------------------
 def _fmt_u64_table(name, vals, per_line=4, qual="static const uint64_t"):
@@ -238,7 +284,7 @@ def _fmt_u64_table(name, vals, per_line=4, qual="static const uint64_t"):
 _QUAL = ["static const uint64_t"]
 
 
-def emit(path, guard, rc, fp, cuda):
+def emit(path, guard, rc, fp, cuda, pp=None):
     # CUDA: tables live in constant bank 3; with unrolled rounds ptxas folds them into c[0x3][imm] operands
     _QUAL[0] = "static __device__ __constant__ uint64_t" if cuda else "static const uint64_t"
     flat = lambda mm: [x for row in mm for x in row]
@@ -305,6 +351,37 @@ def emit(path, guard, rc, fp, cuda):
             for c in range(WIDTH):
                 il += limbs(fp["init_m"][r][c])   # column 0 is zero: rows are 12 terms so INIT shares dot12_limbs
         out.append("static __device__ __constant__ uint32_t PMT_FP_INIT_L[%d] = {%s};" % (len(il), ", ".join(map(str, il))))
+        out.append("// tables of the fused permutation (poseidon.cuh permute_fused): the MDS constants with 2^52 folded in (the DFMA")
+        out.append("// accumulators then hold 2^52 + integer, whose mantissa IS the integer), and the partial-round limb tables")
+        out.append("// without the lane-0 column (W_HAT: lane 0 has the small coefficient M00; INIT: column 0 is zero).")
+        ndm = []
+        for x in nxt:
+            ndm += ["%d.0" % ((x & 0xFFFFFFFF) + 2 ** 52), "%d.0" % ((x >> 32) + 2 ** 52)]
+        out.append("static __device__ __constant__ double PMT_RC_AFTER_FULL_DM[%d] = {%s};" % (len(ndm), ", ".join(ndm)))
+        out.append("// ALL_ROUND_CONSTANTS rows 1..30 (row 30 = zeros) as (lo + 2^52, hi + 2^52) doubles: the constants added by the")
+        out.append("// MDS layer of round r are row r + 1 (poseidon.cuh permute_rounds)")
+        rdm = []
+        for x in rc[12:] + [0] * 12:
+            rdm += ["%d.0" % ((x & 0xFFFFFFFF) + 2 ** 52), "%d.0" % ((x >> 32) + 2 ** 52)]
+        out.append("static __device__ __constant__ double PMT_RC_DM[%d] = {%s};" % (len(rdm), ", ".join(rdm)))
+        out.append("// paired partial rounds (tools/gen_constants.py::derive_paired): A = M[:,1:] M[1:,:] row-major, and per pair the")
+        out.append("// constants K as (lo + 2^52, hi + 2^52) doubles [pair][lane][lo, hi]")
+        out.append("static __device__ __constant__ double PMT_PP_A_D[144] = {%s};" % ", ".join("%d.0" % x for row in pp["a"] for x in row))
+        kdm = []
+        for row in pp["k"]:
+            for x in row:
+                kdm += ["%d.0" % ((x & 0xFFFFFFFF) + 2 ** 52), "%d.0" % ((x >> 32) + 2 ** 52)]
+        out.append("static __device__ __constant__ double PMT_PP_K_DM[%d] = {%s};" % (len(kdm), ", ".join(kdm)))
+        wl11 = []
+        for r in range(N_PARTIAL):
+            for x in fp["w_hat"][r]:
+                wl11 += limbs(x)
+        out.append("static __device__ __constant__ uint32_t PMT_FP_W_HAT_L11[%d] = {%s};" % (len(wl11), ", ".join(map(str, wl11))))
+        il11 = []
+        for r in range(1, WIDTH):
+            for c in range(1, WIDTH):
+                il11 += limbs(fp["init_m"][r][c])
+        out.append("static __device__ __constant__ uint32_t PMT_FP_INIT_L11[%d] = {%s};" % (len(il11), ", ".join(map(str, il11))))
     out.append("\n#endif")
     os.makedirs(os.path.dirname(path), exist_ok=True)
     with open(path, "w") as f:
@@ -324,11 +401,20 @@ def main():
     for _ in range(50):
         st = [rnd.randrange(P) for _ in range(WIDTH)]
         assert poseidon_fast(st, rc, fp) == poseidon_naive(st, rc)
+    pp = derive_paired(rc)
+    assert max(max(row) for row in pp["a"]) < 2 ** 15
+    # fp64 exactness of the paired layer: (2^32 - 1) * (row sum of A + the col0 coefficient) + constant half < 2^52
+    assert all((sum(row) + 41 + 1) * 0xFFFFFFFF < 2 ** 52 for row in pp["a"])
+    for _ in range(50):
+        st = [rnd.randrange(P) for _ in range(WIDTH)]
+        assert poseidon_paired(st, rc, pp) == poseidon_naive(st, rc)
+    for st in ([0] * 12, [P - 1] * 12, [2 ** 64 - 1] * 12, list(range(12))):
+        assert poseidon_paired(st, rc, pp) == poseidon_naive(st, rc)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     emit(os.path.join(root, "oracle", "poseidon_constants.h"), "PMT_ORACLE_POSEIDON_CONSTANTS_H", rc, fp, False)
     emit(os.path.join(root, "plonky2_merkle_trees_b200", "csrc", "poseidon_constants.cuh"),
-         "PMT_POSEIDON_CONSTANTS_CUH", rc, fp, True)
-    print("ok: constants verified (sha256, upstream KATs, fast==naive on 50 states); headers written")
+         "PMT_POSEIDON_CONSTANTS_CUH", rc, fp, True, pp)
+    print("ok: constants verified (sha256, upstream KATs, fast==naive and paired==naive on 50 states); headers written")
 
 
 if __name__ == "__main__":
