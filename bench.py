@@ -36,9 +36,12 @@ SEED = 0x706D745F62323030
 P = 0xFFFFFFFF00000001
 MAC32_PER_PERM = 10588            # spec-level 32x32->64 multiply-accumulates per permutation
 ALG_BYTES_PER_PERM = 96           # read two 32 B children, write one 32 B parent
-# measured on this pool's B200 by tools/perm_bench.cu (profiles/pipes_r1.jsonl): zero-addend IMAD.WIDE.U32 issue rate,
-# 62.65 lanes/clk/SM at the nominal 1965 MHz x 148 SMs
-PEAK_MAC32_PER_S = 18.22e12
+# measured on this pool's B200 by tools/perm_bench.cu (profiles/pipes_r1.jsonl): the multiply-accumulate issue peak of
+# the SM's fma / fp64 pipes = 63.7 lanes/clk/SM (32-bit IMAD; DFMA reaches 58.3) x 148 SMs x 1965 MHz.  IMAD.WIDE.U32, the
+# instruction a 32x32->64 MAC maps to literally, issues at HALF that rate (31.7 lanes/clk/SM = 9.2 T/s, with or without
+# an addend); the kernel runs the MDS layers' MACs as DFMAs, which is why it can exceed the IMAD.WIDE-only figure.
+IMAD_WIDE_PEAK_PER_S = 9.21e12
+PEAK_MAC32_PER_S = 18.53e12
 
 
 def measured_peaks():
@@ -319,13 +322,15 @@ def run_ours(args):
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")) as f:
-            traffic = json.load(f).get("k_level_dram_bytes_per_launch")
+            traffic = json.load(f).get("k_level_dram_bytes_per_permutation") * lvl["units"] / max(lvl["launches"], 1)
     except Exception:
         pass
     roofline = {
         "kernel": "k_level<Plonky2> (one two_to_one per thread)", "bound": "int32-imad (fma-heavy pipe)",
         "achieved": mac32 / 1e12, "peak": PEAK_MAC32_PER_S / 1e12, "unit": "TMAC32/s", "frac": mac32 / PEAK_MAC32_PER_S,
-        "peak_source": "measured IMAD.WIDE.U32 issue peak, tools/perm_bench.cu (profiles/pipes_r1.jsonl)",
+        "peak_source": "measured multiply-accumulate issue peak of the fma/fp64 pipes (32-bit IMAD 63.7 lanes/clk/SM), "
+                       "tools/perm_bench.cu (profiles/pipes_r1.jsonl)",
+        "imad_wide_only_peak": IMAD_WIDE_PEAK_PER_S / 1e12,
         "algorithmic_work_per_unit": "%d MAC32 per permutation (SURVEY.md 8(d))" % MAC32_PER_PERM,
         "perms_per_s": perms_per_s, "launches_timed": lvl["launches"], "avg_launch_ms": per_launch_ms,
         "share_of_step": lvl["ms"] / total_prof_ms,

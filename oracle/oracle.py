@@ -220,4 +220,10 @@ def merkle_verify_to_cap(leaf_row, idx, cap, cap_height, siblings):
 
 
 def max_threads():
-    return lib().pmt_oracle_max_threads()
+    """host cores this process may run on.  Not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1, which would
+    silently time the CPU baseline on one thread; the thread count is passed to the library explicitly instead."""
+    import os
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or lib().pmt_oracle_max_threads())

@@ -129,6 +129,11 @@ class Context:
             raise PmtError(rc, self.lib.pmt_last_error(self.h).decode())
 
     def call(self, name, *args):
+        if name.endswith("_dev"):
+            # device-pointer entry points read tensors that torch may still be producing on ITS current stream; the ctx
+            # stream is non-blocking, so order it after torch's stream first (event wait, no host sync)
+            from .device import order_after_torch
+            order_after_torch(self)
         self.check(getattr(self.lib, name)(self.h, *args))
 
     def sync(self):

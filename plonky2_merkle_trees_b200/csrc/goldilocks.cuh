@@ -66,9 +66,25 @@ __device__ __forceinline__ uint64_t reduce128_alu(uint32_t w0, uint32_t w1, uint
   return pack(w0, w1);
 }
 
+// Signed two-word form of the same reduction, ANY 128-bit input:
+//   V = (w0 - w2 - w3) + 2^32 (w1 + w2)   (mod p),   lo = w0 - w2 - w3 in (-2^33, 2^32),  hi = w1 + w2 + (lo >> 32)
+// hi overflows 32 bits by n in {-1, 0, 1}; n 2^64 = n (2^32 - 1) = (n << 32) - n is added in 64-bit arithmetic, which
+// cannot wrap again (checked exhaustively on the host against __int128 % p, tools/check_reduce.c).  Written in plain C so
+// that ptxas uses 3-input IADD3 / IADD3.X with two carry predicates: 7 ALU instructions instead of 13.
+__device__ __forceinline__ uint64_t reduce128_c(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+  const int64_t lo = (int64_t)(uint64_t)w0 - (int64_t)(uint64_t)w2 - (int64_t)(uint64_t)w3;
+  const int64_t hi = (int64_t)(uint64_t)w1 + (int64_t)(uint64_t)w2 + (lo >> 32);
+  const int64_t n = hi >> 32;
+  return pack((uint32_t)lo, (uint32_t)hi) + ((uint64_t)n << 32) - (uint64_t)n;
+}
+
+#ifndef PMT_REDUCE_C
+#define PMT_REDUCE_C 1   // 1: the ALU-only reduction is reduce128_c (3-input adds), 0: the hand-written PTX carry chain
+#endif
 template <bool ALU = false>
 __device__ __forceinline__ uint64_t reduce128(u128 v) {
   uint64_t lo = (uint64_t)v, hi = (uint64_t)(v >> 64);
+  if (ALU && PMT_REDUCE_C) return reduce128_c(lo32(lo), hi32(lo), lo32(hi), hi32(hi));
   return ALU ? reduce128_alu(lo32(lo), hi32(lo), lo32(hi), hi32(hi)) : reduce128(lo32(lo), hi32(lo), lo32(hi), hi32(hi));
 }
 

@@ -12,6 +12,7 @@
 // never re-read by the level that produced them, so HBM traffic is the algorithmic 96 B per two_to_one.
 #pragma once
 #include "poseidon.cuh"
+#include "poseidon_quad.cuh"
 
 namespace pmt {
 
@@ -194,13 +195,65 @@ __global__ void __launch_bounds__(BLOCK) k_leaves(Layout lay, const uint64_t* __
 }
 
 // one level: digest(l, k) = two_to_one(children) for k in [k0, k0 + count)
+// PMT_QUAD = 0 (production): one node per thread (poseidon.cuh permute_paired).
+// PMT_QUAD = 1: 32 nodes per warp in the quad layout of poseidon_quad.cuh, MDS layers on the fp64 tensor pipe (DMMA).
+// Thread (q, j) loads / stores element j of the digests of nodes 8 mb + q: the four threads of a quad cover one 32-byte
+// digest.  Bit-exact and 30 % fewer instructions, but not faster on B200 (1.26 vs 1.29 G permutations/s):
+// both forms are bound by the S-boxes' integer work, which the MDS engine does not change.
+#ifndef PMT_QUAD
+#define PMT_QUAD 0
+#endif
+#ifndef PMT_QUAD_SBOX_FMA_MASK
+#define PMT_QUAD_SBOX_FMA_MASK 0
+#endif
+#ifndef PMT_QUAD_PART_FMA_MASK
+#define PMT_QUAD_PART_FMA_MASK 0
+#endif
+#ifndef PMT_QUAD_COMBINE_ALU
+#define PMT_QUAD_COMBINE_ALU 1
+#endif
+__device__ __forceinline__ void permute_quad(uint64_t (&e)[4][3], const poseidon::QuadTables& T, const poseidon::QuadFrags& f,
+                                             unsigned lane) {
+  poseidon::permute_quad<PMT_QUAD_SBOX_FMA_MASK, PMT_QUAD_PART_FMA_MASK, PMT_QUAD_COMBINE_ALU != 0>(e, T, f, lane);
+}
+
 template <class Layout>
 __global__ void __launch_bounds__(BLOCK, PMT_MINB) k_level(Layout lay, int l, size_t k0, size_t count) {
+#if PMT_QUAD
+  __shared__ poseidon::QuadTables T;
+  poseidon::quad_stage_tables(T);
+  const unsigned lane = threadIdx.x & 31, q = lane >> 2, j = lane & 3;
+  poseidon::QuadFrags f;
+  poseidon::quad_load_frags(f, q, j);
+#if PMT_QUAD_FRAGS_SMEM
+  poseidon::quad_publish_frags(T, f, lane);
+#endif
+  for (size_t base = (size_t)blockIdx.x * BLOCK; base < count; base += (size_t)gridDim.x * BLOCK) {
+    const size_t wbase = base + (threadIdx.x & ~31u);
+    if (wbase >= count) continue;                       // warp-uniform
+    uint64_t e[4][3];
+#pragma unroll
+    for (int mb = 0; mb < 4; mb++) {
+      size_t i = wbase + 8 * mb + q;
+      if (i >= count) i = count - 1;                    // ragged tail: recompute the last node, store nothing
+      const uint64_t *a, *b;
+      lay.children(l, k0 + i, a, b);
+      e[mb][0] = a[j]; e[mb][1] = b[j]; e[mb][2] = 0;
+    }
+    permute_quad(e, T, f, lane);
+#pragma unroll
+    for (int mb = 0; mb < 4; mb++) {
+      const size_t i = wbase + 8 * mb + q;
+      if (i < count) lay.at(l, k0 + i)[j] = gl::canonical(e[mb][0]);
+    }
+  }
+#else
   for (size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x; i < count; i += (size_t)gridDim.x * BLOCK) {
     const uint64_t *a, *b;
     lay.children(l, k0 + i, a, b);
     store_digest(lay.at(l, k0 + i), two_to_one(load_digest(a), load_digest(b)));
   }
+#endif
 }
 
 constexpr int TOP_BLOCK = 256;  // 256 x ~100 registers fits one SM's register file without spilling the state

@@ -16,6 +16,10 @@
 #include "goldilocks.cuh"
 #include "poseidon_constants.cuh"
 
+#ifndef PMT_COMBINE_C
+#define PMT_COMBINE_C 1   // 1: the ALU recombination is combine_magic_c (plain C, 3-input adds) instead of the PTX carry chain
+#endif
+
 namespace poseidon {
 
 static constexpr int WIDTH = 12;
@@ -288,7 +292,11 @@ __device__ __forceinline__ uint64_t tie(uint64_t x, uint32_t after, uint32_t zer
 __device__ __forceinline__ uint32_t hi_word(double d) { return (uint32_t)__double2hiint(d); }
 
 // 2^52 + l, 2^52 + h (l, h < 2^43) -> u64 congruent to l + 2^32 h, ALU pipe only.
+__device__ __forceinline__ uint64_t combine_magic_c(double L, double H);
 __device__ __forceinline__ uint64_t combine_magic_alu(double L, double H) {
+#if PMT_COMBINE_C
+  return combine_magic_c(L, H);
+#endif
   const uint64_t lb = (uint64_t)__double_as_longlong(L), hb = (uint64_t)__double_as_longlong(H);
   uint32_t w0 = gl::lo32(lb), w1 = gl::lo32(hb), w2 = gl::hi32(hb) & 0xFFFFFu, net;
   const uint32_t lh = gl::hi32(lb) & 0xFFFFFu;
@@ -300,6 +308,17 @@ __device__ __forceinline__ uint64_t combine_magic_alu(double L, double H) {
   asm("sub.cc.u32 %0, %0, %2;\n\tsubc.u32 %1, %1, 0;" : "+r"(w0), "+r"(w1) : "r"(net));
   w1 += net;
   return gl::pack(w0, w1);
+}
+// The same recombination in plain C (signed two-word form, like gl::reduce128_c): V = (l0 - h1) + 2^32 (l1 + h0 + h1);
+// the exponent bits 0x43300000 of both high words are removed by constants folded into the 3-input adds, so there is
+// no masking.  Exact for every l, h < 2^52 (tools/check_combine.c).
+__device__ __forceinline__ uint64_t combine_magic_c(double L, double H) {
+  const uint64_t lb = (uint64_t)__double_as_longlong(L), hb = (uint64_t)__double_as_longlong(H);
+  const int64_t lo = (int64_t)(uint64_t)gl::lo32(lb) - (int64_t)(uint64_t)gl::hi32(hb) + 0x43300000ll;
+  const int64_t hi = (int64_t)(uint64_t)gl::hi32(lb) + (int64_t)(uint64_t)gl::lo32(hb) + (int64_t)(uint64_t)gl::hi32(hb) +
+                     (lo >> 32) - 0x86600000ll;
+  const int64_t n = hi >> 32;
+  return gl::pack((uint32_t)lo, (uint32_t)hi) + ((uint64_t)n << 32) - (uint64_t)n;
 }
 __device__ __forceinline__ uint64_t combine_magic_fma(double L, double H) {
   const uint64_t li = (uint64_t)__double_as_longlong(L) & 0x000FFFFFFFFFFFFFull;

@@ -24,3 +24,13 @@ def to_host(t):
 
 def dptr(t):
     return C.c_void_p(t.data_ptr())
+
+
+def order_after_torch(ctx, device=None):
+    """Make the ctx stream wait for the work already enqueued on torch's current stream (one event record + wait, no host
+    sync).  The ctx stream is non-blocking, so a tensor produced by torch kernels (e.g. synthetic leaves) is otherwise not
+    guaranteed to be complete when a libpmt kernel reads it."""
+    dev = torch.device("cuda", ctx.device) if device is None else device
+    cur = torch.cuda.current_stream(dev)
+    if cur.cuda_stream != (ctx.stream or 0):
+        torch.cuda.ExternalStream(ctx.stream, device=dev).wait_stream(cur)

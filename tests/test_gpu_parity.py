@@ -364,3 +364,24 @@ def test_sharded_virtual_ranks(ctx, api, oracle, lg, w, h, G):
         t = sharded.ShardedMerkleTree(n, w, h, G, 0, None, gathered, top, top[top.shape[0] - (1 << h):])
         assert np.array_equal(t.cap, ocap)
     assert np.array_equal(t.assemble_global(chunks), odg)
+
+
+# ---- stream ordering between torch and the ctx stream ---------------------------------------------------------------
+def test_dev_entry_points_wait_for_torch_stream(api, ctx, oracle):
+    """Leaves produced by torch kernels on torch's current stream, handed to a *_dev entry point with no host sync in
+    between: the ctx stream (non-blocking) must be ordered after torch's stream (plonky2_merkle_trees_b200/device.py
+    order_after_torch).  Found by tools/multigpu_check.py: without the wait the build read half-written leaves."""
+    import bench
+    n, w = 1 << 16, 4
+    want = None
+    for rep in range(4):
+        # a long-running torch kernel queue in front of the generator makes the race (if any) certain
+        junk = torch.randn(4096, 4096, device="cuda")
+        for _ in range(8):
+            junk = junk @ junk * 1e-3
+        d_leaves = bench.splitmix_torch(rep * n * w, n * w, torch.device("cuda", 0)).view(n, w)
+        t = api.mt.MerkleTree.new_dev(d_leaves, 0, ctx)
+        rows = bench.splitmix_numpy(rep * n * w, n * w).reshape(n, w)
+        dg, cap = oracle.merkle_tree_new(rows, 0, threads=oracle.max_threads(), fast=True)
+        assert np.array_equal(t.cap, cap), rep
+        assert np.array_equal(t.digests, dg), rep

@@ -38,7 +38,8 @@ int main(int argc, char** argv) {
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pmt::k_level<pmt::Plonky2>, pmt::BLOCK, 0));
   cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, pmt::k_level<pmt::Plonky2>));
   const int bps = blocks_per_sm ? blocks_per_sm : occ;
-  const unsigned grid = (unsigned)(prop.multiProcessorCount * bps);
+  // blocks_per_sm < 0: one node per thread (what pmt_api.cu launches); otherwise a persistent grid of resident blocks
+  const unsigned grid = blocks_per_sm < 0 ? (unsigned)((n / 2 + pmt::BLOCK - 1) / pmt::BLOCK) : (unsigned)(prop.multiProcessorCount * bps);
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   const size_t count = n / 2;
   float best = 1e30f;

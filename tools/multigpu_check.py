@@ -1,0 +1,61 @@
+#!/usr/bin/env python3
+"""Multi-GPU parity check, run under torchrun (one rank per GPU, NCCL):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
+        tools/multigpu_check.py
+
+Every rank builds its subtree shard (plonky2_merkle_trees_b200.sharded), the chunks are gathered on rank 0 and compared
+BIT FOR BIT with the same tree built in one piece on rank 0's GPU (which tests/test_gpu_parity.py ties to the oracle).
+Covers cap_height < log2 G (top levels after the all_gather), cap_height >= log2 G (cap slices) and wide leaves.
+Prints one JSON line per case; exit code 1 on any mismatch."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from plonky2_merkle_trees_b200 import _lib, merkle_tree, sharded  # noqa: E402
+from plonky2_merkle_trees_b200.device import to_host  # noqa: E402
+
+
+def main():
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist.init_process_group("nccl", device_id=dev)
+    ctx = _lib.Context(local_rank)
+    eng = sharded.CudaEngine(ctx)
+    ok_all = True
+    cases = [(14, 4, 0), (14, 1, 0), (12, 135, 4), (13, 9, 1), (16, 4, 5), (10, 4, 3)]
+    for lg, w, h in cases:
+        n = 1 << lg
+        per = n // world
+        d_local = bench.splitmix_torch(rank * per * w, per * w, dev).view(per, w)
+        tree = sharded.build_sharded_tree(d_local, n, h, eng)
+        chunk = tree.local_digests.contiguous()
+        chunks = [torch.empty_like(chunk) for _ in range(world)] if rank == 0 else None
+        dist.gather(chunk, chunks, dst=0)
+        if rank == 0:
+            full_leaves = bench.splitmix_numpy(0, n * w).reshape(n, w)
+            ref = merkle_tree.MerkleTree.new(full_leaves, h, ctx)
+            got = tree.assemble_global([to_host(c) for c in chunks])
+            cap = to_host(tree.cap)
+            ok = bool(np.array_equal(got, ref.digests) and np.array_equal(cap, ref.cap))
+            ok_all &= ok
+            print(json.dumps({"check": "sharded_vs_single", "world": world, "log2_n": lg, "width": w, "cap_height": h,
+                              "digests": int(got.shape[0]), "ok": ok}), flush=True)
+    flag = torch.tensor([1 if ok_all else 0], device=dev)
+    dist.broadcast(flag, 0)
+    dist.destroy_process_group()
+    return 0 if int(flag.item()) else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -82,6 +82,66 @@ __global__ void __launch_bounds__(256) k_pipe(uint64_t* out, uint32_t a, uint32_
           double d = __longlong_as_double((long long)acc[j]);
           asm volatile("add.rn.f64 %0, %0, %1;" : "+d"(d) : "d"(dk));
           acc[j] = (uint64_t)__double_as_longlong(d);
+        } else if (MODE == 18) {  // DFMA + IADD3 (1:1): does an fp64 instruction hold the issue port for 2 cycles?
+          double d = __longlong_as_double((long long)acc[j]);
+          asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(d) : "d"(dk), "d"(dx[j]));
+          acc[j] = (uint64_t)__double_as_longlong(d);
+          asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[j]) : "r"(x[(j + 1) % ILP]), "r"(a));
+        } else if (MODE == 19) {  // DFMA + 2 ALU (1:2)
+          double d = __longlong_as_double((long long)acc[j]);
+          asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(d) : "d"(dk), "d"(dx[j]));
+          acc[j] = (uint64_t)__double_as_longlong(d);
+          asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[j]) : "r"(x[(j + 1) % ILP]), "r"(a));
+          asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(y[j]) : "r"(y[(j + 1) % ILP]), "r"(a));
+        } else if (MODE == 20) {  // I2F.F64.U32
+          asm volatile("cvt.rn.f64.u32 %0, %1;" : "=d"(dx[j]) : "r"(x[j]));
+          x[j] += (uint32_t)__double2hiint(dx[j]);
+        } else if (MODE == 21) {  // DFMA + IMAD lo (1:1): same pipe or not
+          double d = __longlong_as_double((long long)acc[j]);
+          asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(d) : "d"(dk), "d"(dx[j]));
+          acc[j] = (uint64_t)__double_as_longlong(d);
+          asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(x[j]) : "r"(a), "r"(b));
+        } else if (MODE == 22) {  // DFMA + IMAD lo + LOP3 (1:1:1)
+          double d = __longlong_as_double((long long)acc[j]);
+          asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(d) : "d"(dk), "d"(dx[j]));
+          acc[j] = (uint64_t)__double_as_longlong(d);
+          asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(x[j]) : "r"(a), "r"(b));
+          asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(y[j]) : "r"(y[(j + 1) % ILP]), "r"(a));
+        } else if (MODE == 23) {  // pure-ALU carry chain with a carry-in AND carry-out in the middle (sub.cc / subc.cc / subc)
+          asm volatile("sub.cc.u32 %0, %0, %3;\n\tsubc.cc.u32 %1, %1, %4;\n\tsubc.u32 %2, %2, 0;"
+                       : "+r"(x[j]), "+r"(y[j]), "+r"(z[j]) : "r"(x[(j + 1) % ILP]), "r"(y[(j + 1) % ILP]));
+        } else if (MODE == 24) {  // 2 DFMA + 1 LOP3
+          double d = __longlong_as_double((long long)acc[j]);
+          asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(d) : "d"(dk), "d"(dx[j]));
+          asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(dx[j]) : "d"(dk), "d"(dk));
+          acc[j] = (uint64_t)__double_as_longlong(d);
+          asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[j]) : "r"(x[(j + 1) % ILP]), "r"(a));
+        } else if (MODE == 30) {  // IMAD.WIDE.U32 zero addend, operands depend on the previous result (nothing to hoist)
+          asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(acc[j]) : "r"((uint32_t)acc[j]), "r"(y[j]));
+        } else if (MODE == 31) {  // IMAD.WIDE.U32 accumulate form, multiplicand depends on the accumulator
+          asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"((uint32_t)acc[j]), "r"(y[j]));
+        } else if (MODE == 32) {  // zero-addend IMAD.WIDE + LOP3 (1:1)
+          asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(acc[j]) : "r"((uint32_t)acc[j]), "r"(y[j]));
+          asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[j]) : "r"(x[(j + 1) % ILP]), "r"(a));
+        } else if (MODE == 33) {  // accumulate-form IMAD.WIDE + LOP3 (1:1)
+          asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"((uint32_t)acc[j]), "r"(y[j]));
+          asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[j]) : "r"(x[(j + 1) % ILP]), "r"(a));
+        } else if (MODE == 34) {  // accumulate-form IMAD.WIDE + 2 LOP3 (1:2)
+          asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"((uint32_t)acc[j]), "r"(y[j]));
+          asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[j]) : "r"(x[(j + 1) % ILP]), "r"(a));
+          asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(z[j]) : "r"(z[(j + 1) % ILP]), "r"(a));
+        } else if (MODE == 35) {  // zero-addend IMAD.WIDE + carry chain add.cc/addc (1:2)
+          asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(acc[j]) : "r"((uint32_t)acc[j]), "r"(y[j]));
+          asm volatile("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, %1, %3;" : "+r"(x[j]), "+r"(z[j]) : "r"(x[(j + 1) % ILP]), "r"(z[(j + 1) % ILP]));
+        } else if (MODE == 36) {  // 32-bit IMAD with data-dependent operands + LOP3 (1:1)
+          asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(y[j]) : "r"(y[(j + 1) % ILP]), "r"(a));
+          asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[j]) : "r"(x[(j + 1) % ILP]), "r"(a));
+        } else if (MODE == 37) {  // 32-bit IMAD alone, data-dependent
+          asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(y[j]) : "r"(y[(j + 1) % ILP]), "r"(a));
+        } else if (MODE == 38) {  // IMAD.WIDE.U32 zero addend with BOTH result words consumed (so it stays an IMAD.WIDE) + 1 LOP3
+          uint64_t w;
+          asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w) : "r"(x[j]), "r"(y[j]));
+          asm volatile("lop3.b32 %0, %1, %2, %0, 0x96;" : "+r"(x[j]) : "r"((uint32_t)w), "r"((uint32_t)(w >> 32)));
         } else if (MODE == 13) {  // SEL
           asm volatile("{ .reg .pred p; setp.lt.u32 p, %0, %1; selp.u32 %0, %1, %2, p; }" : "+r"(x[j]) : "r"(x[(j + 1) % ILP]), "r"(a));
         }
@@ -234,6 +294,22 @@ int main(int argc, char** argv) {
     run_pipe<17>("dadd", 1, sms);
     run_pipe<15>("dfma+imad_wide_acc (1:1)", 2, sms);
     run_pipe<16>("dfma+imad_wide_acc+iadd3 (1:1:1)", 3, sms);
+    run_pipe<38>("imad_wide zero-addend, both words used (+1 lop3, counted 1)", 1, sms);
+    run_pipe<30>("imad_wide zero-addend (dependent operands)", 1, sms);
+    run_pipe<31>("imad_wide accumulate (dependent operands)", 1, sms);
+    run_pipe<32>("imad_wide zero + lop3 (1:1)", 2, sms);
+    run_pipe<33>("imad_wide acc + lop3 (1:1)", 2, sms);
+    run_pipe<34>("imad_wide acc + 2 lop3 (1:2)", 3, sms);
+    run_pipe<35>("imad_wide zero + add.cc/addc (1:2)", 3, sms);
+    run_pipe<37>("imad_lo (dependent operands)", 1, sms);
+    run_pipe<36>("imad_lo + lop3 (1:1)", 2, sms);
+    run_pipe<18>("dfma+lop3 (1:1)", 2, sms);
+    run_pipe<19>("dfma+2lop3 (1:2)", 3, sms);
+    run_pipe<20>("i2f.f64.u32(+iadd)", 1, sms);
+    run_pipe<21>("dfma+imad_lo (1:1)", 2, sms);
+    run_pipe<22>("dfma+imad_lo+lop3 (1:1:1)", 3, sms);
+    run_pipe<23>("sub.cc+subc.cc+subc", 3, sms);
+    run_pipe<24>("2dfma+lop3 (2:1)", 3, sms);
   }
   if (argc > 1 && strstr(argv[1], "lat")) run_latency(sms);
   if (perms) {
