@@ -96,46 +96,66 @@ def splitmix_torch(start, count, device):
 # clocks
 # ------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock + throttle reasons DURING the timed region.  NVML in a thread (one sample per ~5 ms: the timed region of 10
+    steps is only ~140 ms, too short for `nvidia-smi -lms`); falls back to polling nvidia-smi if pynvml is unusable."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, gpu_index):
-        self.samples, self.proc, self.idx = [], None, gpu_index
+        self.idx, self.sm, self.reasons, self.max_mhz = gpu_index, [], set(), None
+        self.stop_flag, self.thread, self.how = threading.Event(), None, None
+
+    def _nvml_loop(self, nv, h):
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                for name, bit in self.BITS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def _smi_loop(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.sm.append(float(f[0])); self.max_mhz = float(f[1])
+                for nm, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [int(x) for x in vis.split(",")] if vis and all(x.strip().isdigit() for x in vis.split(",")) else None
+            h = nv.nvmlDeviceGetHandleByIndex(ids[self.idx] if ids else self.idx)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.how = "nvml"
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
         except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.samples.append(line.strip())
+            self.how = "nvidia-smi"
+            self.thread = threading.Thread(target=self._smi_loop, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            f = [x.strip() for x in s.split(",")]
-            try:
-                sm.append(float(f[0])); mx = float(f[1])
-                for nm, v in zip(names, f[2:6]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
-            except Exception:
-                pass
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        self.stop_flag.set()
+        if self.thread:
+            self.thread.join(timeout=6)
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no clock samples"], "samples": 0, "how": self.how}
+        return {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.sm), "how": self.how}
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -161,7 +181,7 @@ def cpu_tree_throughput(log2_sample, reps=1):
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return 0
+        return None, 0
     log2_sample = 20
     for _ in range(args.warmup):
         cpu_tree_throughput(log2_sample)
@@ -185,8 +205,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "leaves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
-    return 0
+    return line, 0
 
 
 def workload_config(n_gpus):
@@ -309,7 +328,7 @@ def run_ours(args):
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
-        return 0
+        return None, 0
 
     # ---- roofline of the dominant kernel ------------------------------------------------------------------------------
     peaks, peak_src = measured_peaks()
@@ -360,10 +379,24 @@ def run_ours(args):
         "roofline": roofline,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
-    return 0
+    return line, 0
+
+
+class StdoutToStderr:
+    """Everything written to fd 1 while active goes to stderr (NCCL prints its version banner to stdout when NCCL_DEBUG is
+    set on the box); the JSON line is printed after restore(), so stdout carries exactly one line."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def restore(self):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
 
 
 def main():
@@ -373,9 +406,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
-    return run_ours(args)
+    guard = StdoutToStderr()
+    line, rc = run_reference(args) if args.impl == "reference" else run_ours(args)
+    guard.restore()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    return rc
 
 
 if __name__ == "__main__":

@@ -332,6 +332,36 @@ __global__ void __launch_bounds__(COOP_BLOCK) k_top_coop(Layout lay, int l0, int
   }
 }
 
+// multi-GPU finish: the levels above n_roots gathered subtree roots, ONE block, 16 lanes per permutation (the levels are
+// sequential and tiny: G - 1 permutations for G ranks).  out is level-major: n_roots/2, n_roots/4, ..., n_cap digests.
+__global__ void __launch_bounds__(COOP_BLOCK) k_top_roots_coop(const uint64_t* __restrict__ roots, size_t n_roots, size_t n_cap,
+                                                               uint64_t* __restrict__ out) {
+  __shared__ uint64_t rc_smem[WIDTH * (PMT_ROUNDS + 1)];
+  coop_stage_constants(rc_smem);
+  const unsigned g = threadIdx.x & 15, base_lane = threadIdx.x & 16;
+  const size_t group = threadIdx.x >> 4, groups = blockDim.x >> 4;
+  const uint64_t* cur = roots;
+  uint64_t* dst = out;
+  for (size_t m = n_roots / 2; m >= n_cap && m >= 1; m >>= 1) {
+    for (size_t base = 0; base < m; base += groups) {
+      const size_t first_of_warp = base + (group & ~(size_t)1);
+      if (first_of_warp < m) {                       // warp-uniform: both groups of a warp run the shuffles
+        const size_t k = base + group;
+        const bool active = k < m;
+        uint64_t v = 0;
+        if (active && g < 8) v = cur[8 * k + g];     // children 2k and 2k + 1 are adjacent
+        v = poseidon::permute_coop(v, rc_smem, g, base_lane);
+        if (active && g < 4) dst[4 * k + g] = gl::canonical(v);
+      }
+    }
+    __threadfence_block();
+    __syncthreads();
+    cur = dst;
+    dst += 4 * m;
+    if (m == 1) break;
+  }
+}
+
 // hash_or_noop of ONE row by one 16-lane group (bagging the peaks): the sponge's permutations are sequential, so the
 // cooperative form cuts the latency by ~10x
 __global__ void __launch_bounds__(32) k_hash_one_coop(const uint64_t* __restrict__ felts, size_t w, uint64_t* __restrict__ out) {

@@ -410,6 +410,12 @@ int pmt_top_levels_dev(pmt_ctx* c, const uint64_t* d_roots, size_t n_roots, uint
   if ((int)cap_height > g) return fail(c, PMT_E_RANGE, "top levels: cap_height %u > log2(roots)", cap_height);
   if ((int)cap_height == g) return PMT_OK;  // the roots are the cap
   if (!d_roots || !d_top_out) return fail(c, PMT_E_INVALID_ARG, "top levels: null pointer");
+  if (n_roots <= 4096) {   // always, in practice (one root per rank): one single-block cooperative launch for all levels
+    TAG(c, "k_top_roots_coop", n_roots - ((size_t)1 << cap_height));
+    k_top_roots_coop<<<1, COOP_BLOCK, 0, c->stream>>>(d_roots, n_roots, (size_t)1 << cap_height, d_top_out);
+    CHECK_LAUNCH(c);
+    return PMT_OK;
+  }
   const uint64_t* cur = d_roots;
   uint64_t* out = d_top_out;
   for (size_t m = n_roots / 2; m >= ((size_t)1 << cap_height); m >>= 1) {

@@ -72,6 +72,11 @@ class CudaEngine:
     def sync(self):
         self.ctx.sync()
 
+    def publish(self):
+        """order torch's current stream (the one NCCL synchronises with) after the ctx stream: no host round trip"""
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_stream(torch.cuda.ExternalStream(self.ctx.stream, device=self.device))
+
 
 class ShardedMerkleTree:
     """Result on one rank: its chunk of `digests`, the replicated top digests and the replicated cap."""
@@ -135,7 +140,8 @@ def build_sharded_tree(d_local_leaves, n_total, cap_height, engine, group=None):
         engine.sync()
         return ShardedMerkleTree(n_total, width, cap_height, 1, 0, d_digests, None, None, d_local_cap)
     gathered = torch.empty((world * d_local_cap.shape[0], 4), dtype=d_local_cap.dtype, device=d_local_cap.device)
-    engine.sync()  # the local cap must be complete before NCCL (a different stream) reads it
+    # the local cap must be complete before NCCL (a different stream) reads it
+    engine.publish() if hasattr(engine, "publish") else engine.sync()
     dist.all_gather_into_tensor(gathered, d_local_cap.contiguous(), group=group)
     if cap_height >= g:
         return ShardedMerkleTree(n_total, width, cap_height, world, rank, d_digests, None, None, gathered)
@@ -143,3 +149,198 @@ def build_sharded_tree(d_local_leaves, n_total, cap_height, engine, group=None):
     engine.sync()
     ncap = 1 << cap_height
     return ShardedMerkleTree(n_total, width, cap_height, world, rank, d_digests, gathered, d_top, d_top[d_top.shape[0] - ncap:])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Subtree-sharded MMR (/root/reference/src/mmr/merkle_mountain_ranges.rs)
+# ---------------------------------------------------------------------------------------------------------------------
+def mmr_size(n_leaves):
+    return 2 * n_leaves - bin(n_leaves).count("1")
+
+
+def mmr_pos(level, k):
+    """post-order position of node (level, k) in `elements` (closed form of add_leaf, :89-120)."""
+    last = ((k + 1) << level) - 1
+    return 2 * last - bin(last).count("1") + level
+
+
+def _cuda_mmr_engine_methods():
+    # CudaEngine grows the three MMR calls the sharded form needs; kept here so the plonky2-tree engine above stays small
+    from . import hasher, mmr as mmr_mod
+
+    def new_mmr(self):
+        return mmr_mod.MMR(self.ctx)
+
+    def hash_or_noop(self, felts):
+        return hasher.hash_or_noop(np.asarray(felts, dtype=np.uint64).reshape(1, -1), self.ctx)[0]
+
+    CudaEngine.new_mmr = new_mmr
+    CudaEngine.hash_or_noop = hash_or_noop
+
+
+_cuda_mmr_engine_methods()
+
+
+class ShardedMMR:
+    """One rank's part of an MMR over n leaves, G = world size (a power of two).
+
+    Plan (mmr_shard_plan): every set bit 2^b >= G of n is one mountain, cut into G equal perfect sub-mountains of
+    m_i = 2^b / G leaves, one per rank ("round" i); the bits below G (< G leaves in total) are the tail, kept by the last
+    rank.  So rank r owns the leaves  [S_i + r m_i, S_i + (r + 1) m_i)  of every round (S_i = leaves before round i) --
+    perfectly balanced for any n -- and its local MMR over those leaves, fed in round order, has exactly these
+    sub-mountains as its own mountains (m_1 > m_2 > ...): ONE batch append builds them all.
+
+      local      the rank's MMR; sub-mountain i is the contiguous slice of the global post-order `elements` that starts at
+                 mmr_size(S_i + r m_i)  (popcounts add: S_i, r m_i and the local index occupy disjoint bit ranges)
+      rounds     per round: m_i, the G gathered sub-mountain roots and the log2 G levels above them (replicated;
+                 global positions mmr_pos(level, S_i / 2^level + k))
+      tail       MMR over the last < G leaves (last rank only)
+      peaks      global get_peaks(): one per round, then the tail's (replicated)
+    """
+
+    def __init__(self, n_total, world, rank, plan, local, rounds, tail, peaks, engine):
+        self.n_total, self.world, self.rank, self.plan = n_total, world, rank, plan
+        self.local, self.rounds, self.tail, self.peaks, self.engine = local, rounds, tail, peaks, engine
+
+    def __len__(self):
+        return mmr_size(self.n_total)
+
+    def get_peaks(self):
+        return self.peaks
+
+    def bagging_the_peaks(self):
+        """merkle_mountain_ranges.rs:122-127 on the replicated peaks: the same digest on every rank."""
+        return self.engine.hash_or_noop(self.peaks.reshape(-1))
+
+    def locate(self, normal_index):
+        """-> (rank, round or None for the tail, index local to that rank's MMR / tail MMR)."""
+        start, before = 0, 0
+        for i, m in enumerate(self.plan[0]):
+            if normal_index < start + self.world * m:
+                r, x = divmod(normal_index - start, m)
+                return r, i, before + x
+            start += self.world * m
+            before += m
+        if normal_index >= self.n_total:
+            raise IndexError("leaf index out of range")
+        return self.world - 1, None, normal_index - start
+
+    def owner(self, normal_index):
+        return self.locate(normal_index)[0]
+
+    def get_proof_normal_index(self, normal_index):
+        """merkle_mountain_ranges.rs:203-223 for a leaf this rank owns -> MMR_proof (same fields as the reference)."""
+        from .mmr import MMR_proof
+        r, rnd, x = self.locate(normal_index)
+        if r != self.rank:
+            raise IndexError("leaf %d lives on rank %d" % (normal_index, r))
+        src = self.tail if rnd is None else self.local
+        sib, left, ln = src.prove_batch([x])
+        path = [(sib[0, j].copy(), bool(left[0, j])) for j in range(int(ln[0]))]
+        if rnd is not None:
+            m, roots, top = self.rounds[rnd]
+            k = self.rank                       # index of the sub-mountain among the round's G roots
+            level_nodes, pos = roots, 0
+            for _ in range(log2_strict(self.world)):
+                path.append((np.array(level_nodes[k ^ 1], dtype=np.uint64), bool(k & 1)))
+                cnt = level_nodes.shape[0] // 2
+                level_nodes = top[pos:pos + cnt]
+                pos += cnt
+                k >>= 1
+        return MMR_proof(len(self), path, self.peaks)
+
+    def assemble_global(self, gathered_local, tail_elements):
+        """host-side helper (tests / small MMRs): the reference's full `elements` from every rank's local elements."""
+        out = np.zeros((len(self), 4), np.uint64)
+        start, before = 0, 0     # global leaves / local leaves before the round
+        for m, roots, top in self.rounds:
+            lg_m = log2_strict(m)
+            for r, chunk in enumerate(gathered_local):
+                src = mmr_size(before)
+                dst = mmr_size(start + r * m)
+                out[dst:dst + 2 * m - 1] = chunk[src:src + 2 * m - 1]
+            pos, cnt, level = 0, self.world // 2, lg_m + 1
+            while cnt >= 1:
+                for k in range(cnt):
+                    out[mmr_pos(level, (start >> level) + k)] = top[pos + k]
+                pos += cnt
+                cnt //= 2
+                level += 1
+            start += self.world * m
+            before += m
+        if tail_elements is not None and tail_elements.shape[0]:
+            off = mmr_size(start)
+            out[off:off + tail_elements.shape[0]] = tail_elements
+        return out
+
+
+def mmr_shard_plan(n_total, world):
+    """-> ([m_1, m_2, ...], t): sub-mountain sizes per round (decreasing powers of two) and the tail length (< world)."""
+    log2_strict(world)
+    ms, rest = [], n_total
+    while rest >= world:
+        m = 1 << ((rest // world).bit_length() - 1)
+        ms.append(m)
+        rest -= world * m
+    return ms, rest
+
+
+def mmr_shard_ranges(n_total, world, rank):
+    """global leaf ranges [(start, count), ...] that `rank` owns, in the order it must feed them to build_sharded_mmr."""
+    ms, t = mmr_shard_plan(n_total, world)
+    out, start = [], 0
+    for m in ms:
+        out.append((start + rank * m, m))
+        start += world * m
+    if t and rank == world - 1:
+        out.append((start, t))
+    return out
+
+
+def build_sharded_mmr(d_local_leaves, n_total, engine, group=None):
+    """Collective over `group`: rank r passes the leaves of mmr_shard_ranges(n_total, world, r), concatenated, as single
+    felts.  Equivalent to n_total calls of MMR::add_leaf (:89-120) on one machine."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    ms, t = mmr_shard_plan(n_total, world)
+    n_main = sum(ms)
+    want = n_main + (t if rank == world - 1 else 0)
+    d_local_leaves = d_local_leaves.reshape(-1)
+    if d_local_leaves.numel() != want:
+        raise ValueError("rank %d: expected %d leaves, got %d" % (rank, want, d_local_leaves.numel()))
+    dev = d_local_leaves.device
+    local = engine.new_mmr()
+    if n_main:
+        local.extend_dev(d_local_leaves[:n_main])
+    k = len(ms)
+    my_roots = torch.zeros((max(k, 1), 4), dtype=torch.int64, device=dev)
+    if k:
+        my_roots.copy_(torch.from_numpy(local.get_peaks().view(np.int64)))
+    tail = None
+    n_tail_peaks = bin(t).count("1")
+    tail_peaks = torch.zeros((max(n_tail_peaks, 1), 4), dtype=torch.int64, device=dev)
+    if t and rank == world - 1:
+        tail = engine.new_mmr()
+        tail.extend_dev(d_local_leaves[n_main:])
+        tail_peaks.copy_(torch.from_numpy(tail.get_peaks().view(np.int64)))
+    rounds, big = [], []
+    if world > 1:
+        gathered = torch.empty((world, max(k, 1), 4), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(gathered.view(world * max(k, 1), 4), my_roots.contiguous(), group=group)
+        if t:
+            src = dist.get_global_rank(group, world - 1) if group is not None else world - 1
+            dist.broadcast(tail_peaks, src=src, group=group)
+        for i, m in enumerate(ms):
+            roots = gathered[:, i, :].contiguous()
+            top = engine.top_levels(roots, 0)
+            engine.sync()
+            top_h = top.cpu().numpy().view(np.uint64)
+            rounds.append((m, roots.cpu().numpy().view(np.uint64), top_h))
+            big.append(top_h[-1:])
+    else:
+        roots_h = my_roots.cpu().numpy().view(np.uint64)
+        for i, m in enumerate(ms):
+            rounds.append((m, roots_h[i:i + 1], np.zeros((0, 4), np.uint64)))
+            big.append(roots_h[i:i + 1])
+    peaks = np.concatenate(big + [tail_peaks.cpu().numpy().view(np.uint64)[:n_tail_peaks]], axis=0)
+    return ShardedMMR(n_total, world, rank, (ms, t), local, rounds, tail, peaks, engine)

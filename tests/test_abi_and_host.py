@@ -108,6 +108,50 @@ for lg, w, h in [(6, 4, 0), (5, 9, 1), (5, 135, 3)]:
     full = t.assemble_global([x.numpy().view(np.uint64) for x in chunks])
     assert np.array_equal(full, odg), (lg, w, h)
     assert t.local_offset() == (0 if rank == 0 else [i for i in range(full.shape[0]) if np.array_equal(full[i], chunks[1][0].numpy().view(np.uint64))][0])
+
+# ---- sharded MMR: balanced rounds + tail, elements / peaks / bag / proofs against the sequential add_leaf oracle --------
+class OracleMMR:          # TEST DOUBLE with the interface of plonky2_merkle_trees_b200.mmr.MMR
+    def __init__(self): self.elements = np.zeros((0, 4), np.uint64); self.n_leaves = 0
+    def extend_dev(self, t):
+        x = t.numpy().view(np.uint64).reshape(-1)
+        self.elements = orc.mmr_extend(self.elements if self.n_leaves else None, x); self.n_leaves += x.size
+    def get_peaks(self): return orc.mmr_peaks(self.elements)
+    def prove_batch(self, idx):
+        sib = np.zeros((len(idx), 32, 4), np.uint64); left = np.zeros((len(idx), 32), np.uint8); ln = np.zeros(len(idx), np.uint32)
+        for q, i in enumerate(idx):
+            s_, l_ = orc.mmr_subtree_proof(self.elements, orc.mmr_index(int(i)))
+            sib[q, :len(l_)] = s_; left[q, :len(l_)] = l_; ln[q] = len(l_)
+        return sib, left, ln
+OracleEngine.new_mmr = lambda self: OracleMMR()
+OracleEngine.hash_or_noop = lambda self, felts: orc.hash_or_noop(np.asarray(felts, dtype=np.uint64))
+
+for n in [2, 3, 8, 13, 31, 64, 77, 100, 255]:
+    leaves = splitmix_felts(1000 + n, n)
+    mine = np.concatenate([leaves[a:a + c] for a, c in sharded.mmr_shard_ranges(n, 2, rank)]) if sharded.mmr_shard_ranges(n, 2, rank) else np.zeros(0, np.uint64)
+    sm = sharded.build_sharded_mmr(torch.from_numpy(mine.view(np.int64)), n, OracleEngine())
+    want = orc.mmr_extend(None, leaves)
+    assert len(sm) == want.shape[0], n
+    assert np.array_equal(sm.get_peaks(), orc.mmr_peaks(want)), n
+    assert np.array_equal(sm.bagging_the_peaks(), orc.mmr_bag(want)), n
+    loc = torch.from_numpy(np.ascontiguousarray(sm.local.elements).view(np.int64))
+    sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(2)]
+    dist.all_gather(sizes, torch.tensor([loc.shape[0]]))
+    assert sizes[0].item() == sizes[1].item(), "rounds are balanced"
+    chunks = [torch.empty_like(loc) for _ in range(2)]
+    if loc.numel(): dist.all_gather(chunks, loc)
+    tail_el = sm.tail.elements if sm.tail is not None else None
+    if rank == 1:   # the last rank owns the tail and can assemble everything
+        full = sm.assemble_global([c.numpy().view(np.uint64) for c in chunks], tail_el)
+        assert np.array_equal(full, want), n
+    root = orc.mmr_bag(want)
+    for i in range(n):
+        if sm.owner(i) != rank: continue
+        pr = sm.get_proof_normal_index(i)
+        es, el = orc.mmr_subtree_proof(want, orc.mmr_index(i))
+        assert pr.mmr_size == want.shape[0] and len(pr.merkle_proof) == len(el), (n, i)
+        for (d, on_left), ed, eo in zip(pr.merkle_proof, es, el):
+            assert np.array_equal(d, ed) and bool(on_left) == bool(eo), (n, i)
+        assert orc.mmr_verify(leaves[i], root, np.array([d for d, _ in pr.merkle_proof]).reshape(-1, 4), [int(b) for _, b in pr.merkle_proof], pr.peaks) == 1
 dist.destroy_process_group()
 print("rank", rank, "ok")
 '''

@@ -366,6 +366,41 @@ def test_sharded_virtual_ranks(ctx, api, oracle, lg, w, h, G):
     assert np.array_equal(t.assemble_global(chunks), odg)
 
 
+@pytest.mark.parametrize("n_roots,h", [(2, 0), (2, 1), (8, 0), (8, 2), (64, 0), (1024, 3), (4096, 0), (8192, 1)])
+def test_top_levels_above_gathered_roots(ctx, oracle, n_roots, h):
+    """pmt_top_levels_dev: single cooperative launch up to 4096 roots, one launch per level beyond that."""
+    from plonky2_merkle_trees_b200 import sharded
+    from plonky2_merkle_trees_b200.device import to_device, to_host
+    roots = splitmix_felts(n_roots + h, n_roots * 4).reshape(n_roots, 4)
+    eng = sharded.CudaEngine(ctx)
+    d_top = eng.top_levels(to_device(roots, eng.device), h)
+    eng.sync()
+    got = to_host(d_top)
+    cur, want = roots, []
+    while cur.shape[0] > (1 << h):
+        cur = oracle.two_to_one_batch(cur[0::2], cur[1::2])
+        want.append(cur)
+    want = np.concatenate(want) if want else np.zeros((0, 4), np.uint64)
+    assert got.shape == want.shape and np.array_equal(got, want)
+
+
+def test_sharded_mmr_virtual_world_of_one(ctx, api, oracle):
+    """build_sharded_mmr without a process group (world 1): rounds = the set bits of n, no tail; elements, peaks, bag and
+    proofs against the sequential add_leaf oracle.  (world > 1: tests/test_abi_and_host.py on gloo, tools/multigpu_check.py)"""
+    from plonky2_merkle_trees_b200 import sharded
+    from plonky2_merkle_trees_b200.device import to_device
+    eng = sharded.CudaEngine(ctx)
+    for n in (1, 2, 77, 1000, 4097):
+        leaves = splitmix_felts(n, n)
+        sm = sharded.build_sharded_mmr(to_device(leaves, eng.device), n, eng)
+        want = oracle.mmr_extend(None, leaves)
+        assert np.array_equal(sm.assemble_global([sm.local.elements], None), want)
+        assert np.array_equal(sm.get_peaks(), oracle.mmr_peaks(want))
+        assert np.array_equal(sm.bagging_the_peaks(), oracle.mmr_bag(want))
+        for i in {0, n // 2, n - 1}:
+            assert sm.get_proof_normal_index(i).verify(int(leaves[i]), sm.bagging_the_peaks(), ctx)
+
+
 # ---- stream ordering between torch and the ctx stream ---------------------------------------------------------------
 def test_dev_entry_points_wait_for_torch_stream(api, ctx, oracle):
     """Leaves produced by torch kernels on torch's current stream, handed to a *_dev entry point with no host sync in

@@ -51,6 +51,40 @@ def main():
             ok_all &= ok
             print(json.dumps({"check": "sharded_vs_single", "world": world, "log2_n": lg, "width": w, "cap_height": h,
                               "digests": int(got.shape[0]), "ok": ok}), flush=True)
+    # ---- sharded MMR (balanced rounds + tail) against one MMR built on rank 0's GPU ------------------------------------
+    from plonky2_merkle_trees_b200 import mmr
+    for n in [1 << 14, (1 << 14) - 1, 100100, 77, world]:
+        leaves = bench.splitmix_numpy(7, n)
+        rngs = sharded.mmr_shard_ranges(n, world, rank)
+        mine = np.concatenate([leaves[a:a + c] for a, c in rngs]) if rngs else np.zeros(0, np.uint64)
+        d_mine = torch.from_numpy(mine.view(np.int64)).to(dev)
+        sm = sharded.build_sharded_mmr(d_mine, n, eng)
+        loc = torch.from_numpy(np.ascontiguousarray(sm.local.elements).view(np.int64)).to(dev)
+        chunks = [torch.empty_like(loc) for _ in range(world)]
+        if loc.numel():
+            dist.all_gather(chunks, loc)
+        tail_len = torch.tensor([0 if sm.tail is None else sm.tail.elements.shape[0]], device=dev)
+        dist.broadcast(tail_len, world - 1)
+        tail_el = torch.zeros((int(tail_len.item()), 4), dtype=torch.int64, device=dev)
+        if sm.tail is not None:
+            tail_el.copy_(torch.from_numpy(sm.tail.elements.view(np.int64)))
+        if tail_el.numel():
+            dist.broadcast(tail_el, world - 1)
+        # every rank proves + verifies (on its GPU) a few leaves it owns
+        own = [i for i in range(0, n, max(1, n // 64)) if sm.owner(i) == rank][:16]
+        bag = sm.bagging_the_peaks()
+        ok_proofs = all(sm.get_proof_normal_index(i).verify(int(leaves[i]), bag, ctx) for i in own)
+        okt = torch.tensor([1 if ok_proofs else 0], device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            ref = mmr.MMR.new(ctx)
+            ref.extend(leaves)
+            got = sm.assemble_global([to_host(c) for c in chunks], to_host(tail_el))
+            ok = bool(np.array_equal(got, ref.elements) and np.array_equal(sm.get_peaks(), ref.get_peaks())
+                      and np.array_equal(bag, ref.bagging_the_peaks()) and int(okt.item()) == 1)
+            ok_all &= ok
+            print(json.dumps({"check": "sharded_mmr_vs_single", "world": world, "n_leaves": n, "rounds": len(sm.rounds),
+                              "tail": sm.plan[1], "elements": int(got.shape[0]), "ok": ok}), flush=True)
     flag = torch.tensor([1 if ok_all else 0], device=dev)
     dist.broadcast(flag, 0)
     dist.destroy_process_group()
