@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -607,7 +608,14 @@ int pmt_merkle_tree_build(pmt_ctx* c, const uint64_t* leaves, size_t n, size_t w
   uint64_t* d_leaves = (uint64_t*)a;
   uint64_t* d_dig = (uint64_t*)b; uint64_t* d_cap = d_dig + 4 * n_dig;
   const int L = lg - (int)cap_height;
-  int cb = lg - 4;                 // log2(leaves per chunk): 16 chunks
+  // log2(leaves per chunk): 16 chunks.  The D2H of every digest (1 GiB at 2^24 leaves, 18.9 ms) is the bound; measured
+  // with tools/e2e_bench.py: 8 / 16 / 32 / 64 chunks = 25.0 / 22.1 / 25.9 / 34.3 ms (every chunk adds one latency-bound
+  // subtree tail of ~13 tiny launches); alternating chunks between two compute streams did not help (23.1 ms at 16).
+  int log2_chunks = 4;
+  if (const char* e = getenv("PMT_PIPELINE_LOG2_CHUNKS")) log2_chunks = atoi(e);   // tuning knob (tools/e2e_bench.py)
+  if (log2_chunks < 1) log2_chunks = 1;
+  if (log2_chunks > 10) log2_chunks = 10;
+  int cb = lg - log2_chunks;
   if (cb > L) cb = L;
   if (cb < 12 || n * w * 8 < ((size_t)8 << 20)) {   // small: one shot
     H2D(c, d_leaves, leaves, n * w * 8);
