@@ -91,6 +91,14 @@ int pmt_merkle_tree_build(pmt_ctx* ctx, const uint64_t* leaves, size_t n, size_t
                           uint64_t* digests_out, uint64_t* cap_out);
 int pmt_merkle_tree_build_dev(pmt_ctx* ctx, const uint64_t* d_leaves, size_t n, size_t width, uint32_t cap_height,
                               uint64_t* d_digests, uint64_t* d_cap);
+/* The same tree built straight from the prover's column-major LDE values: what [UPSTREAM] fri/oracle.rs
+ * PolynomialBatch::from_values / from_coeffs feeds to MerkleTree::new inside circuit_data.prove
+ * (/root/reference/src/mmr/mmr_plonky2_verifier.rs:148): leaves = reverse_index_bits(transpose(columns)), i.e.
+ * leaf i = (col_0[rev(i)], ..., col_{w-1}[rev(i)]).  d_columns: w columns of n felts each, column-major.
+ * bit_reverse != 0 applies the index reversal.  d_leaves_out (nullable): the row-major n x w leaves upstream keeps in
+ * MerkleTree.leaves for openings.  The transpose never materialises unless d_leaves_out is given. */
+int pmt_merkle_tree_build_from_columns_dev(pmt_ctx* ctx, const uint64_t* d_columns, size_t n, size_t width, int bit_reverse,
+                                           uint32_t cap_height, uint64_t* d_leaves_out, uint64_t* d_digests, uint64_t* d_cap);
 /* MerkleTree::prove for a batch: siblings_out n_idx * (log2 n - h) digests */
 int pmt_merkle_prove_dev(pmt_ctx* ctx, const uint64_t* d_digests, size_t n, uint32_t cap_height, const uint64_t* d_idx,
                          size_t n_idx, uint64_t* d_siblings_out);

@@ -194,6 +194,42 @@ __global__ void __launch_bounds__(BLOCK) k_leaves(Layout lay, const uint64_t* __
     store_digest(lay.at(0, k0 + i), hash_or_noop(rows + i * w, w));
 }
 
+// level 0 straight from the prover's column-major LDE output ([UPSTREAM plonky2 fri module, PolynomialBatch::from_values /
+// from_coeffs]: leaves = reverse_index_bits(transpose(columns)), i.e. leaf i = (col_0[rev(i)], ..., col_{w-1}[rev(i)])).
+// Thread t reads element t of every column (coalesced) and owns leaf i = rev(t): the transpose and the bit reversal
+// cost one scattered 32-byte digest store per leaf instead of a 1 GiB round trip through a row-major copy.
+// rows_out (optional): the row-major leaves upstream's MerkleTree keeps for openings.
+template <class Layout>
+__global__ void __launch_bounds__(BLOCK) k_leaves_columns(Layout lay, const uint64_t* __restrict__ cols, size_t n, size_t w,
+                                                          int log2n, bool bit_reverse, uint64_t* __restrict__ rows_out) {
+  for (size_t t = (size_t)blockIdx.x * BLOCK + threadIdx.x; t < n; t += (size_t)gridDim.x * BLOCK) {
+    const size_t i = (bit_reverse && log2n > 0) ? (size_t)(__brevll((unsigned long long)t) >> (64 - log2n)) : t;
+    Digest d;
+    if (w <= 4) {   // hash_or_noop: canonicalising copy
+#pragma unroll
+      for (int c = 0; c < 4; c++) d.v[c] = (size_t)c < w ? gl::canonical(cols[(size_t)c * n + t]) : 0ull;
+      if (rows_out)
+        for (size_t c = 0; c < w; c++) rows_out[i * w + c] = cols[c * n + t];
+    } else {
+      uint64_t s[WIDTH];
+#pragma unroll
+      for (int c = 0; c < WIDTH; c++) s[c] = 0;
+      for (size_t off = 0; off < w; off += 8) {
+#pragma unroll
+        for (int c = 0; c < 8; c++)
+          if (off + c < w) {
+            s[c] = cols[(off + c) * n + t];
+            if (rows_out) rows_out[i * w + off + c] = s[c];
+          }
+        permute(s);
+      }
+#pragma unroll
+      for (int c = 0; c < 4; c++) d.v[c] = gl::canonical(s[c]);
+    }
+    store_digest(lay.at(0, i), d);
+  }
+}
+
 // one level: digest(l, k) = two_to_one(children) for k in [k0, k0 + count)
 // PMT_QUAD = 0 (production): one node per thread (poseidon.cuh permute_paired).
 // PMT_QUAD = 1: 32 nodes per warp in the quad layout of poseidon_quad.cuh, MDS layers on the fp64 tensor pipe (DMMA).

@@ -386,6 +386,25 @@ int pmt_merkle_tree_build_dev(pmt_ctx* c, const uint64_t* d_leaves, size_t n, si
   return run_levels(c, lay, 1, L, n / 2);
 }
 
+// MerkleTree::new fed by the prover's column-major LDE values (transpose + reverse_index_bits fused into the leaf kernel)
+int pmt_merkle_tree_build_from_columns_dev(pmt_ctx* c, const uint64_t* d_columns, size_t n, size_t w, int bit_reverse,
+                                           uint32_t cap_height, uint64_t* d_leaves_out, uint64_t* d_digests, uint64_t* d_cap) {
+  if (int rc = bind(c)) return rc;
+  const int lg = log2_strict(n);
+  if (lg < 0) return fail(c, PMT_E_NOT_POW2, "MerkleTree::new: %zu leaves is not a power of two (log2_strict)", n);
+  if ((int)cap_height > lg) return fail(c, PMT_E_RANGE, "MerkleTree::new: cap_height=%u should be at most log2(leaves.len())=%d", cap_height, lg);
+  if (w == 0) return fail(c, PMT_E_INVALID_ARG, "MerkleTree::new: zero-width leaves");
+  if (!d_columns || !d_cap || (!d_digests && (size_t)lg > cap_height)) return fail(c, PMT_E_INVALID_ARG, "MerkleTree::new: null pointer");
+  const int L = lg - (int)cap_height;
+  Plonky2 lay{d_digests, d_cap, L};
+  TAG(c, "k_leaves_columns", w <= 4 ? 0 : n * ((w + 7) / 8));
+  k_leaves_columns<Plonky2><<<w <= 4 ? grid_copy(c, n) : grid_for(c, n), BLOCK, 0, c->stream>>>(lay, d_columns, n, w, lg, bit_reverse != 0,
+                                                                                             d_leaves_out);
+  CHECK_LAUNCH(c);
+  if (L == 0) return PMT_OK;
+  return run_levels(c, lay, 1, L, n / 2);
+}
+
 int pmt_merkle_prove_dev(pmt_ctx* c, const uint64_t* d_digests, size_t n, uint32_t cap_height, const uint64_t* d_idx,
                          size_t n_idx, uint64_t* d_out) {
   if (int rc = bind(c)) return rc;

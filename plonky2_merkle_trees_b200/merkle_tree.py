@@ -44,6 +44,28 @@ class MerkleTree:
         ctx.sync()
         return cls(ctx, n, w, cap_height, d_leaves, d_digests, d_cap)
 
+    @classmethod
+    def from_columns_dev(cls, d_columns, cap_height, bit_reverse=True, keep_leaves=False, ctx=None):
+        """The commitment the prover builds from its LDE values ([UPSTREAM] plonky2 fri module, PolynomialBatch::from_values):
+        d_columns is (width, n) -- one row per polynomial, column-major for the tree -- and the leaves are
+        reverse_index_bits(transpose(d_columns)).  The transpose + bit reversal are fused into the leaf kernel; the row-major
+        `leaves` are only materialised when keep_leaves is set."""
+        ctx = ctx or _lib.default_context()
+        w, n = d_columns.shape
+        lg = n.bit_length() - 1
+        if n == 0 or n & (n - 1):
+            raise PmtError(_lib.PMT_E_NOT_POW2, "log2_strict: %d leaves is not a power of two" % n)
+        if cap_height > lg:
+            raise PmtError(_lib.PMT_E_RANGE, "cap_height=%d should be at most log2(leaves.len())=%d" % (cap_height, lg))
+        ncap = 1 << cap_height
+        d_digests = dev_u64((2 * (n - ncap), 4), d_columns.device)
+        d_cap = dev_u64((ncap, 4), d_columns.device)
+        d_leaves = dev_u64((n, w), d_columns.device) if keep_leaves else None
+        ctx.call("pmt_merkle_tree_build_from_columns_dev", dptr(d_columns.contiguous()), n, w, 1 if bit_reverse else 0, cap_height,
+                 dptr(d_leaves) if keep_leaves else None, dptr(d_digests), dptr(d_cap))
+        ctx.sync()
+        return cls(ctx, n, w, cap_height, d_leaves, d_digests, d_cap)
+
     @property
     def leaves(self):
         return to_host(self.d_leaves)

@@ -401,6 +401,50 @@ def test_sharded_mmr_virtual_world_of_one(ctx, api, oracle):
             assert sm.get_proof_normal_index(i).verify(int(leaves[i]), sm.bagging_the_peaks(), ctx)
 
 
+# ---- tree fed by the prover's column-major LDE values (SURVEY 8(f) N1) -----------------------------------------------------
+def _reverse_index_bits(rows):
+    """[UPSTREAM] plonky2_util::reverse_index_bits: out[i] = in[bit_reverse(i, log2 n)]"""
+    n = rows.shape[0]
+    lg = n.bit_length() - 1
+    idx = np.array([int(format(i, "0%db" % lg)[::-1], 2) if lg else 0 for i in range(n)], dtype=np.int64)
+    return rows[idx]
+
+
+@pytest.mark.parametrize("lg,w,h,rev", [(1, 1, 0, True), (4, 4, 0, True), (6, 5, 2, True), (8, 135, 4, True), (8, 135, 4, False),
+                                        (10, 9, 0, True), (12, 4, 3, True), (5, 3, 5, True), (0, 7, 0, True)])
+def test_tree_from_columns_equals_transpose_then_build(ctx, api, oracle, lg, w, h, rev):
+    from plonky2_merkle_trees_b200.device import to_device
+    n = 1 << lg
+    cols = splitmix_felts(97 * lg + w, w * n).reshape(w, n)
+    cols[0, 0] = np.uint64(2**64 - 1)          # non-canonical inputs are canonicalised in the no-op leaf rule
+    if n > 1:
+        cols[w - 1, n - 1] = np.uint64(P)
+    rows = np.ascontiguousarray(cols.T)
+    if rev:
+        rows = _reverse_index_bits(rows)
+    dg, cap = oracle.merkle_tree_new(rows, h, threads=2, fast=True)
+    t = api.mt.MerkleTree.from_columns_dev(to_device(cols, "cuda:0"), h, bit_reverse=rev, keep_leaves=True, ctx=ctx)
+    assert np.array_equal(t.cap, cap)
+    assert np.array_equal(t.digests, dg)
+    assert np.array_equal(t.leaves, rows)      # MerkleTree.leaves as upstream keeps them (raw felts, row-major)
+    t2 = api.mt.MerkleTree.from_columns_dev(to_device(cols, "cuda:0"), h, bit_reverse=rev, keep_leaves=False, ctx=ctx)
+    assert np.array_equal(t2.digests, dg) and np.array_equal(t2.cap, cap)
+    if lg > h:                                 # openings verify against the cap
+        i = n // 3
+        assert api.mt.verify_merkle_proof_to_cap(rows[i], i, t.cap, h, t.prove(i), ctx)
+
+
+def test_tree_from_columns_errors(ctx, api):
+    from plonky2_merkle_trees_b200 import _lib
+    from plonky2_merkle_trees_b200.device import to_device
+    with pytest.raises(_lib.PmtError) as e:
+        api.mt.MerkleTree.from_columns_dev(to_device(np.zeros((4, 6), np.uint64), "cuda:0"), 0, ctx=ctx)
+    assert e.value.code == _lib.PMT_E_NOT_POW2
+    with pytest.raises(_lib.PmtError) as e:
+        api.mt.MerkleTree.from_columns_dev(to_device(np.zeros((4, 8), np.uint64), "cuda:0"), 4, ctx=ctx)
+    assert e.value.code == _lib.PMT_E_RANGE
+
+
 # ---- stream ordering between torch and the ctx stream ---------------------------------------------------------------
 def test_dev_entry_points_wait_for_torch_stream(api, ctx, oracle):
     """Leaves produced by torch kernels on torch's current stream, handed to a *_dev entry point with no host sync in

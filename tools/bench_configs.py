@@ -90,7 +90,20 @@ def main():
         prof = ctx.profile_read(); ctx.profile(False)
         emit("C4", "FRI-style 2^20 rows x 135 felts, cap 4 (1 GPU)", n, "leaves", b, m, 17 * n + n - 16)
         print(json.dumps({"config": "C4-kernels", "kernels": prof}))
-        del d_leaves, d_dig
+        # the same commitment fed by the prover's column-major LDE values (transpose + reverse_index_bits fused into the
+        # leaf kernel) against transposing first with torch and then building
+        d_cols = d_leaves.t().contiguous()          # (w, n)
+        b2, m2 = timed(ctx, lambda: ctx.call("pmt_merkle_tree_build_from_columns_dev", dptr(d_cols), n, w, 1, h, None, dptr(d_dig), dptr(d_cap)),
+                       reps=3, warm=1)
+        emit("C4-columns", "same tree from column-major LDE values, fused transpose + bit reversal", n, "leaves", b2, m2, 17 * n + n - 16)
+        rev = torch.tensor([int(format(i, "020b")[::-1], 2) for i in range(n)], device=dev)
+
+        def transpose_then_build():
+            rows = d_cols.t().contiguous()[rev]     # what a prover without the fused feed does: 2 x 1 GiB round trips
+            ctx.call("pmt_merkle_tree_build_dev", dptr(rows), n, w, h, dptr(d_dig), dptr(d_cap))
+        b3, m3 = timed(ctx, transpose_then_build, reps=3, warm=1)
+        emit("C4-transpose-first", "torch transpose + index_select, then pmt_merkle_tree_build_dev", n, "leaves", b3, m3, 17 * n + n - 16)
+        del d_leaves, d_dig, d_cols
     if "C5" in only:
         n, w = 1 << 28, 4
         torch.cuda.empty_cache()
