@@ -689,6 +689,11 @@ int pmt_merkle_tree_build(pmt_ctx* c, const uint64_t* leaves, size_t n, size_t w
   return PMT_OK;
 }
 
+// Host-buffer batch append.  Only the old PEAKS are uploaded (a new node's left child is either new or an old peak), and
+// large batches run as a 3-stage pipeline over aligned power-of-two chunks: appending chunk i to the MMR of the leaves
+// before it creates exactly the elements [mmr_size(n0 + i*chunk), mmr_size(n0 + (i+1)*chunk)) -- the chunk's perfect
+// sub-mountain followed by every ancestor it completes -- ONE contiguous slice of the post-order array, so it is
+// downloaded while the next chunk is hashed and the one after that is uploaded.
 int pmt_mmr_extend(pmt_ctx* c, uint64_t* elements, size_t n0, const uint64_t* new_leaves, size_t m) {
   if (int rc = bind(c)) return rc;
   if (m == 0) return PMT_OK;
@@ -698,10 +703,56 @@ int pmt_mmr_extend(pmt_ctx* c, uint64_t* elements, size_t n0, const uint64_t* ne
   void *a, *b;
   if (int rc = arena_get(c, 0, m * 8, &a)) return rc;
   if (int rc = arena_get(c, 1, s1 * 32, &b)) return rc;
-  H2D(c, a, new_leaves, m * 8);
-  if (s0) H2D(c, b, elements, s0 * 32);  // the old peaks (and only they) are read; uploading the prefix keeps it simple
-  if (int rc = pmt_mmr_extend_dev(c, (uint64_t*)b, n0, (uint64_t*)a, m)) return rc;
-  D2H(c, elements + 4 * s0, (uint64_t*)b + 4 * s0, (s1 - s0) * 32);
+  uint64_t* d_leaves = (uint64_t*)a;
+  uint64_t* d_el = (uint64_t*)b;
+  // old peaks: one per set bit of n0, at the last position of its mountain (get_peaks, :179-200)
+  {
+    size_t base = 0;
+    for (int bit = 63; bit >= 0; bit--)
+      if ((n0 >> bit) & 1) {
+        base += (size_t)1 << bit;
+        const size_t pos = pmt_mmr_size(base) - 1;
+        H2D(c, d_el + 4 * pos, elements + 4 * pos, 32);
+      }
+  }
+  int lgm = 0;
+  while (((size_t)2 << lgm) <= m) lgm++;                 // floor(log2 m)
+  const size_t chunk = lgm >= 20 ? (size_t)1 << (lgm - 4) : m;   // 16 .. 31 chunks for big batches, else one shot
+  if (chunk >= m) {
+    H2D(c, d_leaves, new_leaves, m * 8);
+    if (int rc = pmt_mmr_extend_dev(c, d_el, n0, d_leaves, m)) return rc;
+    D2H(c, elements + 4 * s0, d_el + 4 * s0, (s1 - s0) * 32);
+    FINISH(c);
+    return PMT_OK;
+  }
+  // first piece: up to the next multiple of `chunk` so that every later piece is an aligned perfect sub-mountain
+  const size_t chunks = (m + chunk - 1) / chunk + 1;
+  if (!c->copy_in) CU(c, cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
+  if (!c->copy_out) CU(c, cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
+  while (c->ev.size() < 2 * chunks + 2) {
+    cudaEvent_t e;
+    CU(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->ev.push_back(e);
+  }
+  CU(c, cudaEventRecord(c->ev[2 * chunks], c->stream));   // the peaks above (and earlier arena users) come first
+  CU(c, cudaStreamWaitEvent(c->copy_in, c->ev[2 * chunks], 0));
+  CU(c, cudaStreamWaitEvent(c->copy_out, c->ev[2 * chunks], 0));
+  size_t done = 0, i = 0;
+  while (done < m) {
+    size_t len = chunk - ((n0 + done) & (chunk - 1));     // to the next chunk boundary
+    if (len > m - done) len = m - done;
+    CU(c, cudaMemcpyAsync(d_leaves + done, new_leaves + done, len * 8, cudaMemcpyHostToDevice, c->copy_in));
+    CU(c, cudaEventRecord(c->ev[2 * i], c->copy_in));
+    CU(c, cudaStreamWaitEvent(c->stream, c->ev[2 * i], 0));
+    if (int rc = pmt_mmr_extend_dev(c, d_el, n0 + done, d_leaves + done, len)) return rc;
+    CU(c, cudaEventRecord(c->ev[2 * i + 1], c->stream));
+    CU(c, cudaStreamWaitEvent(c->copy_out, c->ev[2 * i + 1], 0));
+    const size_t p0 = pmt_mmr_size(n0 + done), p1 = pmt_mmr_size(n0 + done + len);
+    CU(c, cudaMemcpyAsync(elements + 4 * p0, d_el + 4 * p0, (p1 - p0) * 32, cudaMemcpyDeviceToHost, c->copy_out));
+    done += len;
+    i++;
+  }
+  CU(c, cudaStreamSynchronize(c->copy_out));
   FINISH(c);
   return PMT_OK;
 }

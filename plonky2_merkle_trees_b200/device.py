@@ -32,5 +32,5 @@ def order_after_torch(ctx, device=None):
     guaranteed to be complete when a libpmt kernel reads it."""
     dev = torch.device("cuda", ctx.device) if device is None else device
     cur = torch.cuda.current_stream(dev)
-    if cur.cuda_stream != (ctx.stream or 0):
+    if cur.cuda_stream != (ctx.stream or 0) and not cur.query():   # query(): nothing pending -> nothing to wait for
         torch.cuda.ExternalStream(ctx.stream, device=dev).wait_stream(cur)

@@ -314,6 +314,31 @@ def test_mmr_host_buffer_abi(ctx, oracle):
     assert lib.pmt_mmr_index(15) == 26
 
 
+@pytest.mark.parametrize("n0,m", [(0, (1 << 20) + 777), (12345, 1 << 20), (3 * (1 << 16), (1 << 21) - 5)])
+def test_mmr_host_buffer_pipeline(ctx, api, oracle, n0, m):
+    """pmt_mmr_extend for big batches: old peaks only are uploaded, and the append runs as a pipeline of aligned chunks,
+    each downloading one contiguous slice of `elements`.  Against the device-resident path (tied to the oracle above) for
+    every element, and against the sequential add_leaf oracle for the first 2^17 + n0 leaves."""
+    from plonky2_merkle_trees_b200._lib import ptr
+    from plonky2_merkle_trees_b200.device import to_device
+    lib = ctx.lib
+    leaves = splitmix_felts(n0 + m, n0 + m)
+    el = np.zeros((lib.pmt_mmr_size(n0 + m), 4), np.uint64)
+    if n0:
+        ctx.call("pmt_mmr_extend", ptr(el), 0, ptr(leaves[:n0]), n0)
+    before = el[:lib.pmt_mmr_size(n0)].copy()
+    ctx.call("pmt_mmr_extend", ptr(el), n0, ptr(leaves[n0:]), m)
+    assert np.array_equal(el[:before.shape[0]], before)            # the old elements are never written
+    ref = api.mmr.MMR.new(ctx)
+    ref.extend_dev(to_device(leaves, "cuda:0"))
+    assert np.array_equal(el, ref.elements)
+    k = n0 + (1 << 17)
+    want = oracle.mmr_extend(None, leaves[:k])
+    # elements of the first k leaves that are not touched by later leaves = everything below the last peak merge: compare
+    # the prefix that the k-leaf MMR and the full MMR share (all of it: post-order is append-only)
+    assert np.array_equal(el[:want.shape[0]], want)
+
+
 def test_mmr_2p20_against_tree(api):
     """an MMR with 2^20 leaves is one mountain: its nodes are the simple tree's levels in post-order (size check)."""
     n = 1 << 20

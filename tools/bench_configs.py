@@ -60,6 +60,21 @@ def main():
         d_el = dev_u64((size, 4), dev)
         b, m = timed(ctx, lambda: ctx.call("pmt_mmr_extend_dev", dptr(d_el), 0, dptr(d_leaves), n), reps=3, warm=1)
         emit(tag, "MMR extend by %d single-felt leaves from empty" % n, n, "leaves", b, m, n - bin(n).count("1"))
+        if tag == "C3":   # end to end through host buffers: pinned leaves up, every element down (pipelined)
+            import time
+            import ctypes as C
+            from plonky2_merkle_trees_b200._lib import u64p
+            h_leaves = torch.empty(n, dtype=torch.int64).pin_memory(); h_leaves.copy_(d_leaves)
+            h_el = torch.empty((size, 4), dtype=torch.int64).pin_memory()
+            ts = []
+            for _ in range(4):
+                ctx.sync(); t0 = time.perf_counter()
+                ctx.call("pmt_mmr_extend", C.cast(h_el.data_ptr(), u64p), 0, C.cast(h_leaves.data_ptr(), u64p), n)
+                ts.append(1e3 * (time.perf_counter() - t0))
+            ok = bool(torch.equal(h_el, d_el.cpu()))
+            emit("C3-e2e", "MMR extend through HOST buffers (128 MiB up, 1 GiB down), equals device path: %s" % ok, n, "leaves",
+                 min(ts[1:]), sorted(ts[1:])[1], n - bin(n).count("1"))
+            del h_leaves, h_el
         d_root = dev_u64((4,), dev)
         b, m = timed(ctx, lambda: ctx.call("pmt_mmr_bag_dev", dptr(d_el), n, dptr(d_root)))
         emit(tag + "-bag", "peaks + bag (%d peaks)" % bin(n).count("1"), 1, "bags", b, m, (4 * bin(n).count("1") + 7) // 8 if bin(n).count("1") > 1 else 0)
