@@ -559,4 +559,84 @@ __global__ void __launch_bounds__(BLOCK) k_mmr_verify(const uint64_t* __restrict
   status[q] = digest_eq(load_digest(bagged), load_digest_canonical(root)) ? 1 : 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// cooperative verification (batches too small to fill the GPU with one thread per proof): 16 lanes fold one path, so a
+// proof of length L costs L x 6.6 us instead of L x 38 us.  Lanes 0..3 of a group carry the running digest.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool group_all(bool pred, unsigned base_lane) {
+  const unsigned b = __ballot_sync(0xffffffffu, pred), mask = 0xFFFFu << base_lane;
+  return (b & mask) == mask;
+}
+// one fold step: v <- two_to_one(sibling, v) if on_left else two_to_one(v, sibling); `sib` points at the sibling digest
+__device__ __forceinline__ uint64_t coop_fold(uint64_t v, const uint64_t* __restrict__ sib, bool on_left, bool active,
+                                              const uint64_t* rc_smem, unsigned g, unsigned base_lane) {
+  const uint64_t moved = gl::pack(__shfl_sync(0xffffffffu, gl::lo32(v), base_lane + ((g - 4) & 15)),
+                                  __shfl_sync(0xffffffffu, gl::hi32(v), base_lane + ((g - 4) & 15)));   // lane g <- lane g - 4
+  uint64_t st = 0;
+  if (on_left) { if (g < 4) st = active ? sib[g] : 0; else if (g < 8) st = moved; }
+  else         { if (g < 4) st = v; else if (g < 8) st = active ? sib[g - 4] : 0; }
+  return poseidon::permute_coop(st, rc_smem, g, base_lane);
+}
+
+// merkle_mountain_ranges.rs:232-252, same contract as k_mmr_verify
+__global__ void __launch_bounds__(COOP_BLOCK) k_mmr_verify_coop(const uint64_t* __restrict__ leaves, size_t n_idx,
+                                                                const uint64_t* __restrict__ sib, const uint8_t* __restrict__ left,
+                                                                const uint32_t* __restrict__ len, const uint64_t* __restrict__ peaks,
+                                                                uint32_t n_peaks, const uint64_t* __restrict__ bagged,
+                                                                const uint64_t* __restrict__ root, int8_t* __restrict__ status) {
+  __shared__ uint64_t rc_smem[WIDTH * (PMT_ROUNDS + 1)];
+  coop_stage_constants(rc_smem);
+  const unsigned g = threadIdx.x & 15, base_lane = threadIdx.x & 16;
+  const size_t q = (size_t)blockIdx.x * COOP_GROUPS + (threadIdx.x >> 4);
+  const bool have = q < n_idx;
+  const uint32_t L = have ? len[q] : 0;
+  const uint32_t Lw = max(L, __shfl_xor_sync(0xffffffffu, L, 16));     // both groups of the warp run the same trip count
+  uint64_t v = (have && g == 0) ? gl::canonical(leaves[q]) : 0ull;     // hash_or_noop(&[leaf]) = [leaf, 0, 0, 0]
+  for (uint32_t j = 0; j < Lw; j++) {
+    const bool act = j < L;
+    const bool on_left = act && left[q * 32 + j] != 0;
+    const uint64_t p = coop_fold(v, sib + 4 * (q * 32 + j), on_left, act, rc_smem, g, base_lane);
+    v = act ? p : v;
+  }
+  v = gl::canonical(v);
+  bool found = false;
+  for (uint32_t k = 0; k < n_peaks; k++) found |= group_all(g >= 4 || v == gl::canonical(peaks[4 * k + g]), base_lane);
+  if (have && g == 0) {
+    if (!found) status[q] = -1;
+    else status[q] = digest_eq(load_digest(bagged), load_digest_canonical(root)) ? 1 : 0;
+  }
+}
+
+// simple_merkle_tree.rs:91-109 / [UPSTREAM hash/merkle_proofs.rs verify_merkle_proof_to_cap], same contract as k_verify_to_cap
+__global__ void __launch_bounds__(COOP_BLOCK) k_verify_to_cap_coop(const uint64_t* __restrict__ rows, size_t w,
+                                                                   const uint64_t* __restrict__ idx, size_t n_idx,
+                                                                   const uint64_t* __restrict__ cap, uint32_t cap_height,
+                                                                   const uint64_t* __restrict__ proofs, size_t path_len,
+                                                                   uint8_t* __restrict__ ok) {
+  __shared__ uint64_t rc_smem[WIDTH * (PMT_ROUNDS + 1)];
+  coop_stage_constants(rc_smem);
+  const unsigned g = threadIdx.x & 15, base_lane = threadIdx.x & 16;
+  const size_t q = (size_t)blockIdx.x * COOP_GROUPS + (threadIdx.x >> 4);
+  const bool have = q < n_idx;
+  const uint64_t* row = rows + (have ? q : 0) * w;
+  uint64_t v = 0;
+  if (w <= 4) {
+    if (have && g < w) v = gl::canonical(row[g]);
+  } else {
+    for (size_t off = 0; off < w; off += 8) {            // overwrite-mode sponge; w is uniform, so is the trip count
+      if (have && g < 8 && off + g < w) v = row[off + g];
+      v = poseidon::permute_coop(v, rc_smem, g, base_lane);
+    }
+  }
+  size_t index = have ? idx[q] : 0;
+  for (size_t j = 0; j < path_len; j++) {
+    v = coop_fold(v, proofs + 4 * ((have ? q : 0) * path_len + j), (index & 1) != 0, have, rc_smem, g, base_lane);
+    index >>= 1;
+  }
+  v = gl::canonical(v);
+  const bool in_cap = index < ((size_t)1 << cap_height);
+  const bool eq = group_all(g >= 4 || (in_cap && have && v == gl::canonical(cap[4 * index + g])), base_lane);
+  if (have && g == 0) ok[q] = in_cap && eq;
+}
+
 }  // namespace pmt

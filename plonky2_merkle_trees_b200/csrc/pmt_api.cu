@@ -129,6 +129,9 @@ int arena_get(pmt_ctx* c, int slot, size_t bytes, void** out) {
 // cooperative one; per permutation the cooperative form issues 2.4x more instructions, so it only wins while the level
 // is latency-bound: <= 2^13 nodes.
 constexpr size_t COOP_MAX = (size_t)1 << 13;
+// proof batches up to this size are verified 16 lanes per proof (the GPU holds 148 x 8 x 16 = 18 944 such groups at once;
+// beyond that the thread-per-proof kernel's 2.4x lower instruction count wins)
+constexpr size_t COOP_VERIFY_MAX = (size_t)1 << 14;
 constexpr size_t TOP_FUSE = 16;   // levels with <= 16 nodes are fused into one block (k_top_coop)
 
 template <class Layout>
@@ -356,8 +359,15 @@ int pmt_merkle_verify_dev(pmt_ctx* c, const uint64_t* d_rows, size_t w, const ui
   if (n_idx == 0) return PMT_OK;
   if (!d_rows || !d_idx || !d_cap || !d_ok || (!d_proofs && path_len)) return fail(c, PMT_E_INVALID_ARG, "verify: null pointer");
   if (w == 0 || cap_height > 40 || path_len > 63) return fail(c, PMT_E_INVALID_ARG, "verify: bad width / cap_height / path_len");
-  k_verify_to_cap<<<(unsigned)((n_idx + BLOCK - 1) / BLOCK), BLOCK, 0, c->stream>>>(d_rows, w, d_idx, n_idx, d_cap, cap_height,
-                                                                                   d_proofs, path_len, d_ok);
+  if (n_idx <= COOP_VERIFY_MAX) {   // latency-bound batch: 16 lanes per proof
+    TAG(c, "k_verify_to_cap_coop", n_idx * (path_len + (w <= 4 ? 0 : (w + 7) / 8)));
+    k_verify_to_cap_coop<<<(unsigned)((n_idx + COOP_GROUPS - 1) / COOP_GROUPS), COOP_BLOCK, 0, c->stream>>>(
+        d_rows, w, d_idx, n_idx, d_cap, cap_height, d_proofs, path_len, d_ok);
+  } else {
+    TAG(c, "k_verify_to_cap", n_idx * (path_len + (w <= 4 ? 0 : (w + 7) / 8)));
+    k_verify_to_cap<<<(unsigned)((n_idx + BLOCK - 1) / BLOCK), BLOCK, 0, c->stream>>>(d_rows, w, d_idx, n_idx, d_cap, cap_height,
+                                                                                     d_proofs, path_len, d_ok);
+  }
   CHECK_LAUNCH(c);
   return PMT_OK;
 }
@@ -526,8 +536,15 @@ int pmt_mmr_verify_dev(pmt_ctx* c, const uint64_t* d_leaves, size_t n_idx, const
   TAG(c, "k_hash_one_coop", (4 * n_peaks + 7) / 8);
   k_hash_one_coop<<<1, 32, 0, c->stream>>>(d_peaks, (size_t)4 * n_peaks, d_bag);
   CHECK_LAUNCH(c);
-  k_mmr_verify<<<(unsigned)((n_idx + BLOCK - 1) / BLOCK), BLOCK, 0, c->stream>>>(d_leaves, n_idx, d_sib, d_left, d_len, d_peaks,
-                                                                                n_peaks, d_bag, d_root, d_status);
+  if (n_idx <= COOP_VERIFY_MAX) {
+    TAG(c, "k_mmr_verify_coop", n_idx);
+    k_mmr_verify_coop<<<(unsigned)((n_idx + COOP_GROUPS - 1) / COOP_GROUPS), COOP_BLOCK, 0, c->stream>>>(
+        d_leaves, n_idx, d_sib, d_left, d_len, d_peaks, n_peaks, d_bag, d_root, d_status);
+  } else {
+    TAG(c, "k_mmr_verify", n_idx);
+    k_mmr_verify<<<(unsigned)((n_idx + BLOCK - 1) / BLOCK), BLOCK, 0, c->stream>>>(d_leaves, n_idx, d_sib, d_left, d_len, d_peaks,
+                                                                                  n_peaks, d_bag, d_root, d_status);
+  }
   CHECK_LAUNCH(c);
   return PMT_OK;
 }

@@ -362,6 +362,52 @@ def test_mmr_2p20_against_tree(api):
     assert (st == 1).all()
 
 
+# ---- batched verification: cooperative (<= 2^14 proofs) and thread-per-proof (larger) kernels agree ---------------------------
+def test_verify_batches_cooperative_and_thread_kernels_agree(ctx, api, oracle):
+    rnd = np.random.default_rng(5)
+    # MMR, ragged size: several mountains, path lengths 0..9
+    n = 1000 + 1
+    leaves = splitmix_felts(77, n)
+    m = api.mmr.MMR.new(ctx)
+    m.extend(leaves)
+    peaks, root = m.get_peaks(), m.bagging_the_peaks()
+    big = 20000
+    idx = rnd.integers(0, n, size=big).astype(np.uint64)
+    idx[:3] = [0, n - 1, 512]                       # n - 1: the single-leaf mountain (empty path)
+    sib, left, ln = m.prove_batch(idx)
+    claimed = leaves[idx.astype(np.int64)].copy()
+    bad_leaf = rnd.random(big) < 0.1
+    claimed[bad_leaf] ^= np.uint64(1)
+    st_big = api.mmr.verify_batch(claimed, sib, left, ln, peaks, root, ctx)                    # thread-per-proof kernel
+    st_small = np.concatenate([api.mmr.verify_batch(claimed[a:a + 5000], sib[a:a + 5000], left[a:a + 5000], ln[a:a + 5000], peaks, root, ctx)
+                               for a in range(0, big, 5000)])                                  # cooperative kernel
+    assert np.array_equal(st_big, st_small)
+    assert (st_big[~bad_leaf] == 1).all() and (st_big[bad_leaf] == -1).all()   # a wrong leaf misses every peak: assert! :245
+    wrong_root = root.copy(); wrong_root[0] ^= np.uint64(1)
+    assert (api.mmr.verify_batch(claimed[:100], sib[:100], left[:100], ln[:100], peaks, wrong_root, ctx)[~bad_leaf[:100]] == 0).all()
+    for q in (0, 1, 2, 7):
+        want = oracle.mmr_verify(claimed[q], root, sib[q, :ln[q]], left[q, :ln[q]], peaks)
+        assert st_big[q] == want
+    # plonky2 tree with a cap and sponge-hashed leaves
+    lg, w, h = 10, 9, 2
+    rows = splitmix_felts(78, (1 << lg) * w).reshape(1 << lg, w)
+    t = api.mt.MerkleTree.new(rows, h, ctx)
+    idx = rnd.integers(0, 1 << lg, size=big).astype(np.uint64)
+    proofs = t.prove_batch(idx)
+    claimed = rows[idx.astype(np.int64)].copy()
+    bad = rnd.random(big) < 0.1
+    claimed[bad, 3] ^= np.uint64(2)
+    ok_big = api.mt.verify_merkle_proofs_to_cap(claimed, idx, t.cap, h, proofs, ctx)
+    ok_small = np.concatenate([api.mt.verify_merkle_proofs_to_cap(claimed[a:a + 4000], idx[a:a + 4000], t.cap, h, proofs[a:a + 4000], ctx)
+                               for a in range(0, big, 4000)])
+    assert np.array_equal(ok_big, ok_small) and np.array_equal(ok_big, ~bad)
+    for q in range(4):
+        assert bool(ok_big[q]) == oracle.merkle_verify_to_cap(claimed[q], int(idx[q]), t.cap, h, proofs[q])
+    # wrong index / index beyond the tree
+    assert not api.mt.verify_merkle_proofs_to_cap(rows[5:6], [4], t.cap, h, proofs[:1] * 0 + t.prove_batch([5]), ctx)[0]
+    assert not api.mt.verify_merkle_proofs_to_cap(rows[5:6], [5 + (1 << lg)], t.cap, h, t.prove_batch([5]), ctx)[0]
+
+
 # ---- sharded build (virtual ranks on one GPU) ---------------------------------------------------------------------------
 @pytest.mark.parametrize("lg,w,h,G", [(10, 4, 0, 8), (10, 4, 1, 4), (9, 135, 4, 8), (8, 4, 3, 8), (6, 1, 0, 2)])
 def test_sharded_virtual_ranks(ctx, api, oracle, lg, w, h, G):
