@@ -134,7 +134,8 @@ int pmt_mmr_prove_dev(pmt_ctx* ctx, const uint64_t* d_elements, size_t n_leaves,
 int pmt_mmr_verify_dev(pmt_ctx* ctx, const uint64_t* d_leaves, size_t n_idx, const uint64_t* d_siblings,
                        const uint8_t* d_on_left, const uint32_t* d_path_len, const uint64_t* d_peaks, uint32_t n_peaks,
                        const uint64_t* d_root, int8_t* d_status_out);
-/* host-buffer conveniences (upload, run, download) */
+/* host-buffer forms: only the <= 32 peak digests are touched (peaks: a gather on the host, nothing to compute; bag: the
+ * peaks are uploaded and hashed on the GPU) */
 int pmt_mmr_bag(pmt_ctx* ctx, const uint64_t* elements, size_t n_leaves, uint64_t* root_out);
 int pmt_mmr_peaks(pmt_ctx* ctx, const uint64_t* elements, size_t n_leaves, uint64_t* peaks_out, uint32_t* n_peaks_out);
 

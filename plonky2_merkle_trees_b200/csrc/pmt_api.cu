@@ -774,34 +774,53 @@ int pmt_mmr_extend(pmt_ctx* c, uint64_t* elements, size_t n0, const uint64_t* ne
   return PMT_OK;
 }
 
+// positions of the peaks in the post-order array, largest mountain first (get_peaks, :179-200)
+static uint32_t peak_positions(size_t n_leaves, size_t* pos) {
+  uint32_t k = 0;
+  size_t base = 0;
+  for (int bit = 63; bit >= 0; bit--)
+    if ((n_leaves >> bit) & 1) {
+      base += (size_t)1 << bit;
+      pos[k++] = pmt_mmr_size(base) - 1;
+    }
+  return k;
+}
+
+// get_peaks on a HOST array is a gather of <= 32 digests: done on the host (nothing to compute); canonicalised like
+// every output of the library.
 int pmt_mmr_peaks(pmt_ctx* c, const uint64_t* elements, size_t n_leaves, uint64_t* peaks_out, uint32_t* n_peaks_out) {
-  if (int rc = bind(c)) return rc;
-  const size_t s = pmt_mmr_size(n_leaves);
+  if (!c) return PMT_E_INVALID_ARG;
   if (n_leaves == 0) { if (n_peaks_out) *n_peaks_out = 0; return PMT_OK; }
   if (!elements || !peaks_out) return fail(c, PMT_E_INVALID_ARG, "mmr peaks: null pointer");
-  void *b, *p;
-  if (int rc = arena_get(c, 1, s * 32, &b)) return rc;
-  if (int rc = arena_get(c, 0, 64 * 32, &p)) return rc;
-  H2D(c, b, elements, s * 32);
-  uint32_t k = 0;
-  if (int rc = pmt_mmr_peaks_dev(c, (uint64_t*)b, n_leaves, (uint64_t*)p, &k)) return rc;
-  D2H(c, peaks_out, p, (size_t)k * 32);
-  FINISH(c);
+  if (n_leaves >> 32) return fail(c, PMT_E_RANGE, "mmr peaks: size does not fit u32 (merkle_mountain_ranges.rs:184)");
+  size_t pos[64];
+  const uint32_t k = peak_positions(n_leaves, pos);
+  for (uint32_t i = 0; i < k; i++)
+    for (int e = 0; e < 4; e++) {
+      const uint64_t x = elements[4 * pos[i] + e];
+      peaks_out[4 * i + e] = x >= PMT_P ? x - PMT_P : x;
+    }
   if (n_peaks_out) *n_peaks_out = k;
   return PMT_OK;
 }
 
+// bagging_the_peaks on a HOST array: only the peaks travel to the GPU (the old form uploaded all of `elements`)
 int pmt_mmr_bag(pmt_ctx* c, const uint64_t* elements, size_t n_leaves, uint64_t* root_out) {
   if (int rc = bind(c)) return rc;
   if (n_leaves == 0) return fail(c, PMT_E_INVALID_ARG, "mmr bag: empty MMR");
   if (!elements || !root_out) return fail(c, PMT_E_INVALID_ARG, "mmr bag: null pointer");
-  const size_t s = pmt_mmr_size(n_leaves);
-  void *b, *r;
-  if (int rc = arena_get(c, 1, s * 32, &b)) return rc;
-  if (int rc = arena_get(c, 0, 64, &r)) return rc;
-  H2D(c, b, elements, s * 32);
-  if (int rc = pmt_mmr_bag_dev(c, (uint64_t*)b, n_leaves, (uint64_t*)r)) return rc;
-  D2H(c, root_out, r, 32);
+  if (n_leaves >> 32) return fail(c, PMT_E_RANGE, "mmr bag: size does not fit u32 (merkle_mountain_ranges.rs:184)");
+  size_t pos[64];
+  const uint32_t k = peak_positions(n_leaves, pos);
+  void* p = nullptr;
+  if (int rc = arena_get(c, 2, 64 * 32 + 64, &p)) return rc;
+  uint64_t* d_peaks = (uint64_t*)p;
+  uint64_t* d_root = d_peaks + 64 * 4;
+  for (uint32_t i = 0; i < k; i++) H2D(c, d_peaks + 4 * i, elements + 4 * pos[i], 32);
+  TAG(c, "k_hash_one_coop", (4 * k + 7) / 8);
+  k_hash_one_coop<<<1, 32, 0, c->stream>>>(d_peaks, (size_t)4 * k, d_root);
+  CHECK_LAUNCH(c);
+  D2H(c, root_out, d_root, 32);
   FINISH(c);
   return PMT_OK;
 }
