@@ -31,14 +31,14 @@ namespace poseidon {
 constexpr int QUAD_SLOTS = 2 * PMT_FULL_HALF + PMT_PARTIAL / 2;   // 8 full rounds + 11 pairs
 
 // per-block tables in shared memory (lane-dependent, so they cannot be constant-bank operands)
-struct QuadTables {
+struct alignas(16) QuadTables {
   // accumulator start values of the DMMA pass of each round slot, per j:
-  // [L(j), L(4+j), H(j), H(4+j), L(8+j), L(y0), H(8+j), H(y0)], every entry = constant half + 2^52
-  double acc_init[QUAD_SLOTS][4][8];
+  // [L(j), L(4+j), H(j), H(4+j), L(8+j), L(y0), H(8+j), H(y0), pad, pad], every entry = constant half + 2^52
+  double acc_init[QUAD_SLOTS][4][10];   // 8 used; 80-byte rows: the 4 rows a quarter-warp reads fall in distinct banks
   uint64_t rc0[WIDTH];   // first constant layer
   // B fragments per lane (PMT_QUAD_FRAGS_SMEM): [lane][bF 3x2 | bP 3x2 | rk 3 | pad] -- reloaded at the top of every
   // round instead of living in 30 registers for the whole kernel
-  double frags[32][16];
+  double frags[16][32];   // [fragment][lane]: consecutive lanes, consecutive banks
 };
 
 // all threads of the block; ends with a block barrier
@@ -99,11 +99,11 @@ __device__ __forceinline__ void quad_publish_frags(QuadTables& T, const QuadFrag
   if (threadIdx.x < 32) {
 #pragma unroll
     for (int ks = 0; ks < 3; ks++) {
-      T.frags[lane][2 * ks] = f.bF[ks][0]; T.frags[lane][2 * ks + 1] = f.bF[ks][1];
-      T.frags[lane][6 + 2 * ks] = f.bP[ks][0]; T.frags[lane][6 + 2 * ks + 1] = f.bP[ks][1];
+      T.frags[2 * ks][lane] = f.bF[ks][0]; T.frags[2 * ks + 1][lane] = f.bF[ks][1];
+      T.frags[6 + 2 * ks][lane] = f.bP[ks][0]; T.frags[6 + 2 * ks + 1][lane] = f.bP[ks][1];
     }
 #pragma unroll
-    for (int t = 0; t < 3; t++) T.frags[lane][12 + t] = f.rk[t];
+    for (int t = 0; t < 3; t++) T.frags[12 + t][lane] = f.rk[t];
   }
   __syncthreads();
 }
@@ -155,7 +155,7 @@ __device__ __forceinline__ void permute_quad(uint64_t (&e)[4][3], const QuadTabl
 #pragma unroll
       for (int ks = 0; ks < 3; ks++)
 #pragma unroll
-        for (int nb = 0; nb < 2; nb++) bF[ks][nb] = PMT_QUAD_FRAGS_SMEM ? lds_f64_pinned(&T.frags[lane][2 * ks + nb]) : f.bF[ks][nb];
+        for (int nb = 0; nb < 2; nb++) bF[ks][nb] = PMT_QUAD_FRAGS_SMEM ? lds_f64_pinned(&T.frags[2 * ks + nb][lane]) : f.bF[ks][nb];
 #pragma unroll
       for (int mb = 0; mb < 4; mb++) {
         uint64_t x[3];
@@ -176,7 +176,7 @@ __device__ __forceinline__ void permute_quad(uint64_t (&e)[4][3], const QuadTabl
 #pragma unroll
         for (int ks = 0; ks < 3; ks++)
 #pragma unroll
-          for (int nb = 0; nb < 2; nb++) bP[ks][nb] = PMT_QUAD_FRAGS_SMEM ? lds_f64_pinned(&T.frags[lane][6 + 2 * ks + nb]) : f.bP[ks][nb];
+          for (int nb = 0; nb < 2; nb++) bP[ks][nb] = PMT_QUAD_FRAGS_SMEM ? lds_f64_pinned(&T.frags[6 + 2 * ks + nb][lane]) : f.bP[ks][nb];
         // first S-box: lane 0 of state 8 m + q sits in thread (q, 0); thread (q, m) computes it
         uint64_t v = e[0][0];
 #pragma unroll
@@ -200,7 +200,7 @@ __device__ __forceinline__ void permute_quad(uint64_t (&e)[4][3], const QuadTabl
         for (int m = 1; m < 4; m++) { const uint64_t t = shfl64(y0[m], quad0); v = j == (unsigned)m ? t : v; }
         v = pow7_mix<PART_FMA_MASK>(v);
 #pragma unroll
-        for (int t = 0; t < 3; t++) rk[t] = PMT_QUAD_FRAGS_SMEM ? lds_f64_pinned(&T.frags[lane][12 + t]) : f.rk[t];
+        for (int t = 0; t < 3; t++) rk[t] = PMT_QUAD_FRAGS_SMEM ? lds_f64_pinned(&T.frags[12 + t][lane]) : f.rk[t];
 #pragma unroll
         for (int m = 0; m < 4; m++) {
           const uint64_t x = shfl64(v, quad0 | m);
