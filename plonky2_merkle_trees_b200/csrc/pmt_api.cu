@@ -332,6 +332,12 @@ int pmt_simple_tree_build_dev(pmt_ctx* c, const uint64_t* d_leaves, size_t n, ui
   if (lg < 1) return fail(c, PMT_E_INVALID_ARG, "simple tree: needs at least 2 leaves (simple_merkle_tree.rs:38)");
   if (!d_leaves || !d_levels || !d_root) return fail(c, PMT_E_INVALID_ARG, "simple tree: null pointer");
   LevelMajor lay{d_levels, d_root, n, lg};
+  if (n / 2 > COOP_MAX) {   // big tree: the leaf copy rides along with level 1
+    TAG(c, "k_level", n / 2);
+    k_leaves_level1<LevelMajor><<<grid_for(c, n / 2), BLOCK, 0, c->stream>>>(lay, d_leaves, 1, 0, n / 2);
+    CHECK_LAUNCH(c);
+    return run_levels(c, lay, 2, lg, n / 4);
+  }
   TAG(c, "k_leaves", 0);
   k_leaves<LevelMajor><<<grid_copy(c, n), BLOCK, 0, c->stream>>>(lay, d_leaves, 1, 0, n);
   CHECK_LAUNCH(c);
@@ -388,6 +394,13 @@ int pmt_merkle_tree_build_dev(pmt_ctx* c, const uint64_t* d_leaves, size_t n, si
   if (!d_leaves || !d_cap || (!d_digests && (size_t)lg > cap_height)) return fail(c, PMT_E_INVALID_ARG, "MerkleTree::new: null pointer");
   const int L = lg - (int)cap_height;
   Plonky2 lay{d_digests, d_cap, L};
+  if (w <= 4 && L >= 1 && n / 2 > COOP_MAX) {   // narrow leaves, big tree: the leaf copy rides along with level 1
+    TAG(c, "k_level", n / 2);
+    k_leaves_level1<Plonky2><<<grid_for(c, n / 2), BLOCK, 0, c->stream>>>(lay, d_leaves, w, 0, n / 2);
+    CHECK_LAUNCH(c);
+    if (L == 1) return PMT_OK;
+    return run_levels(c, lay, 2, L, n / 4);
+  }
   TAG(c, "k_leaves", w <= 4 ? 0 : n * ((w + 7) / 8));
   k_leaves<Plonky2><<<w <= 4 ? grid_copy(c, n) : grid_for(c, n), BLOCK, 0, c->stream>>>(lay, d_leaves, w, 0, n);
   CHECK_LAUNCH(c);
@@ -472,10 +485,23 @@ int pmt_mmr_extend_dev(pmt_ctx* c, uint64_t* d_elements, size_t n0, const uint64
   if (!d_elements || !d_new) return fail(c, PMT_E_INVALID_ARG, "mmr extend: null pointer");
   if (n0 + m > ((size_t)1 << 30)) return fail(c, PMT_E_RANGE, "mmr extend: more than 2^30 leaves (get_mmr_index is i32, merkle_mountain_ranges.rs:264)");
   Mmr lay{d_elements};
-  TAG(c, "k_leaves", 0);
-  k_leaves<Mmr><<<grid_copy(c, m), BLOCK, 0, c->stream>>>(lay, d_new, 1, n0, m);
-  CHECK_LAUNCH(c);
-  for (int l = 1; l < 40; l++) {
+  int first_level = 1;
+  if ((n0 & 1) == 0 && m / 2 > COOP_MAX) {   // every level-1 node has two NEW leaves: copy them and hash in one pass
+    TAG(c, "k_level", m / 2);
+    k_leaves_level1<Mmr><<<grid_for(c, m / 2), BLOCK, 0, c->stream>>>(lay, d_new, 1, n0 / 2, m / 2);
+    CHECK_LAUNCH(c);
+    if (m & 1) {                             // the unpaired last leaf
+      TAG(c, "k_leaves", 0);
+      k_leaves<Mmr><<<1, BLOCK, 0, c->stream>>>(lay, d_new + (m - 1), 1, n0 + m - 1, 1);
+      CHECK_LAUNCH(c);
+    }
+    first_level = 2;
+  } else {
+    TAG(c, "k_leaves", 0);
+    k_leaves<Mmr><<<grid_copy(c, m), BLOCK, 0, c->stream>>>(lay, d_new, 1, n0, m);
+    CHECK_LAUNCH(c);
+  }
+  for (int l = first_level; l < 40; l++) {
     const size_t k0 = n0 >> l, k1 = (n0 + m) >> l;
     if (k1 == 0) break;
     if (k1 > k0)

@@ -362,6 +362,30 @@ def test_mmr_2p20_against_tree(api):
     assert (st == 1).all()
 
 
+# ---- narrow leaves, big trees: the leaf copy is fused into level 1 (k_leaves_level1) ------------------------------------------
+@pytest.mark.parametrize("w,h", [(1, 0), (3, 2), (4, 0), (4, 5)])
+def test_fused_leaf_level_plonky2(ctx, api, oracle, w, h):
+    n = 1 << 15
+    rows = splitmix_felts(500 + w, n * w).reshape(n, w)
+    rows[0, 0] = np.uint64(2**64 - 1); rows[n - 1, w - 1] = np.uint64(P)      # non-canonical inputs
+    t = api.mt.MerkleTree.new(rows, h, ctx)
+    dg, cap = oracle.merkle_tree_new(rows, h, threads=oracle.max_threads(), fast=True)
+    assert np.array_equal(t.digests, dg) and np.array_equal(t.cap, cap)
+
+
+def test_fused_leaf_level_simple_tree_and_mmr(ctx, api, oracle):
+    n = 1 << 15
+    leaves = splitmix_felts(600, n + 1)
+    leaves[5] = np.uint64(P + 3)
+    t = api.smt.MerkleTree.build(leaves[:n], ctx)
+    levels, root = oracle.simple_tree_build(leaves[:n])
+    assert np.array_equal(np.concatenate(t.tree), levels) and np.array_equal(t.root, root)
+    m = api.mmr.MMR.new(ctx)
+    m.extend(leaves[:6])            # even n_before, odd batch: fused pass + the unpaired last leaf
+    m.extend(leaves[6:])
+    assert np.array_equal(m.elements, oracle.mmr_extend(None, leaves))
+
+
 # ---- batched verification: cooperative (<= 2^14 proofs) and thread-per-proof (larger) kernels agree ---------------------------
 def test_verify_batches_cooperative_and_thread_kernels_agree(ctx, api, oracle):
     rnd = np.random.default_rng(5)
