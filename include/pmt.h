@@ -111,6 +111,11 @@ int pmt_merkle_verify_dev(pmt_ctx* ctx, const uint64_t* d_leaf_rows, size_t widt
  * cap.  cap_height == g: nothing to do (the roots are the cap). */
 int pmt_top_levels_dev(pmt_ctx* ctx, const uint64_t* d_roots, size_t n_roots, uint32_t cap_height, uint64_t* d_top_out);
 
+/* the same for `batch` independent sets of n_roots roots in one launch (sets n_roots digests apart in d_roots and
+ * n_roots - 2^h digests apart in d_top_out): the rounds of a subtree-sharded MMR (one mountain per set bit of n) */
+int pmt_top_levels_batch_dev(pmt_ctx* ctx, const uint64_t* d_roots, size_t batch, size_t n_roots, uint32_t cap_height,
+                             uint64_t* d_top_out);
+
 /* ---- MMR: merkle_mountain_ranges.rs ------------------------------------------------------------------------------------ */
 /* number of elements of an MMR with n leaves = 2n - popcount(n) */
 size_t pmt_mmr_size(size_t n_leaves);

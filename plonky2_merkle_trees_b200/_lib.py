@@ -50,6 +50,7 @@ _SIGNATURES = {
     "pmt_merkle_prove_dev": (_INT, [_VP, _VP, _SZ, _U32, _VP, _SZ, _VP]),
     "pmt_merkle_verify_dev": (_INT, [_VP, _VP, _SZ, _VP, _SZ, _VP, _U32, _VP, _SZ, _VP]),
     "pmt_top_levels_dev": (_INT, [_VP, _VP, _SZ, _U32, _VP]),
+    "pmt_top_levels_batch_dev": (_INT, [_VP, _VP, _SZ, _SZ, _U32, _VP]),
     "pmt_mmr_size": (_SZ, [_SZ]),
     "pmt_mmr_index": (_SZ, [_SZ]),
     "pmt_mmr_extend": (_INT, [_VP, u64p, _SZ, u64p, _SZ]),

@@ -385,10 +385,14 @@ __global__ void __launch_bounds__(COOP_BLOCK) k_top_coop(Layout lay, int l0, int
 
 // multi-GPU finish: the levels above n_roots gathered subtree roots, ONE block, 16 lanes per permutation (the levels are
 // sequential and tiny: G - 1 permutations for G ranks).  out is level-major: n_roots/2, n_roots/4, ..., n_cap digests.
+// blockIdx.x = which set of roots (a batch of independent finishes: the rounds of a sharded MMR); sets are n_roots digests
+// apart in `roots` and n_roots - n_cap digests apart in `out`.
 __global__ void __launch_bounds__(COOP_BLOCK) k_top_roots_coop(const uint64_t* __restrict__ roots, size_t n_roots, size_t n_cap,
                                                                uint64_t* __restrict__ out) {
   __shared__ uint64_t rc_smem[WIDTH * (PMT_ROUNDS + 1)];
   coop_stage_constants(rc_smem);
+  roots += 4 * n_roots * blockIdx.x;
+  out += 4 * (n_roots - n_cap) * blockIdx.x;
   const unsigned g = threadIdx.x & 15, base_lane = threadIdx.x & 16;
   const size_t group = threadIdx.x >> 4, groups = blockDim.x >> 4;
   const uint64_t* cur = roots;

@@ -472,6 +472,21 @@ int pmt_top_levels_dev(pmt_ctx* c, const uint64_t* d_roots, size_t n_roots, uint
   return PMT_OK;
 }
 
+// `batch` independent finishes of the same shape in ONE launch (one block each): the rounds of a sharded MMR
+int pmt_top_levels_batch_dev(pmt_ctx* c, const uint64_t* d_roots, size_t batch, size_t n_roots, uint32_t cap_height, uint64_t* d_top_out) {
+  if (int rc = bind(c)) return rc;
+  const int g = log2_strict(n_roots);
+  if (g < 0) return fail(c, PMT_E_NOT_POW2, "top levels: %zu roots is not a power of two", n_roots);
+  if ((int)cap_height > g) return fail(c, PMT_E_RANGE, "top levels: cap_height %u > log2(roots)", cap_height);
+  if (n_roots > 4096 || batch > 65535) return fail(c, PMT_E_RANGE, "top levels batch: at most 4096 roots x 65535 sets");
+  if ((int)cap_height == g || batch == 0) return PMT_OK;
+  if (!d_roots || !d_top_out) return fail(c, PMT_E_INVALID_ARG, "top levels: null pointer");
+  TAG(c, "k_top_roots_coop", batch * (n_roots - ((size_t)1 << cap_height)));
+  k_top_roots_coop<<<(unsigned)batch, COOP_BLOCK, 0, c->stream>>>(d_roots, n_roots, (size_t)1 << cap_height, d_top_out);
+  CHECK_LAUNCH(c);
+  return PMT_OK;
+}
+
 // ---- MMR ---------------------------------------------------------------------------------------------------------------
 size_t pmt_mmr_size(size_t n) { return 2 * n - (size_t)__builtin_popcountll((unsigned long long)n); }
 size_t pmt_mmr_index(size_t i) { return 2 * i - (size_t)__builtin_popcountll((unsigned long long)i); }

@@ -69,6 +69,13 @@ class CudaEngine:
         self.ctx.call("pmt_top_levels_dev", dptr(d_roots), g, cap_height, dptr(d_top))
         return d_top[:g - (1 << cap_height)]
 
+    def top_levels_batch(self, d_roots):
+        """d_roots: (batch, G, 4) -> (batch, G - 1, 4): the levels above every set of G roots, one launch."""
+        b, g = d_roots.shape[0], d_roots.shape[1]
+        d_top = dev_u64((b, max(g - 1, 1), 4), self.device)
+        self.ctx.call("pmt_top_levels_batch_dev", dptr(d_roots), b, g, 0, dptr(d_top))
+        return d_top[:, :g - 1]
+
     def sync(self):
         self.ctx.sync()
 
@@ -330,13 +337,21 @@ def build_sharded_mmr(d_local_leaves, n_total, engine, group=None):
         if t:
             src = dist.get_global_rank(group, world - 1) if group is not None else world - 1
             dist.broadcast(tail_peaks, src=src, group=group)
-        for i, m in enumerate(ms):
-            roots = gathered[:, i, :].contiguous()
-            top = engine.top_levels(roots, 0)
+        by_round = gathered.permute(1, 0, 2).contiguous()            # (rounds, world, 4)
+        if k and hasattr(engine, "top_levels_batch"):                  # all rounds' finishes in one launch
+            tops = engine.top_levels_batch(by_round)
             engine.sync()
-            top_h = top.cpu().numpy().view(np.uint64)
-            rounds.append((m, roots.cpu().numpy().view(np.uint64), top_h))
-            big.append(top_h[-1:])
+            tops_h = tops.cpu().numpy().view(np.uint64)
+        else:
+            tops_h = []
+            for i in range(k):
+                t_i = engine.top_levels(by_round[i], 0)
+                engine.sync()
+                tops_h.append(t_i.cpu().numpy().view(np.uint64))
+        roots_h = by_round.cpu().numpy().view(np.uint64)
+        for i, m in enumerate(ms):
+            rounds.append((m, roots_h[i], np.ascontiguousarray(tops_h[i])))
+            big.append(np.ascontiguousarray(tops_h[i])[-1:])
     else:
         roots_h = my_roots.cpu().numpy().view(np.uint64)
         for i, m in enumerate(ms):

@@ -479,6 +479,23 @@ def test_top_levels_above_gathered_roots(ctx, oracle, n_roots, h):
     assert got.shape == want.shape and np.array_equal(got, want)
 
 
+def test_top_levels_batch(ctx, oracle):
+    from plonky2_merkle_trees_b200 import sharded
+    from plonky2_merkle_trees_b200.device import to_device, to_host
+    eng = sharded.CudaEngine(ctx)
+    for b, g in [(1, 2), (21, 8), (5, 64), (3, 1)]:
+        roots = splitmix_felts(b * 100 + g, b * g * 4).reshape(b, g, 4)
+        d_top = eng.top_levels_batch(to_device(roots, eng.device).view(b, g, 4))
+        eng.sync()
+        got = to_host(d_top.contiguous()).reshape(b, g - 1, 4)
+        for i in range(b):
+            cur, want = roots[i], []
+            while cur.shape[0] > 1:
+                cur = oracle.two_to_one_batch(cur[0::2], cur[1::2]); want.append(cur)
+            want = np.concatenate(want) if want else np.zeros((0, 4), np.uint64)
+            assert np.array_equal(got[i], want), (b, g, i)
+
+
 def test_sharded_mmr_virtual_world_of_one(ctx, api, oracle):
     """build_sharded_mmr without a process group (world 1): rounds = the set bits of n, no tail; elements, peaks, bag and
     proofs against the sequential add_leaf oracle.  (world > 1: tests/test_abi_and_host.py on gloo, tools/multigpu_check.py)"""
