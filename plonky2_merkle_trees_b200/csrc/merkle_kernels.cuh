@@ -20,9 +20,11 @@ using poseidon::WIDTH;
 
 // the production permutation (see DESIGN.md "Permutation variants" for the measurements behind this choice).
 // PMT_PERM selects the form for A/B runs (tools/ab_level.cu): 0 = permute_fast (sparse partial rounds), 1 = permute_fused,
-// 2 = permute_rounds (30 x S-box + DFMA MDS), 3 = permute_paired (partial rounds in pairs; production).
+// 2 = permute_rounds (30 x S-box + DFMA MDS), 3 = permute_paired (partial rounds in pairs; round-1 production until the
+// frequency form), 4 = permute_paired_freq (3 with the MDS layers as frequency-domain convolutions, poseidon_freq.cuh;
+// production: 1.55 against 1.29 G permutations/s, profiles/ab_freq_r1.jsonl).
 #ifndef PMT_PERM
-#define PMT_PERM 3
+#define PMT_PERM 4
 #endif
 #ifndef PMT_SBOX_FMA_MASK
 #define PMT_SBOX_FMA_MASK 0
@@ -51,6 +53,9 @@ using poseidon::WIDTH;
 #ifndef PMT_PPIPE
 #define PMT_PPIPE 0
 #endif
+#ifndef PMT_FQ_SPLIT
+#define PMT_FQ_SPLIT 0   // 1: fence the high halves behind the low halves (measured slower: 1.51 against 1.55)
+#endif
 #ifndef PMT_COMPRESS_SPECIALISED
 #define PMT_COMPRESS_SPECIALISED 0
 #endif
@@ -61,6 +66,8 @@ __device__ __forceinline__ void permute_impl(uint64_t (&s)[WIDTH]) {
 #elif PMT_PERM == 3
   poseidon::permute_paired<PMT_SBOX_FMA_MASK, PMT_PART_FMA_MASK, PMT_COLUMN != 0, PMT_CVT_I2F != 0, PMT_COMBINE_ALU != 0, CAP_ZERO,
                            OUT4>(s);
+#elif PMT_PERM == 4
+  poseidon::permute_paired_freq<PMT_SBOX_FMA_MASK, PMT_PART_FMA_MASK, PMT_CVT_I2F != 0, CAP_ZERO, OUT4, PMT_FQ_SPLIT>(s);
 #elif PMT_PERM == 2
   poseidon::permute_rounds<PMT_SBOX_FMA_MASK, PMT_PART_FMA_MASK, PMT_COLUMN != 0, PMT_CVT_I2F != 0, PMT_COMBINE_ALU != 0, CAP_ZERO,
                            OUT4>(s);
@@ -181,14 +188,18 @@ struct Mmr {
 #ifndef PMT_BLOCK
 #define PMT_BLOCK 128
 #endif
+#ifndef PMT_MINB_L1
+#define PMT_MINB_L1 5
+#endif
 #ifndef PMT_MINB
-#define PMT_MINB 1   // minimum resident blocks per SM asked of ptxas (register cap); tuned with tools/ab_level.cu
+#define PMT_MINB 5   // minimum resident blocks per SM asked of ptxas (register cap: 96 registers, no spills, 20 warps/SM;
+                     // uncapped ptxas takes 132 = 12 warps/SM and 4 % less throughput); tuned with tools/ab_level.cu
 #endif
 constexpr int BLOCK = PMT_BLOCK;
 
 // level 0: digest(0, k0 + i) = hash_or_noop(row i),  rows row-major count x w
 template <class Layout>
-__global__ void __launch_bounds__(BLOCK) k_leaves(Layout lay, const uint64_t* __restrict__ rows, size_t w, size_t k0,
+__global__ void __launch_bounds__(BLOCK, PMT_MINB) k_leaves(Layout lay, const uint64_t* __restrict__ rows, size_t w, size_t k0,
                                                   size_t count) {
   for (size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x; i < count; i += (size_t)gridDim.x * BLOCK)
     store_digest(lay.at(0, k0 + i), hash_or_noop(rows + i * w, w));
@@ -198,7 +209,7 @@ __global__ void __launch_bounds__(BLOCK) k_leaves(Layout lay, const uint64_t* __
 // 2k + 1 into their digests, stores both and their parent.  Saves the separate copy pass (one read + one write of all
 // leaf digests: 0.3 ms of the 13.7 ms of a 2^24-leaf tree).  count = number of level-1 nodes.
 template <class Layout>
-__global__ void __launch_bounds__(BLOCK, PMT_MINB) k_leaves_level1(Layout lay, const uint64_t* __restrict__ rows, size_t w, size_t k0,
+__global__ void __launch_bounds__(BLOCK, PMT_MINB_L1) k_leaves_level1(Layout lay, const uint64_t* __restrict__ rows, size_t w, size_t k0,
                                                                    size_t count) {
   for (size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x; i < count; i += (size_t)gridDim.x * BLOCK) {
     const size_t k = k0 + i;
@@ -215,7 +226,7 @@ __global__ void __launch_bounds__(BLOCK, PMT_MINB) k_leaves_level1(Layout lay, c
 // cost one scattered 32-byte digest store per leaf instead of a 1 GiB round trip through a row-major copy.
 // rows_out (optional): the row-major leaves upstream's MerkleTree keeps for openings.
 template <class Layout>
-__global__ void __launch_bounds__(BLOCK) k_leaves_columns(Layout lay, const uint64_t* __restrict__ cols, size_t n, size_t w,
+__global__ void __launch_bounds__(BLOCK, PMT_MINB) k_leaves_columns(Layout lay, const uint64_t* __restrict__ cols, size_t n, size_t w,
                                                           int log2n, bool bit_reverse, uint64_t* __restrict__ rows_out) {
   for (size_t t = (size_t)blockIdx.x * BLOCK + threadIdx.x; t < n; t += (size_t)gridDim.x * BLOCK) {
     const size_t i = (bit_reverse && log2n > 0) ? (size_t)(__brevll((unsigned long long)t) >> (64 - log2n)) : t;
@@ -436,7 +447,7 @@ __global__ void __launch_bounds__(32) k_hash_one_coop(const uint64_t* __restrict
 }
 
 // generic batches (parity hooks of the Hasher trait)
-__global__ void __launch_bounds__(BLOCK) k_permute(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, size_t n) {
+__global__ void __launch_bounds__(BLOCK, PMT_MINB) k_permute(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, size_t n) {
   for (size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x; i < n; i += (size_t)gridDim.x * BLOCK) {
     uint64_t s[WIDTH];
 #pragma unroll
@@ -448,14 +459,14 @@ __global__ void __launch_bounds__(BLOCK) k_permute(const uint64_t* __restrict__ 
 }
 
 // out[i] = two_to_one(l[i], r[i]); `stride` u64 between consecutive inputs (4 = dense arrays, 8 = adjacent sibling pairs)
-__global__ void __launch_bounds__(BLOCK) k_two_to_one(const uint64_t* __restrict__ l, const uint64_t* __restrict__ r,
+__global__ void __launch_bounds__(BLOCK, PMT_MINB) k_two_to_one(const uint64_t* __restrict__ l, const uint64_t* __restrict__ r,
                                                       uint64_t* __restrict__ out, size_t n, size_t stride) {
   for (size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x; i < n; i += (size_t)gridDim.x * BLOCK)
     store_digest(out + 4 * i, two_to_one(load_digest(l + stride * i), load_digest(r + stride * i)));
 }
 
 template <bool NOOP_RULE>
-__global__ void __launch_bounds__(BLOCK) k_hash_rows(const uint64_t* __restrict__ rows, size_t n, size_t w,
+__global__ void __launch_bounds__(BLOCK, PMT_MINB) k_hash_rows(const uint64_t* __restrict__ rows, size_t n, size_t w,
                                                      uint64_t* __restrict__ out) {
   for (size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x; i < n; i += (size_t)gridDim.x * BLOCK)
     store_digest(out + 4 * i, NOOP_RULE ? hash_or_noop(rows + i * w, w) : hash_no_pad(rows + i * w, w));
@@ -539,7 +550,7 @@ __device__ __forceinline__ Digest load_digest_canonical(const uint64_t* __restri
 
 // simple_merkle_tree.rs:91-109 verify_merkle_proof and [UPSTREAM hash/merkle_proofs.rs verify_merkle_proof_to_cap]:
 // fold by index parity, compare with cap[index >> path_len] (cap_height 0 + width 1 = the simple tree's root)
-__global__ void __launch_bounds__(BLOCK) k_verify_to_cap(const uint64_t* __restrict__ rows, size_t w,
+__global__ void __launch_bounds__(BLOCK, PMT_MINB) k_verify_to_cap(const uint64_t* __restrict__ rows, size_t w,
                                                          const uint64_t* __restrict__ idx, size_t n_idx,
                                                          const uint64_t* __restrict__ cap, uint32_t cap_height,
                                                          const uint64_t* __restrict__ proofs, size_t path_len,
@@ -558,7 +569,7 @@ __global__ void __launch_bounds__(BLOCK) k_verify_to_cap(const uint64_t* __restr
 
 // merkle_mountain_ranges.rs:232-252 MMR_proof::verify: fold by sibling_on_left, membership in peaks (else the
 // reference panics: status -1), re-bag, compare with root
-__global__ void __launch_bounds__(BLOCK) k_mmr_verify(const uint64_t* __restrict__ leaves, size_t n_idx,
+__global__ void __launch_bounds__(BLOCK, PMT_MINB) k_mmr_verify(const uint64_t* __restrict__ leaves, size_t n_idx,
                                                       const uint64_t* __restrict__ sib, const uint8_t* __restrict__ left,
                                                       const uint32_t* __restrict__ len, const uint64_t* __restrict__ peaks,
                                                       uint32_t n_peaks, const uint64_t* __restrict__ bagged,

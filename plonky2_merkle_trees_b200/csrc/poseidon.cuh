@@ -15,6 +15,7 @@
 #pragma once
 #include "goldilocks.cuh"
 #include "poseidon_constants.cuh"
+#include "poseidon_freq.cuh"
 
 #ifndef PMT_COMBINE_C
 #define PMT_COMBINE_C 1   // 1: the ALU recombination is combine_magic_c (plain C, 3-input adds) instead of the PTX carry chain
@@ -289,6 +290,11 @@ __device__ __forceinline__ uint64_t tie(uint64_t x, uint32_t after, uint32_t zer
   asm("lop3.b32 %0, %0, %1, %2, 0xf8;" : "+r"(lo) : "r"(after), "r"(zero));   // lo | (after & zero)
   return gl::pack(lo, gl::hi32(x));
 }
+__device__ __forceinline__ uint64_t tie_hi(uint64_t x, uint32_t after, uint32_t zero) {   // the same fence on the high word
+  uint32_t hi = gl::hi32(x);
+  asm("lop3.b32 %0, %0, %1, %2, 0xf8;" : "+r"(hi) : "r"(after), "r"(zero));
+  return gl::pack(gl::lo32(x), hi);
+}
 __device__ __forceinline__ uint32_t hi_word(double d) { return (uint32_t)__double2hiint(d); }
 
 // 2^52 + l, 2^52 + h (l, h < 2^43) -> u64 congruent to l + 2^32 h, ALU pipe only.
@@ -533,6 +539,79 @@ __device__ __forceinline__ void permute_paired(uint64_t (&s)[WIDTH]) {
           L[j] = fma(xlo, c, L[j]); H[j] = fma(xhi, c, H[j]);
           s[j] = COMBINE_ALU ? combine_magic_alu(L[j], H[j]) : combine_magic_fma(L[j], H[j]);
         }
+      }
+    }
+  }
+}
+
+// Paired form with the MDS layers in the frequency domain (poseidon_freq.cuh): 204 fp64 operations per full layer instead
+// of 288, 260 per pair of partial rounds instead of 336 -- the same digests (tools/check_freq.cpp, tests/test_gpu_parity.py).
+// FQ_SPLIT: finish the low halves before the high halves are converted (lower register pressure) instead of leaving the
+// order to ptxas.
+template <int SBOX_FMA_MASK = 0, int PART_FMA_MASK = 0, bool CVT_I2F = true, bool CAP_ZERO = false, bool OUT4 = false,
+          int FQ_SPLIT = 1>
+__device__ __forceinline__ void permute_paired_freq(uint64_t (&s)[WIDTH]) {
+  const double MAGIC = 4503599627370496.0;  // 2^52
+  const uint32_t zero = PMT_ZERO32;
+  auto half_of = [&](uint64_t x, int h) -> double {
+    const uint32_t w = h ? gl::hi32(x) : gl::lo32(x);
+    return CVT_I2F ? (double)w : __hiloint2double(0x43300000, (int)w) - MAGIC;
+  };
+#pragma unroll
+  for (int i = 0; i < (CAP_ZERO ? 8 : WIDTH); i++) s[i] = gl::add_canonical(s[i], PMT_RC[i]);
+#pragma unroll 1
+  for (int half = 0; half < 2; half++) {
+#pragma unroll 1
+    for (int q = 0; q < PMT_FULL_HALF; q++) {
+      const int r = half ? PMT_FULL_HALF + PMT_PARTIAL + q : q;
+#pragma unroll
+      for (int i = 0; i < 8; i++) s[i] = pow7_mix<SBOX_FMA_MASK>(s[i]);
+      if (CAP_ZERO && r == 0) {
+#pragma unroll
+        for (int i = 8; i < WIDTH; i++) s[i] = PMT_SBOX_RC_CAP[i - 8];
+      } else {
+#pragma unroll
+        for (int i = 8; i < WIDTH; i++) s[i] = pow7_mix<SBOX_FMA_MASK>(s[i]);
+      }
+      if (OUT4 && r == PMT_ROUNDS - 1) {
+        mds_layer_dfma2<false, CVT_I2F, true>(s, &PMT_RC_DM[2 * WIDTH * r], true);   // 4 rows: the matrix form is shorter
+      } else {
+        double x[WIDTH], olo[WIDTH], ohi[WIDTH];
+#pragma unroll
+        for (int i = 0; i < WIDTH; i++) x[i] = half_of(s[i], 0);
+        freq::full_layer_half<2>(x, &PMT_RC_DM[2 * WIDTH * r], olo);
+#pragma unroll
+        for (int i = 0; i < WIDTH; i++) {
+          // fence (see tie()): the high halves are converted after the low halves are done, or ptxas interleaves both
+          // halves and needs 200 registers
+          if (FQ_SPLIT == 1) x[i] = half_of(tie_hi(s[i], hi_word(olo[i]), zero), 1);
+          else x[i] = half_of(s[i], 1);
+        }
+        freq::full_layer_half<2>(x, &PMT_RC_DM[2 * WIDTH * r + 1], ohi);
+#pragma unroll
+        for (int i = 0; i < WIDTH; i++) s[i] = combine_magic_alu(olo[i], ohi[i]);
+      }
+    }
+    if (half == 0) {
+#pragma unroll 1
+      for (int pair = 0; pair < PMT_PARTIAL / 2; pair++) {
+        const int r = PMT_FULL_HALF + 2 * pair;
+        s[0] = pow7_mix<PART_FMA_MASK>(s[0]);
+        double x[WIDTH], ylo[WIDTH], yhi[WIDTH], l0lo, l0hi, x0lo, x0hi;
+#pragma unroll
+        for (int i = 0; i < WIDTH; i++) x[i] = half_of(s[i], 0);
+        freq::pair_half_begin(x, PMT_RC_DM[2 * WIDTH * r], l0lo, ylo, x0lo);
+#pragma unroll
+        for (int i = 0; i < WIDTH; i++) {
+          if (FQ_SPLIT == 1) x[i] = half_of(tie_hi(s[i], hi_word(ylo[i]), zero), 1);
+          else x[i] = half_of(s[i], 1);
+        }
+        freq::pair_half_begin(x, PMT_RC_DM[2 * WIDTH * r + 1], l0hi, yhi, x0hi);
+        const uint64_t xs = pow7_mix<PART_FMA_MASK>(combine_magic_alu(l0lo, l0hi));
+        freq::pair_half_end<2>(ylo, half_of(xs, 0), x0lo, l0lo, &PMT_FQ_KPAIR_DM[2 * WIDTH * pair]);
+        freq::pair_half_end<2>(yhi, half_of(xs, 1), x0hi, l0hi, &PMT_FQ_KPAIR_DM[2 * WIDTH * pair + 1]);
+#pragma unroll
+        for (int i = 0; i < WIDTH; i++) s[i] = combine_magic_alu(ylo[i], yhi[i]);
       }
     }
   }

@@ -1,4 +1,5 @@
 """Pin the CPU oracle (C + pure Python) to every known answer the reference holds for this path (CPU only)."""
+import os
 import random
 
 import numpy as np
@@ -162,3 +163,31 @@ def test_simple_tree_equals_plonky2_tree_cap0(oracle):
         for k in range(m):
             assert dg[po.digest_index(l, k)].tolist() == levels[off + k].tolist()
         off += m; m //= 2; l += 1
+
+
+def test_frequency_domain_mds_is_exact_on_the_host(tmp_path):
+    """The production MDS layer (csrc/poseidon_freq.cuh: fp64, frequency-domain convolution) compiled for the HOST with g++
+    and checked by tools/check_freq.cpp: every layer output at all 4096 corners of the input cube against the integer
+    matrix form for every constant set, and 200 000 whole permutations (random + edge states) against the oracle's
+    specification-form permutation.  tools/gen_freq_constants.py re-derives the tables and proves the bounds."""
+    import subprocess
+    import oracle as orc
+    orc.build()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "check_freq")
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-o", exe, os.path.join(root, "tools", "check_freq.cpp"),
+                           "-L" + os.path.join(root, "oracle"), "-lpmt_oracle", "-Wl,-rpath," + os.path.join(root, "oracle")])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout + out.stderr
+
+
+def test_frequency_domain_tables_are_reproducible(tmp_path):
+    """the committed poseidon_freq_constants.cuh is what tools/gen_freq_constants.py derives (and its proofs pass)"""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(root, "plonky2_merkle_trees_b200", "csrc", "poseidon_freq_constants.cuh")
+    before = open(path).read()
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "gen_freq_constants.py")], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "exactness: worst" in out.stdout, out.stdout + out.stderr
+    assert open(path).read() == before
