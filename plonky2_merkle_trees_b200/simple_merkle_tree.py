@@ -10,6 +10,7 @@ The tree is built on the GPU and stays resident there (`d_levels`) so batches of
 copy (`tree`, the reference's Vec<Vec<HashOut>>) is downloaded once, on first access.
 """
 import numpy as np
+import torch
 
 from . import _lib
 from ._lib import PmtError, as_u64
@@ -99,7 +100,7 @@ def verify_merkle_proofs(leaves, leaf_indices, root, proofs, ctx=None):
     proofs = as_u64(proofs)
     proofs = proofs.reshape(idx.size, -1, 4)
     dev = "cuda:%d" % ctx.device
-    d_ok = __import__("torch").empty(idx.size, dtype=__import__("torch").uint8, device=dev)
+    d_ok = torch.empty(idx.size, dtype=torch.uint8, device=dev)
     d_l, d_i, d_r, d_p = to_device(leaves, dev), to_device(idx, dev), to_device(as_u64(root).reshape(4), dev), to_device(proofs, dev)
     ctx.call("pmt_simple_tree_verify_dev", dptr(d_l), dptr(d_i), idx.size, dptr(d_r), dptr(d_p), proofs.shape[1], dptr(d_ok))
     ctx.sync()

@@ -244,6 +244,73 @@ def test_full_size_properties_2p20(api, oracle):
     assert api.mt.verify_merkle_proofs_to_cap(rows[idx.astype(np.int64)], idx, t0.cap, 0, proofs).all()
 
 
+def test_full_size_properties_2p24(api, oracle):
+    """The headline workload (2^24 x 4 felts, cap 0) and BASELINE C3 (MMR of 2^24 and 2^24 - 1 leaves) at FULL size, through
+    properties that do not need a CPU rebuild of 16.7 M permutations:
+    (1) every one of 6 000 randomly sampled inner nodes, spread over all 24 levels, equals the ORACLE's two_to_one of its two
+        children as stored in the digests array (so a wrong node anywhere on a sampled path cannot hide);
+    (2) the root is the fold of the 16 cap-4 subtree roots of a second, independent build (checksum of checksums);
+    (3) 1 024 proofs verify against the cap and fail for the neighbouring leaf;
+    (4) the MMR over the same first-column leaves is ONE mountain whose nodes are the width-1 tree's, its 2^24 - 1 sibling
+        has 24 peaks whose bag equals the oracle's sponge over the GPU's peaks, and 1 024 proofs verify."""
+    lg, w = 24, 4
+    n = 1 << lg
+    rows = splitmix_felts(0x706d745f62323030, n * w).reshape(n, w)
+    t0 = api.mt.MerkleTree.new(rows, 0)
+    d = t0.digests
+    assert d.shape == (2 * n - 2, 4)
+    node = lambda l, k: 2 * (((k >> 1) << (l + 1)) + (1 << l) - 1) + (k & 1)      # upstream's interleaved layout, cap 0
+    rnd = random.Random(24)
+    ls, ks = [], []
+    for _ in range(6000):
+        l = rnd.randrange(1, lg)
+        ls.append(l); ks.append(rnd.randrange(n >> l))
+    par = np.array([node(l, k) for l, k in zip(ls, ks)])
+    c0 = np.array([node(l - 1, 2 * k) for l, k in zip(ls, ks)])
+    c1 = np.array([node(l - 1, 2 * k + 1) for l, k in zip(ls, ks)])
+    assert np.array_equal(oracle.two_to_one_batch(d[c0], d[c1]), d[par])
+    assert np.array_equal(oracle.two_to_one(d[node(lg - 1, 0)], d[node(lg - 1, 1)]), t0.cap[0])
+    assert np.array_equal(d[0::4][:n // 2], rows[0::2]) and np.array_equal(d[1::4][:n // 2], rows[1::2])   # no-op leaves
+    assert (d < np.uint64(P)).all()                                                                          # canonical
+    # (2)
+    t4 = api.mt.MerkleTree.new(rows, 4)
+    lvl = t4.cap
+    while lvl.shape[0] > 1:
+        lvl = oracle.two_to_one_batch(lvl[0::2], lvl[1::2])
+    assert np.array_equal(lvl[0], t0.cap[0])
+    # (3)
+    idx = (splitmix_felts(5, 1024) % np.uint64(n)).astype(np.uint64)
+    proofs = t0.prove_batch(idx)
+    assert proofs.shape == (1024, lg, 4)
+    assert api.mt.verify_merkle_proofs_to_cap(rows[idx.astype(np.int64)], idx, t0.cap, 0, proofs).all()
+    assert not api.mt.verify_merkle_proofs_to_cap(rows[(idx ^ np.uint64(1)).astype(np.int64)], idx, t0.cap, 0, proofs).any()
+    del t0, t4, d
+    # (4)
+    leaves = np.ascontiguousarray(rows[:, 0])
+    m = api.mmr.MMR.new(); m.extend(leaves)
+    t1 = api.mt.MerkleTree.new(leaves.reshape(n, 1), 0)
+    assert len(m) == 2 * n - 1 and m.get_peaks().shape[0] == 1
+    assert np.array_equal(m.bagging_the_peaks(), t1.cap[0])
+    el, d1 = m.elements, t1.digests
+    pos = lambda h, k: 2 * (((k + 1) << h) - 1) - bin(((k + 1) << h) - 1).count("1") + h
+    for _ in range(2000):
+        h = rnd.randrange(0, lg)
+        k = rnd.randrange(n >> h)
+        assert np.array_equal(el[pos(h, k)], d1[node(h, k)])
+    del el, d1, t1
+    m2 = api.mmr.MMR.new(); m2.extend(leaves[:n - 1])
+    peaks = m2.get_peaks()
+    assert peaks.shape[0] == 24 and len(m2) == 2 * (n - 1) - 23
+    assert np.array_equal(m2.bagging_the_peaks(), oracle.hash_or_noop(peaks.reshape(-1)))
+    idx = (splitmix_felts(6, 1024) % np.uint64(n - 1)).astype(np.uint64)
+    sib, left, ln = m2.prove_batch(idx)
+    st = api.mmr.verify_batch(leaves[idx.astype(np.int64)], sib, left, ln, peaks, m2.bagging_the_peaks())
+    assert (st == 1).all()
+    # one proof end to end against the oracle's verifier
+    i = int(idx[0])
+    assert oracle.mmr_verify(int(leaves[i]), m2.bagging_the_peaks(), sib[0, :ln[0]], left[0, :ln[0]], peaks) == 1
+
+
 # ---- MMR -------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n", list(range(1, 36)) + [63, 64, 65, 70, 100, 255, 1000, 4097])
 def test_mmr_extend_vs_sequential_add_leaf(api, oracle, n):
