@@ -32,6 +32,8 @@ struct pmt_ctx {
   // copy streams + events of the pipelined host-buffer tree build (created on first use)
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
   std::vector<cudaEvent_t> ev;
+  // levels with at most this many nodes run the cooperative kernel (COOP_MAX; PMT_COOP_MAX_LOG2 is a tuning knob)
+  size_t coop_max = (size_t)1 << 13;
 };
 
 static inline void prof_begin(pmt_ctx* c, const char* name, double units) {
@@ -137,7 +139,7 @@ constexpr size_t TOP_FUSE = 16;   // levels with <= 16 nodes are fused into one 
 template <class Layout>
 int launch_level(pmt_ctx* c, const Layout& lay, int l, size_t k0, size_t count) {
   if (count == 0) return PMT_OK;
-  if (count > COOP_MAX) {
+  if (count > c->coop_max) {
     TAG(c, "k_level", count);
     k_level<Layout><<<grid_for(c, count), BLOCK, 0, c->stream>>>(lay, l, k0, count);
   } else {
@@ -192,6 +194,11 @@ int pmt_init(pmt_ctx** out, int device_id) {
   }
   c->sms = prop.multiProcessorCount;
   c->stream = c->own_stream;
+  c->coop_max = COOP_MAX;
+  if (const char* e2 = getenv("PMT_COOP_MAX_LOG2")) {   // tuning knob (tools/bench_configs.py), like PMT_PIPELINE_LOG2_CHUNKS
+    const int lg = atoi(e2);
+    if (lg >= 4 && lg <= 24) c->coop_max = (size_t)1 << lg;
+  }
   *out = c;
   return PMT_OK;
 }

@@ -300,7 +300,7 @@ def test_full_size_properties_2p24(api, oracle):
     del el, d1, t1
     m2 = api.mmr.MMR.new(); m2.extend(leaves[:n - 1])
     peaks = m2.get_peaks()
-    assert peaks.shape[0] == 24 and len(m2) == 2 * (n - 1) - 23
+    assert peaks.shape[0] == 24 and len(m2) == 2 * (n - 1) - 24
     assert np.array_equal(m2.bagging_the_peaks(), oracle.hash_or_noop(peaks.reshape(-1)))
     idx = (splitmix_felts(6, 1024) % np.uint64(n - 1)).astype(np.uint64)
     sib, left, ln = m2.prove_batch(idx)
