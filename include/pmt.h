@@ -144,6 +144,26 @@ int pmt_mmr_verify_dev(pmt_ctx* ctx, const uint64_t* d_leaves, size_t n_idx, con
 int pmt_mmr_bag(pmt_ctx* ctx, const uint64_t* elements, size_t n_leaves, uint64_t* root_out);
 int pmt_mmr_peaks(pmt_ctx* ctx, const uint64_t* elements, size_t n_leaves, uint64_t* peaks_out, uint32_t* n_peaks_out);
 
+/* ---- host-buffer proofs and verification ---------------------------------------------------------------------------------
+ * Proofs are gathers from the arrays the host-buffer builders filled: done on the host, no GPU work (the reference does
+ * the same lookups after cloning the whole tree: simple_merkle_tree.rs:55-74, merkle_mountain_ranges.rs:147-223).  An
+ * index the reference would panic on is PMT_E_RANGE.  Output layouts as for the *_dev forms. */
+int pmt_simple_tree_prove(pmt_ctx* ctx, const uint64_t* levels, size_t n, const uint64_t* idx, size_t n_idx,
+                          uint64_t* siblings_out);
+int pmt_merkle_prove(pmt_ctx* ctx, const uint64_t* digests, size_t n, uint32_t cap_height, const uint64_t* idx, size_t n_idx,
+                     uint64_t* siblings_out);
+int pmt_mmr_prove(pmt_ctx* ctx, const uint64_t* elements, size_t n_leaves, const uint64_t* leaf_idx, size_t n_idx,
+                  uint64_t* siblings_out, uint8_t* on_left_out, uint32_t* path_len_out);
+/* verify_merkle_proof (:91-109), verify_merkle_proof_to_cap, MMR_proof::verify (:232-252) for a batch in HOST buffers: the
+ * batch is uploaded, every path is folded on the GPU, the verdicts come back; synchronous. */
+int pmt_simple_tree_verify(pmt_ctx* ctx, const uint64_t* leaves, const uint64_t* idx, size_t n_idx, const uint64_t* root,
+                           const uint64_t* proofs, size_t path_len, uint8_t* ok_out);
+int pmt_merkle_verify(pmt_ctx* ctx, const uint64_t* leaf_rows, size_t width, const uint64_t* idx, size_t n_idx,
+                      const uint64_t* cap, uint32_t cap_height, const uint64_t* proofs, size_t path_len, uint8_t* ok_out);
+int pmt_mmr_verify(pmt_ctx* ctx, const uint64_t* leaves, size_t n_idx, const uint64_t* siblings, const uint8_t* on_left,
+                   const uint32_t* path_len, const uint64_t* peaks, uint32_t n_peaks, const uint64_t* root,
+                   int8_t* status_out);
+
 #ifdef __cplusplus
 }
 #endif

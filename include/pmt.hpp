@@ -83,23 +83,6 @@ class Engine {
 };
 
 namespace detail {
-// device scratch for the batch verifiers (pmt_malloc / pmt_free: the ABI's allocator for hosts without their own)
-class DeviceBuf {
- public:
-  DeviceBuf(const Engine& e, size_t bytes) : e_(e) { e_.check(pmt_malloc(e_.ctx(), bytes ? bytes : 1, &p_)); }
-  DeviceBuf(const Engine& e, const void* host, size_t bytes) : DeviceBuf(e, bytes) {
-    if (bytes) e_.check(pmt_memcpy_h2d(e_.ctx(), p_, host, bytes));
-  }
-  ~DeviceBuf() { pmt_free(e_.ctx(), p_); }
-  DeviceBuf(const DeviceBuf&) = delete;
-  DeviceBuf& operator=(const DeviceBuf&) = delete;
-  template <class T> T* as() const { return static_cast<T*>(p_); }
-  void download(void* host, size_t bytes) const { e_.check(pmt_memcpy_d2h(e_.ctx(), host, p_, bytes)); }
-
- private:
-  const Engine& e_;
-  void* p_ = nullptr;
-};
 inline const uint64_t* words(const std::vector<HashOut>& v) { return reinterpret_cast<const uint64_t*>(v.data()); }
 inline uint64_t* words(std::vector<HashOut>& v) { return reinterpret_cast<uint64_t*>(v.data()); }
 inline unsigned popcount(uint64_t x) { return (unsigned)__builtin_popcountll(x); }
@@ -163,12 +146,8 @@ inline std::vector<bool> verify_merkle_proofs(const Engine& e, const std::vector
     if (p.size() != path_len) throw Error(PMT_E_INVALID_ARG, "verify_merkle_proofs: proofs of different lengths");
     flat.insert(flat.end(), p.begin(), p.end());
   }
-  detail::DeviceBuf d_leaves(e, leaves.data(), 8 * n), d_idx(e, leaf_indices.data(), 8 * n), d_root(e, &root, 32),
-      d_proofs(e, flat.data(), 32 * flat.size()), d_ok(e, n);
-  e.check(pmt_simple_tree_verify_dev(e.ctx(), d_leaves.as<uint64_t>(), d_idx.as<uint64_t>(), n, d_root.as<uint64_t>(),
-                                     d_proofs.as<uint64_t>(), path_len, d_ok.as<uint8_t>()));
   std::vector<uint8_t> ok(n);
-  d_ok.download(ok.data(), n);
+  e.check(pmt_simple_tree_verify(e.ctx(), leaves.data(), leaf_indices.data(), n, root.elements.data(), detail::words(flat), path_len, ok.data()));
   return std::vector<bool>(ok.begin(), ok.end());
 }
 
@@ -212,12 +191,9 @@ struct MMR_proof {
     std::array<uint8_t, 32> left{};
     for (size_t j = 0; j < merkle_proof.size(); j++) { sib[j] = merkle_proof[j].first; left[j] = merkle_proof[j].second; }
     const uint32_t len = (uint32_t)merkle_proof.size();
-    detail::DeviceBuf d_leaf(e, &leaf, 8), d_sib(e, sib.data(), sizeof sib), d_left(e, left.data(), 32), d_len(e, &len, 4),
-        d_peaks(e, peaks.data(), 32 * peaks.size()), d_root(e, &root, 32), d_status(e, 1);
-    e.check(pmt_mmr_verify_dev(e.ctx(), d_leaf.as<uint64_t>(), 1, d_sib.as<uint64_t>(), d_left.as<uint8_t>(), d_len.as<uint32_t>(),
-                               d_peaks.as<uint64_t>(), (uint32_t)peaks.size(), d_root.as<uint64_t>(), d_status.as<int8_t>()));
     int8_t status = 0;
-    d_status.download(&status, 1);
+    e.check(pmt_mmr_verify(e.ctx(), &leaf, 1, reinterpret_cast<const uint64_t*>(sib.data()), left.data(), &len, detail::words(peaks),
+                           (uint32_t)peaks.size(), root.elements.data(), &status));
     if (status < 0) throw Error(PMT_E_INVALID_ARG, "assert!(self.peaks.contains(&next_hash)) (merkle_mountain_ranges.rs:245)");
     return status == 1;
   }
@@ -346,12 +322,9 @@ struct MerkleTree {
 inline bool verify_merkle_proof_to_cap(const Engine& e, const std::vector<F>& leaf_data, size_t leaf_index, const MerkleCap& cap,
                                        const MerkleProof& proof) {
   const uint64_t idx = leaf_index;
-  detail::DeviceBuf d_leaf(e, leaf_data.data(), 8 * leaf_data.size()), d_idx(e, &idx, 8), d_cap(e, cap.hashes.data(), 32 * cap.hashes.size()),
-      d_proof(e, proof.siblings.data(), 32 * proof.siblings.size()), d_ok(e, 1);
-  e.check(pmt_merkle_verify_dev(e.ctx(), d_leaf.as<uint64_t>(), leaf_data.size(), d_idx.as<uint64_t>(), 1, d_cap.as<uint64_t>(),
-                                (uint32_t)cap.height(), d_proof.as<uint64_t>(), proof.siblings.size(), d_ok.as<uint8_t>()));
   uint8_t ok = 0;
-  d_ok.download(&ok, 1);
+  e.check(pmt_merkle_verify(e.ctx(), leaf_data.data(), leaf_data.size(), &idx, 1, detail::words(cap.hashes), (uint32_t)cap.height(),
+                            detail::words(proof.siblings), proof.siblings.size(), &ok));
   return ok == 1;
 }
 

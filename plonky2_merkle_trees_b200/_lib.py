@@ -61,6 +61,13 @@ _SIGNATURES = {
     "pmt_mmr_verify_dev": (_INT, [_VP, _VP, _SZ, _VP, _VP, _VP, _VP, _U32, _VP, _VP]),
     "pmt_mmr_bag": (_INT, [_VP, u64p, _SZ, u64p]),
     "pmt_mmr_peaks": (_INT, [_VP, u64p, _SZ, u64p, u32p]),
+    # host-buffer proofs (gathers on the host) and verification (upload, fold on the GPU, download)
+    "pmt_simple_tree_prove": (_INT, [_VP, u64p, _SZ, u64p, _SZ, u64p]),
+    "pmt_merkle_prove": (_INT, [_VP, u64p, _SZ, _U32, u64p, _SZ, u64p]),
+    "pmt_mmr_prove": (_INT, [_VP, u64p, _SZ, u64p, _SZ, u64p, u8p, u32p]),
+    "pmt_simple_tree_verify": (_INT, [_VP, u64p, u64p, _SZ, u64p, u64p, _SZ, u8p]),
+    "pmt_merkle_verify": (_INT, [_VP, u64p, _SZ, u64p, _SZ, u64p, _U32, u64p, _SZ, u8p]),
+    "pmt_mmr_verify": (_INT, [_VP, u64p, _SZ, u64p, u8p, u32p, u64p, _U32, u64p, i8p]),
 }
 
 _lib = None

@@ -873,4 +873,135 @@ int pmt_mmr_bag(pmt_ctx* c, const uint64_t* elements, size_t n_leaves, uint64_t*
   return PMT_OK;
 }
 
+// ---- host-buffer proofs: gathers from the caller's arrays (nothing to compute: done on the host, like get_peaks) ---------
+static inline void copy_digest_canonical(uint64_t* dst, const uint64_t* src) {
+  for (int e = 0; e < 4; e++) dst[e] = src[e] >= PMT_P ? src[e] - PMT_P : src[e];
+}
+
+// get_merkle_proof (simple_merkle_tree.rs:55-74) for a batch, from the level-major host array pmt_simple_tree_build filled
+int pmt_simple_tree_prove(pmt_ctx* c, const uint64_t* levels, size_t n, const uint64_t* idx, size_t n_idx, uint64_t* siblings_out) {
+  if (!c) return PMT_E_INVALID_ARG;
+  const int lg = log2_strict(n);
+  if (lg < 1) return fail(c, PMT_E_NOT_POW2, "simple tree prove: bad leaf count %zu", n);
+  if (n_idx == 0) return PMT_OK;
+  if (!levels || !idx || !siblings_out) return fail(c, PMT_E_INVALID_ARG, "simple tree prove: null pointer");
+  for (size_t q = 0; q < n_idx; q++) {
+    if (idx[q] >= n) return fail(c, PMT_E_RANGE, "assert!(leaf_index < self.tree[0].len()): %llu >= %zu (simple_merkle_tree.rs:56)", (unsigned long long)idx[q], n);
+    for (int l = 0; l < lg; l++) {
+      const size_t k = (idx[q] >> l) ^ 1;
+      copy_digest_canonical(siblings_out + 4 * (q * lg + l), levels + 4 * ((2 * n - ((2 * n) >> l)) + k));
+    }
+  }
+  return PMT_OK;
+}
+
+// [UPSTREAM] MerkleTree::prove for a batch, from the host `digests` array pmt_merkle_tree_build filled
+int pmt_merkle_prove(pmt_ctx* c, const uint64_t* digests, size_t n, uint32_t cap_height, const uint64_t* idx, size_t n_idx,
+                     uint64_t* siblings_out) {
+  if (!c) return PMT_E_INVALID_ARG;
+  const int lg = log2_strict(n);
+  if (lg < 0) return fail(c, PMT_E_NOT_POW2, "prove: %zu leaves is not a power of two", n);
+  if ((int)cap_height > lg) return fail(c, PMT_E_RANGE, "prove: cap_height %u > log2 n", cap_height);
+  const int L = lg - (int)cap_height;
+  if (n_idx == 0 || L == 0) return PMT_OK;
+  if (!digests || !idx || !siblings_out) return fail(c, PMT_E_INVALID_ARG, "prove: null pointer");
+  for (size_t q = 0; q < n_idx; q++) {
+    if (idx[q] >= n) return fail(c, PMT_E_RANGE, "prove: leaf index %llu >= %zu", (unsigned long long)idx[q], n);
+    for (int l = 0; l < L; l++)
+      copy_digest_canonical(siblings_out + 4 * (q * L + l), digests + 4 * plonky2_index(L, l, (idx[q] >> l) ^ 1));
+  }
+  return PMT_OK;
+}
+
+// get_proof_normal_index (merkle_mountain_ranges.rs:203-223) for a batch, from the host `elements` array; same output
+// layout as pmt_mmr_prove_dev (32 entries per proof)
+int pmt_mmr_prove(pmt_ctx* c, const uint64_t* elements, size_t n_leaves, const uint64_t* leaf_idx, size_t n_idx,
+                  uint64_t* siblings_out, uint8_t* on_left_out, uint32_t* path_len_out) {
+  if (!c) return PMT_E_INVALID_ARG;
+  if (n_idx == 0) return PMT_OK;
+  if (!elements || !leaf_idx || !siblings_out || !on_left_out || !path_len_out) return fail(c, PMT_E_INVALID_ARG, "mmr prove: null pointer");
+  if (n_leaves == 0 || n_leaves > ((size_t)1 << 30)) return fail(c, PMT_E_RANGE, "mmr prove: bad leaf count");
+  for (size_t q = 0; q < n_idx; q++) {
+    const size_t i = leaf_idx[q];
+    if (i >= n_leaves) return fail(c, PMT_E_RANGE, "mmr prove: leaf index %zu >= %zu", i, n_leaves);
+    int H = 0;
+    size_t base = 0;
+    for (int b = 63; b >= 0; b--)
+      if ((n_leaves >> b) & 1) {
+        if (i < base + ((size_t)1 << b)) { H = b; break; }
+        base += (size_t)1 << b;
+      }
+    path_len_out[q] = (uint32_t)H;
+    for (int j = 0; j < H; j++) {
+      const size_t k = (i >> j) ^ 1, last = ((k + 1) << j) - 1;                        // sibling (height j, index k)
+      const size_t pos = 2 * last - (size_t)__builtin_popcountll((unsigned long long)last) + (size_t)j;
+      copy_digest_canonical(siblings_out + 4 * (32 * q + j), elements + 4 * pos);
+      on_left_out[32 * q + j] = (uint8_t)((i >> j) & 1);
+    }
+  }
+  return PMT_OK;
+}
+
+// ---- host-buffer verification: upload the batch, fold every path on the GPU, download the verdicts ------------------------
+int pmt_merkle_verify(pmt_ctx* c, const uint64_t* leaf_rows, size_t w, const uint64_t* idx, size_t n_idx, const uint64_t* cap,
+                      uint32_t cap_height, const uint64_t* proofs, size_t path_len, uint8_t* ok_out) {
+  if (int rc = bind(c)) return rc;
+  if (n_idx == 0) return PMT_OK;
+  if (!leaf_rows || !idx || !cap || !ok_out || (!proofs && path_len)) return fail(c, PMT_E_INVALID_ARG, "verify: null pointer");
+  if (w == 0 || cap_height > 40 || path_len > 63) return fail(c, PMT_E_INVALID_ARG, "verify: bad width / cap_height / path_len");
+  const size_t b_rows = n_idx * w * 8, b_idx = n_idx * 8, b_cap = ((size_t)32) << cap_height, b_pr = n_idx * path_len * 32;
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  void* a;
+  if (int rc = arena_get(c, 0, al(b_rows) + al(b_idx) + al(b_cap) + al(b_pr) + al(n_idx), &a)) return rc;
+  char* p = (char*)a;
+  uint64_t* d_rows = (uint64_t*)p; p += al(b_rows);
+  uint64_t* d_idx = (uint64_t*)p; p += al(b_idx);
+  uint64_t* d_cap = (uint64_t*)p; p += al(b_cap);
+  uint64_t* d_pr = (uint64_t*)p; p += al(b_pr);
+  uint8_t* d_ok = (uint8_t*)p;
+  H2D(c, d_rows, leaf_rows, b_rows);
+  H2D(c, d_idx, idx, b_idx);
+  H2D(c, d_cap, cap, b_cap);
+  if (b_pr) H2D(c, d_pr, proofs, b_pr);
+  if (int rc = pmt_merkle_verify_dev(c, d_rows, w, d_idx, n_idx, d_cap, cap_height, d_pr, path_len, d_ok)) return rc;
+  D2H(c, ok_out, d_ok, n_idx);
+  FINISH(c);
+  return PMT_OK;
+}
+
+int pmt_simple_tree_verify(pmt_ctx* c, const uint64_t* leaves, const uint64_t* idx, size_t n_idx, const uint64_t* root,
+                           const uint64_t* proofs, size_t path_len, uint8_t* ok_out) {
+  return pmt_merkle_verify(c, leaves, 1, idx, n_idx, root, 0, proofs, path_len, ok_out);
+}
+
+int pmt_mmr_verify(pmt_ctx* c, const uint64_t* leaves, size_t n_idx, const uint64_t* siblings, const uint8_t* on_left,
+                   const uint32_t* path_len, const uint64_t* peaks, uint32_t n_peaks, const uint64_t* root, int8_t* status_out) {
+  if (int rc = bind(c)) return rc;
+  if (n_idx == 0) return PMT_OK;
+  if (!leaves || !siblings || !on_left || !path_len || !peaks || !root || !status_out) return fail(c, PMT_E_INVALID_ARG, "mmr verify: null pointer");
+  if (n_peaks == 0 || n_peaks > 64) return fail(c, PMT_E_INVALID_ARG, "mmr verify: bad peak count");
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t b_lv = n_idx * 8, b_sib = n_idx * 32 * 32, b_left = n_idx * 32, b_len = n_idx * 4, b_pk = (size_t)n_peaks * 32;
+  void* a;
+  if (int rc = arena_get(c, 0, al(b_lv) + al(b_sib) + al(b_left) + al(b_len) + al(b_pk) + al(32) + al(n_idx), &a)) return rc;
+  char* p = (char*)a;
+  uint64_t* d_lv = (uint64_t*)p; p += al(b_lv);
+  uint64_t* d_sib = (uint64_t*)p; p += al(b_sib);
+  uint8_t* d_left = (uint8_t*)p; p += al(b_left);
+  uint32_t* d_len = (uint32_t*)p; p += al(b_len);
+  uint64_t* d_pk = (uint64_t*)p; p += al(b_pk);
+  uint64_t* d_root = (uint64_t*)p; p += al(32);
+  int8_t* d_st = (int8_t*)p;
+  H2D(c, d_lv, leaves, b_lv);
+  H2D(c, d_sib, siblings, b_sib);
+  H2D(c, d_left, on_left, b_left);
+  H2D(c, d_len, path_len, b_len);
+  H2D(c, d_pk, peaks, b_pk);
+  H2D(c, d_root, root, 32);
+  if (int rc = pmt_mmr_verify_dev(c, d_lv, n_idx, d_sib, d_left, d_len, d_pk, n_peaks, d_root, d_st)) return rc;
+  D2H(c, status_out, d_st, n_idx);
+  FINISH(c);
+  return PMT_OK;
+}
+
 }  // extern "C"

@@ -429,6 +429,85 @@ def test_mmr_2p20_against_tree(api):
     assert (st == 1).all()
 
 
+# ---- host-buffer proofs and verification (pmt_*_prove / pmt_*_verify on the caller's arrays) ------------------------
+def test_host_buffer_prove_and_verify_abi(ctx, oracle):
+    """The whole proof path with HOST buffers only, as the Rust shim would drive it: build -> prove (host gathers) -> verify
+    (upload, fold on the GPU, download), each step against the oracle, incl. the reference's panics as PMT_E_RANGE."""
+    import ctypes as C
+    from plonky2_merkle_trees_b200._lib import PMT_E_RANGE, PmtError, ptr, u8p, u32p, i8p
+    p8 = lambda a: a.ctypes.data_as(u8p)
+    # simple tree
+    n, lg = 1 << 9, 9
+    leaves = splitmix_felts(3, n)
+    levels = np.zeros((2 * n - 2, 4), np.uint64); root = np.zeros(4, np.uint64)
+    ctx.call("pmt_simple_tree_build", ptr(leaves), n, ptr(levels), ptr(root))
+    idx = np.array([0, 1, 2, 255, 256, n - 1, 77], np.uint64)
+    sib = np.zeros((idx.size, lg, 4), np.uint64)
+    ctx.call("pmt_simple_tree_prove", ptr(levels), n, ptr(idx), idx.size, ptr(sib))
+    for q, i in enumerate(idx):
+        assert np.array_equal(sib[q], oracle.simple_tree_proof(levels, n, int(i)))
+    ok = np.zeros(idx.size, np.uint8)
+    lv = np.ascontiguousarray(leaves[idx.astype(np.int64)])
+    ctx.call("pmt_simple_tree_verify", ptr(lv), ptr(idx), idx.size, ptr(root), ptr(sib), lg, p8(ok))
+    assert ok.all()
+    bad = sib.copy(); bad[3, 4, 1] ^= np.uint64(1)
+    ctx.call("pmt_simple_tree_verify", ptr(lv), ptr(idx), idx.size, ptr(root), ptr(bad), lg, p8(ok))
+    assert list(ok) == [1, 1, 1, 0, 1, 1, 1]
+    with pytest.raises(PmtError) as e:
+        ctx.call("pmt_simple_tree_prove", ptr(levels), n, ptr(np.array([n], np.uint64)), 1, ptr(sib))   # :56
+    assert e.value.code == PMT_E_RANGE
+    # plonky2 tree, wide leaves, cap 3
+    n, w, h = 1 << 8, 11, 3
+    rows = splitmix_felts(4, n * w).reshape(n, w)
+    dig = np.zeros((2 * (n - (1 << h)), 4), np.uint64); cap = np.zeros((1 << h, 4), np.uint64)
+    ctx.call("pmt_merkle_tree_build", ptr(rows), n, w, h, ptr(dig), ptr(cap))
+    idx = np.array([0, 31, 32, 200, n - 1], np.uint64)
+    L = 8 - h
+    sib = np.zeros((idx.size, L, 4), np.uint64)
+    ctx.call("pmt_merkle_prove", ptr(dig), n, h, ptr(idx), idx.size, ptr(sib))
+    for q, i in enumerate(idx):
+        assert np.array_equal(sib[q], oracle.merkle_prove(dig, n, h, int(i)))
+    ok = np.zeros(idx.size, np.uint8)
+    rr = np.ascontiguousarray(rows[idx.astype(np.int64)])
+    ctx.call("pmt_merkle_verify", ptr(rr), w, ptr(idx), idx.size, ptr(cap), h, ptr(sib), L, p8(ok))
+    assert ok.all()
+    ctx.call("pmt_merkle_verify", ptr(rr), w, ptr(idx ^ np.uint64(1)), idx.size, ptr(cap), h, ptr(sib), L, p8(ok))
+    assert not ok.any()
+    # MMR, ragged size
+    nl = 1000
+    leaves = splitmix_felts(5, nl)
+    el = np.zeros((2 * nl - bin(nl).count("1"), 4), np.uint64)
+    ctx.call("pmt_mmr_extend", ptr(el), 0, ptr(leaves), nl)
+    assert np.array_equal(el, oracle.mmr_extend(None, leaves))
+    idx = np.array([0, 511, 512, 900, 992, 999], np.uint64)
+    sib = np.zeros((idx.size, 32, 4), np.uint64); left = np.zeros((idx.size, 32), np.uint8); ln = np.zeros(idx.size, np.uint32)
+    ctx.call("pmt_mmr_prove", ptr(el), nl, ptr(idx), idx.size, ptr(sib), p8(left), ln.ctypes.data_as(u32p))
+    for q, i in enumerate(idx):
+        osib, oleft = oracle.mmr_subtree_proof(el, 2 * int(i) - bin(int(i)).count("1"))
+        assert ln[q] == len(oleft) and np.array_equal(sib[q, :ln[q]], osib) and list(left[q, :ln[q]]) == list(oleft)
+    peaks = np.zeros((64, 4), np.uint64); npk = C.c_uint32(0)
+    ctx.call("pmt_mmr_peaks", ptr(el), nl, ptr(peaks), C.byref(npk))
+    peaks = np.ascontiguousarray(peaks[:npk.value])
+    bag = np.zeros(4, np.uint64)
+    ctx.call("pmt_mmr_bag", ptr(el), nl, ptr(bag))
+    st = np.zeros(idx.size, np.int8)
+    lv = np.ascontiguousarray(leaves[idx.astype(np.int64)])
+    ctx.call("pmt_mmr_verify", ptr(lv), idx.size, ptr(sib), p8(left), ln.ctypes.data_as(u32p), ptr(peaks), npk.value, ptr(bag),
+             st.ctypes.data_as(i8p))
+    assert (st == 1).all()
+    lv2 = lv.copy(); lv2[2] ^= np.uint64(1)          # wrong leaf: the subtree root is not a peak -> the reference asserts (:245)
+    wrong_root = bag.copy(); wrong_root[0] ^= np.uint64(1)
+    ctx.call("pmt_mmr_verify", ptr(lv2), idx.size, ptr(sib), p8(left), ln.ctypes.data_as(u32p), ptr(peaks), npk.value, ptr(bag),
+             st.ctypes.data_as(i8p))
+    assert list(st) == [1, 1, -1, 1, 1, 1]
+    ctx.call("pmt_mmr_verify", ptr(lv), idx.size, ptr(sib), p8(left), ln.ctypes.data_as(u32p), ptr(peaks), npk.value, ptr(wrong_root),
+             st.ctypes.data_as(i8p))
+    assert (st == 0).all()
+    with pytest.raises(PmtError) as e:
+        ctx.call("pmt_mmr_prove", ptr(el), nl, ptr(np.array([nl], np.uint64)), 1, ptr(sib), p8(left), ln.ctypes.data_as(u32p))
+    assert e.value.code == PMT_E_RANGE
+
+
 # ---- narrow leaves, big trees: the leaf copy is fused into level 1 (k_leaves_level1) ------------------------------------------
 @pytest.mark.parametrize("w,h", [(1, 0), (3, 2), (4, 0), (4, 5)])
 def test_fused_leaf_level_plonky2(ctx, api, oracle, w, h):
