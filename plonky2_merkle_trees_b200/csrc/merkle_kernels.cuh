@@ -53,6 +53,9 @@ using poseidon::WIDTH;
 #ifndef PMT_PPIPE
 #define PMT_PPIPE 0
 #endif
+#ifndef PMT_FQ_COMBINE
+#define PMT_FQ_COMBINE 0   // recombination of the fp64 sums: 0 = ALU only, 1 = IMAD.WIDE folds, 2 = IMAD.WIDE in full layers only, 3 = in pairs only
+#endif
 #ifndef PMT_FQ_SPLIT
 #define PMT_FQ_SPLIT 0   // 1: fence the high halves behind the low halves (measured slower: 1.51 against 1.55)
 #endif
@@ -67,7 +70,7 @@ __device__ __forceinline__ void permute_impl(uint64_t (&s)[WIDTH]) {
   poseidon::permute_paired<PMT_SBOX_FMA_MASK, PMT_PART_FMA_MASK, PMT_COLUMN != 0, PMT_CVT_I2F != 0, PMT_COMBINE_ALU != 0, CAP_ZERO,
                            OUT4>(s);
 #elif PMT_PERM == 4
-  poseidon::permute_paired_freq<PMT_SBOX_FMA_MASK, PMT_PART_FMA_MASK, PMT_CVT_I2F != 0, CAP_ZERO, OUT4, PMT_FQ_SPLIT>(s);
+  poseidon::permute_paired_freq<PMT_SBOX_FMA_MASK, PMT_PART_FMA_MASK, PMT_CVT_I2F != 0, CAP_ZERO, OUT4, PMT_FQ_SPLIT, PMT_FQ_COMBINE>(s);
 #elif PMT_PERM == 2
   poseidon::permute_rounds<PMT_SBOX_FMA_MASK, PMT_PART_FMA_MASK, PMT_COLUMN != 0, PMT_CVT_I2F != 0, PMT_COMBINE_ALU != 0, CAP_ZERO,
                            OUT4>(s);

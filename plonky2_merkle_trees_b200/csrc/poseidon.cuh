@@ -549,7 +549,7 @@ __device__ __forceinline__ void permute_paired(uint64_t (&s)[WIDTH]) {
 // FQ_SPLIT: finish the low halves before the high halves are converted (lower register pressure) instead of leaving the
 // order to ptxas.
 template <int SBOX_FMA_MASK = 0, int PART_FMA_MASK = 0, bool CVT_I2F = true, bool CAP_ZERO = false, bool OUT4 = false,
-          int FQ_SPLIT = 1>
+          int FQ_SPLIT = 1, int COMBINE_MODE = 0>
 __device__ __forceinline__ void permute_paired_freq(uint64_t (&s)[WIDTH]) {
   const double MAGIC = 4503599627370496.0;  // 2^52
   const uint32_t zero = PMT_ZERO32;
@@ -589,7 +589,7 @@ __device__ __forceinline__ void permute_paired_freq(uint64_t (&s)[WIDTH]) {
         }
         freq::full_layer_half<2>(x, &PMT_RC_DM[2 * WIDTH * r + 1], ohi);
 #pragma unroll
-        for (int i = 0; i < WIDTH; i++) s[i] = combine_magic_alu(olo[i], ohi[i]);
+        for (int i = 0; i < WIDTH; i++) s[i] = (COMBINE_MODE == 1 || COMBINE_MODE == 2) ? combine_magic_fma(olo[i], ohi[i]) : combine_magic_alu(olo[i], ohi[i]);
       }
     }
     if (half == 0) {
@@ -611,7 +611,7 @@ __device__ __forceinline__ void permute_paired_freq(uint64_t (&s)[WIDTH]) {
         freq::pair_half_end<2>(ylo, half_of(xs, 0), x0lo, l0lo, &PMT_FQ_KPAIR_DM[2 * WIDTH * pair]);
         freq::pair_half_end<2>(yhi, half_of(xs, 1), x0hi, l0hi, &PMT_FQ_KPAIR_DM[2 * WIDTH * pair + 1]);
 #pragma unroll
-        for (int i = 0; i < WIDTH; i++) s[i] = combine_magic_alu(ylo[i], yhi[i]);
+        for (int i = 0; i < WIDTH; i++) s[i] = (COMBINE_MODE == 1 || COMBINE_MODE == 3) ? combine_magic_fma(ylo[i], yhi[i]) : combine_magic_alu(ylo[i], yhi[i]);
       }
     }
   }
