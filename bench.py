@@ -286,7 +286,11 @@ def run_ours(args):
 
     # ---- e2e: host-buffer C ABI call, pinned host memory, H2D + D2H inside the timed region ------------------------------
     from plonky2_merkle_trees_b200._lib import u64p
+    from plonky2_merkle_trees_b200.device import bind_to_gpu_numa_node
     import ctypes as C
+    # host buffers on the GPU's own NUMA node (one rank per GPU: otherwise 8 ranks' pinned buffers land wherever each
+    # process happened to run); the affinity is restored before the CPU baseline below uses the host cores
+    numa_node, prev_affinity = (None, None) if os.environ.get("PMT_NO_NUMA_BIND") else bind_to_gpu_numa_node(local_rank)
     h_leaves = torch.empty((n_local, WIDTH), dtype=torch.int64).pin_memory()
     h_leaves.copy_(d_leaves)
     n_dig = 2 * (n_local - 1)
@@ -319,6 +323,8 @@ def run_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_ms = float(te.item())
     e2e_value = n_total / (e2e_ms * 1e-3)
+    if prev_affinity is not None:
+        os.sched_setaffinity(0, prev_affinity)
 
     # parity spot check of what was just measured (size-independent property: leaf digests are the canonical no-op copy)
     hd = h_digests.numpy().view(np.uint64)
@@ -378,7 +384,8 @@ def run_ours(args):
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": "leaves/s", "h2d_bytes_per_step": n_local * WIDTH * 8,
                 "d2h_bytes_per_step": (n_dig + 1) * 32, "ms_per_step": e2e_ms,
-                "api": "pmt_merkle_tree_build (host buffers, pinned; every digest downloaded)"},
+                "api": "pmt_merkle_tree_build (host buffers, pinned; every digest downloaded)",
+                "host_numa_node": numa_node},
         "gpu_launches": launches,
         "kernels": prof,
         "roofline": roofline,
