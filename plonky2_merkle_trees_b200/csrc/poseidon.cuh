@@ -545,7 +545,7 @@ __device__ __forceinline__ void permute_paired(uint64_t (&s)[WIDTH]) {
 }
 
 // Paired form with the MDS layers in the frequency domain (poseidon_freq.cuh): 204 fp64 operations per full layer instead
-// of 288, 260 per pair of partial rounds instead of 336 -- the same digests (tools/check_freq.cpp, tests/test_gpu_parity.py).
+// of 288, 260 per pair of partial rounds instead of 336 -- the same digests (tests/cpp/check_freq.cpp, tests/test_gpu_parity.py).
 // FQ_SPLIT: finish the low halves before the high halves are converted (lower register pressure) instead of leaving the
 // order to ptxas.
 template <int SBOX_FMA_MASK = 0, int PART_FMA_MASK = 0, bool CVT_I2F = true, bool CAP_ZERO = false, bool OUT4 = false,

@@ -18,7 +18,7 @@
 //
 // tools/gen_freq_constants.py derives the tables, checks both identities against the matrix forms in exact rational
 // arithmetic and PROVES that every intermediate value below (same operation order) is exactly representable for all
-// inputs; tools/check_freq.cpp runs this very header on the host against the specification-form CPU permutation.
+// inputs; tests/cpp/check_freq.cpp runs this very header on the host against the specification-form CPU permutation.
 #pragma once
 #include <stdint.h>
 

@@ -5,14 +5,14 @@
 //      linear, so each intermediate value takes its extreme magnitude at a corner) for all 16 + 22 constant sets;
 //   2. as a whole permutation (full rounds + paired partial rounds, the device code's structure) against the oracle's
 //      specification-form permutation on random and edge states.
-// build: g++ -O2 -std=c++17 -ffp-contract=off -o /tmp/check_freq tools/check_freq.cpp -Loracle -lpmt_oracle -Wl,-rpath,$PWD/oracle
+// build: g++ -O2 -std=c++17 -ffp-contract=off -o /tmp/check_freq tests/cpp/check_freq.cpp -Loracle -lpmt_oracle -Wl,-rpath,$PWD/oracle
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
-#include "../oracle/pmt_oracle.h"
-#include "../oracle/poseidon_constants.h"
-#include "../plonky2_merkle_trees_b200/csrc/poseidon_freq.cuh"
+#include "../../oracle/pmt_oracle.h"
+#include "../../oracle/poseidon_constants.h"
+#include "../../plonky2_merkle_trees_b200/csrc/poseidon_freq.cuh"
 
 typedef unsigned __int128 u128;
 using namespace poseidon::freq;

@@ -167,7 +167,7 @@ def test_simple_tree_equals_plonky2_tree_cap0(oracle):
 
 def test_frequency_domain_mds_is_exact_on_the_host(tmp_path):
     """The production MDS layer (csrc/poseidon_freq.cuh: fp64, frequency-domain convolution) compiled for the HOST with g++
-    and checked by tools/check_freq.cpp: every layer output at all 4096 corners of the input cube against the integer
+    and checked by tests/cpp/check_freq.cpp: every layer output at all 4096 corners of the input cube against the integer
     matrix form for every constant set, and 200 000 whole permutations (random + edge states) against the oracle's
     specification-form permutation.  tools/gen_freq_constants.py re-derives the tables and proves the bounds."""
     import subprocess
@@ -175,7 +175,7 @@ def test_frequency_domain_mds_is_exact_on_the_host(tmp_path):
     orc.build()
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     exe = str(tmp_path / "check_freq")
-    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-o", exe, os.path.join(root, "tools", "check_freq.cpp"),
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-o", exe, os.path.join(root, "tests", "cpp", "check_freq.cpp"),
                            "-L" + os.path.join(root, "oracle"), "-lpmt_oracle", "-Wl,-rpath," + os.path.join(root, "oracle")])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout + out.stderr
