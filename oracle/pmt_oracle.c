@@ -27,15 +27,18 @@ static inline uint64_t add_no_canon(uint64_t x, uint64_t y) {
   return r + EPSILON * (uint64_t)(r < x); /* cannot overflow twice when y is a reduce-intermediate */
 }
 
+/* [UPSTREAM field/src/goldilocks_field.rs reduce128], branch-free (upstream hints the borrow branch as unlikely and
+ * uses an sbb trick on x86; a data-dependent branch here costs the scalar port 2x) */
 static inline uint64_t reduce128(u128 x) {
   uint64_t lo = (uint64_t)x, hi = (uint64_t)(x >> 64);
   uint64_t hi_hi = hi >> 32, hi_lo = hi & EPSILON;
-  uint64_t t0 = lo - hi_hi;
-  if (lo < hi_hi) t0 -= EPSILON; /* borrow: 2^64 = eps (mod p) */
-  uint64_t t1 = hi_lo * EPSILON;
-  return add_no_canon(t0, t1);
+  uint64_t t0, r;
+  uint64_t borrow = __builtin_sub_overflow(lo, hi_hi, &t0);
+  t0 -= (0 - borrow) & EPSILON; /* borrow: 2^64 = eps (mod p) */
+  uint64_t t1 = (hi_lo << 32) - hi_lo; /* hi_lo * eps */
+  uint64_t carry = __builtin_add_overflow(t0, t1, &r);
+  return r + ((0 - carry) & EPSILON); /* cannot overflow twice */
 }
-
 static inline uint64_t fadd(uint64_t a, uint64_t b) { /* a, b any u64 */
   return reduce128((u128)a + (u128)b);
 }
@@ -77,29 +80,54 @@ void pmt_oracle_permute(uint64_t s[12]) {
 
 /* ---- CPU-baseline speed path ------------------------------------------------------------------------------------
  * Same permutation, engineered the way upstream's scalar x86 path is ([UPSTREAM hash/poseidon.rs mds_layer via
- * u64 hi/lo accumulation, fast partial rounds]): the MDS layer works on 32-bit halves with plain u64 MACs (sums
- * < 2^42, one reduction per lane), partial rounds use the sparse-matrix form.  Tables re-derived by
+ * u64 hi/lo accumulation, fast partial rounds]): the MDS layer works on 32-bit halves in i64 (sums < 2^45, one
+ * reduction per lane) as a shift-and-add convolution, partial rounds use the sparse-matrix form.  Tables re-derived by
  * tools/gen_constants.py; equality with the naive form is a unit test.  Used for CPU-baseline timing. */
 static inline uint64_t reduce96(uint64_t lo, uint64_t hi /* < 2^32 */) {
   return add_no_canon(lo, hi * EPSILON);
 }
 
+/* One 32-bit half of the state through the circulant part of the MDS matrix, as a length-12 cyclic convolution split by
+ * t^12 - 1 = (t^3 - 1)(t^3 + 1)(t^6 + 1): the residues of the kernel are powers of two (64,128,64 | -4,-32,8 |
+ * 4,-8,32,2,-2,-2; the inverse's /4 and /2 folded in), so the layer is shifts and adds on i64 -- the idea of upstream's
+ * frequency-domain mds_multiply_freq.  Exact: every intermediate is an integer below 2^45. */
+static inline void mds_half_freq(const int64_t x[12], int64_t y[12]) {
+  int64_t e[6], d[6], a[3], b[3], A[3], B[3], D[6];
+  for (int j = 0; j < 6; j++) { e[j] = x[j] + x[j + 6]; d[j] = x[j] - x[j + 6]; }
+  for (int j = 0; j < 3; j++) { a[j] = e[j] + e[j + 3]; b[j] = e[j] - e[j + 3]; }
+  /* cyclic 3x3 with (16, 32, 16) */
+  A[0] = 16 * a[0] + 32 * a[2] + 16 * a[1];
+  A[1] = 16 * a[1] + 32 * a[0] + 16 * a[2];
+  A[2] = 16 * a[2] + 32 * a[1] + 16 * a[0];
+  /* negacyclic 3x3 with (-1, -8, 2) */
+  B[0] = -b[0] + 8 * b[2] - 2 * b[1];
+  B[1] = -b[1] - 8 * b[0] - 2 * b[2];
+  B[2] = -b[2] - 8 * b[1] + 2 * b[0];
+  /* negacyclic 6x6 with (2, -4, 16, 1, -1, -1) */
+  D[0] = 2 * d[0] + 4 * d[5] - 16 * d[4] - d[3] + d[2] + d[1];
+  D[1] = 2 * d[1] - 4 * d[0] - 16 * d[5] - d[4] + d[3] + d[2];
+  D[2] = 2 * d[2] - 4 * d[1] + 16 * d[0] - d[5] + d[4] + d[3];
+  D[3] = 2 * d[3] - 4 * d[2] + 16 * d[1] + d[0] + d[5] + d[4];
+  D[4] = 2 * d[4] - 4 * d[3] + 16 * d[2] + d[1] - d[0] + d[5];
+  D[5] = 2 * d[5] - 4 * d[4] + 16 * d[3] + d[2] - d[1] - d[0];
+  for (int j = 0; j < 3; j++) {
+    int64_t p = A[j] + B[j], m = A[j] - B[j];
+    y[j] = p + D[j]; y[j + 6] = p - D[j]; y[j + 3] = m + D[j + 3]; y[j + 9] = m - D[j + 3];
+  }
+}
+
 static inline void mds_layer_fast(uint64_t s[12], const uint64_t *add) {
-  static const uint64_t C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
-  uint64_t lo[24], hi[24], out[12];
-  for (int i = 0; i < 12; i++) {
-    lo[i] = lo[i + 12] = s[i] & EPSILON;
-    hi[i] = hi[i + 12] = s[i] >> 32;
-  }
+  int64_t lo[12], hi[12], L[12], H[12];
+  for (int i = 0; i < 12; i++) { lo[i] = (int64_t)(s[i] & EPSILON); hi[i] = (int64_t)(s[i] >> 32); }
+  mds_half_freq(lo, L);
+  mds_half_freq(hi, H);
+  L[0] += 8 * lo[0]; H[0] += 8 * hi[0];
   for (int r = 0; r < 12; r++) {
-    uint64_t L = 0, H = 0;
-    for (int i = 0; i < 12; i++) { L += lo[i + r] * C[i]; H += hi[i + r] * C[i]; }
-    if (r == 0) { L += lo[0] * 8; H += hi[0] * 8; }
     /* value = L + 2^32 H, H = hh 2^32 + hl  ->  L + 2^32 hl + (2^32 - 1) hh */
-    u128 v = (u128)L + ((u128)(H & EPSILON) << 32) + (u128)(H >> 32) * EPSILON + (add ? add[r] : 0);
-    out[r] = reduce96((uint64_t)v, (uint64_t)(v >> 64));
+    uint64_t l = (uint64_t)L[r], h = (uint64_t)H[r];
+    u128 v = (u128)l + ((u128)(h & EPSILON) << 32) + (u128)(h >> 32) * EPSILON + (add ? add[r] : 0);
+    s[r] = reduce96((uint64_t)v, (uint64_t)(v >> 64));
   }
-  memcpy(s, out, sizeof out);
 }
 
 /* x^7 on all 12 lanes, staged so that the 12 independent multiplications of each stage overlap in the pipeline */
