@@ -91,6 +91,13 @@ int pmt_merkle_tree_build(pmt_ctx* ctx, const uint64_t* leaves, size_t n, size_t
                           uint64_t* digests_out, uint64_t* cap_out);
 int pmt_merkle_tree_build_dev(pmt_ctx* ctx, const uint64_t* d_leaves, size_t n, size_t width, uint32_t cap_height,
                               uint64_t* d_digests, uint64_t* d_cap);
+/* MerkleTree::new over SEVERAL GPUs from one host process (the reference is a single process): n_ctx = 2^g
+ * distinct contexts, normally one per device.  ctx r builds the subtree over leaves [r n/G, (r+1) n/G) on its device from
+ * its own host thread, straight into its contiguous slice of digests_out; for cap_height < g the G subtree roots are
+ * finished on ctxs[0] and the few digests above them placed between the slices.  Host buffers, synchronous, output
+ * identical to pmt_merkle_tree_build.  (One process per GPU with an NCCL all_gather of the roots: DESIGN.md 7.) */
+int pmt_merkle_tree_build_multi(pmt_ctx* const* ctxs, size_t n_ctx, const uint64_t* leaves, size_t n, size_t width,
+                                uint32_t cap_height, uint64_t* digests_out, uint64_t* cap_out);
 /* The same tree built straight from the prover's column-major LDE values: what [UPSTREAM] fri/oracle.rs
  * PolynomialBatch::from_values / from_coeffs feeds to MerkleTree::new inside circuit_data.prove
  * (/root/reference/src/mmr/mmr_plonky2_verifier.rs:148): leaves = reverse_index_bits(transpose(columns)), i.e.

@@ -303,6 +303,32 @@ struct MerkleTree {
     return t;
   }
 
+  // The same constructor over several GPUs from this one process (pmt_merkle_tree_build_multi): a power-of-two list of
+  // distinct engines, normally one per device; engine r builds the subtree over leaves [r n/G, (r+1) n/G) on its own device.
+  static MerkleTree new_multi(const std::vector<const Engine*>& engines, std::vector<std::vector<F>> leaves, size_t cap_height) {
+    if (engines.empty()) throw Error(PMT_E_INVALID_ARG, "MerkleTree::new_multi: no engine");
+    const size_t n = leaves.size();
+    const unsigned log2n = detail::log2_strict(n);
+    if (cap_height > log2n) throw Error(PMT_E_RANGE, "cap_height " + std::to_string(cap_height) + " > log2(leaves.len())");
+    const size_t w = leaves[0].size();
+    std::vector<F> flat;
+    flat.reserve(n * w);
+    for (const auto& row : leaves) {
+      if (row.size() != w) throw Error(PMT_E_INVALID_ARG, "MerkleTree::new: ragged leaves");
+      flat.insert(flat.end(), row.begin(), row.end());
+    }
+    std::vector<pmt_ctx*> ctxs;
+    for (const Engine* e : engines) ctxs.push_back(e ? e->ctx() : nullptr);
+    MerkleTree t;
+    t.digests.resize(2 * (n - (size_t(1) << cap_height)));
+    t.cap.hashes.resize(size_t(1) << cap_height);
+    uint64_t dummy[4];
+    engines[0]->check(pmt_merkle_tree_build_multi(ctxs.data(), ctxs.size(), flat.data(), n, w, (uint32_t)cap_height,
+                                                  t.digests.empty() ? dummy : detail::words(t.digests), detail::words(t.cap.hashes)));
+    t.leaves = std::move(leaves);
+    return t;
+  }
+
   // [UPSTREAM] MerkleTree::prove: siblings bottom-up inside the leaf's cap subtree
   MerkleProof prove(size_t leaf_index) const {
     const size_t n = leaves.size();

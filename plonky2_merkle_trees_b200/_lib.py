@@ -46,6 +46,7 @@ _SIGNATURES = {
     "pmt_simple_tree_verify_dev": (_INT, [_VP, _VP, _VP, _SZ, _VP, _VP, _SZ, _VP]),
     "pmt_merkle_tree_build": (_INT, [_VP, u64p, _SZ, _SZ, _U32, u64p, u64p]),
     "pmt_merkle_tree_build_dev": (_INT, [_VP, _VP, _SZ, _SZ, _U32, _VP, _VP]),
+    "pmt_merkle_tree_build_multi": (_INT, [C.POINTER(_VP), _SZ, u64p, _SZ, _SZ, _U32, u64p, u64p]),  # first arg: ctx array
     "pmt_merkle_tree_build_from_columns_dev": (_INT, [_VP, _VP, _SZ, _SZ, _INT, _U32, _VP, _VP, _VP]),
     "pmt_merkle_prove_dev": (_INT, [_VP, _VP, _SZ, _U32, _VP, _SZ, _VP]),
     "pmt_merkle_verify_dev": (_INT, [_VP, _VP, _SZ, _VP, _SZ, _VP, _U32, _VP, _SZ, _VP]),

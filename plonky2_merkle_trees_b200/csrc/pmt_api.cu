@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <thread>
 #include <vector>
 
 using namespace pmt;
@@ -751,6 +752,81 @@ int pmt_merkle_tree_build(pmt_ctx* c, const uint64_t* leaves, size_t n, size_t w
   D2H(c, cap_out, d_cap, n_cap * 32);
   CU(c, cudaStreamSynchronize(c->copy_out));
   FINISH(c);
+  return PMT_OK;
+}
+
+// Single-process multi-GPU MerkleTree::new for a compiled host (the reference is one process): ctx r owns
+// leaves [r n/G, (r+1) n/G) = one subtree and runs the pipelined host-buffer build above on its own device from its own
+// host thread, straight into its contiguous slice of upstream's `digests`.  cap_height >= log2 G: the slices and cap
+// entries tile the outputs, nothing else to do.  Otherwise the G subtree roots (32 B each) come back through the host,
+// ctx 0 finishes the log2 G - h levels above them in one cooperative launch and the 2G - 2^(h+1) digests are placed at
+// their closed-form positions between the slices.  Nothing but roots ever leaves a device.
+int pmt_merkle_tree_build_multi(pmt_ctx* const* ctxs, size_t n_ctx, const uint64_t* leaves, size_t n, size_t w,
+                                uint32_t cap_height, uint64_t* digests_out, uint64_t* cap_out) {
+  if (!ctxs || n_ctx == 0 || !ctxs[0]) return PMT_E_INVALID_ARG;
+  pmt_ctx* c0 = ctxs[0];
+  for (size_t i = 0; i < n_ctx; i++) {
+    if (!ctxs[i]) return fail(c0, PMT_E_INVALID_ARG, "multi build: null ctx %zu", i);
+    for (size_t j = 0; j < i; j++)
+      if (ctxs[j] == ctxs[i]) return fail(c0, PMT_E_INVALID_ARG, "multi build: ctx %zu given twice (a ctx is not thread-safe)", i);
+  }
+  const int g = log2_strict(n_ctx), lg = log2_strict(n);
+  if (g < 0) return fail(c0, PMT_E_NOT_POW2, "multi build: %zu contexts is not a power of two", n_ctx);
+  if (lg < 0) return fail(c0, PMT_E_NOT_POW2, "MerkleTree::new: %zu leaves is not a power of two (log2_strict)", n);
+  if ((int)cap_height > lg) return fail(c0, PMT_E_RANGE, "MerkleTree::new: cap_height=%u should be at most log2(leaves.len())=%d", cap_height, lg);
+  if (w == 0) return fail(c0, PMT_E_INVALID_ARG, "MerkleTree::new: zero-width leaves");
+  if (g > lg) return fail(c0, PMT_E_RANGE, "multi build: more contexts (%zu) than leaves (%zu)", n_ctx, n);
+  const size_t n_cap = (size_t)1 << cap_height, n_dig = 2 * (n - n_cap);
+  if (!leaves || !cap_out || (!digests_out && n_dig)) return fail(c0, PMT_E_INVALID_ARG, "MerkleTree::new: null pointer");
+  if (n_ctx == 1) return pmt_merkle_tree_build(c0, leaves, n, w, cap_height, digests_out, cap_out);
+  const size_t per = n >> g;
+  const int L = lg - (int)cap_height, Lr = lg - g;
+  const bool gather = (int)cap_height < g;
+  std::vector<uint64_t> roots(gather ? 4 * n_ctx : 0);
+  std::vector<int> rcs(n_ctx, PMT_OK);
+  auto work = [&](size_t r) {
+    const uint64_t* my = leaves + r * per * w;
+    if (!gather) {   // 2^(h-g) cap subtrees per ctx
+      const uint32_t hl = cap_height - (uint32_t)g;
+      const size_t cap_l = (size_t)1 << hl, dig_l = 2 * (per - cap_l);
+      rcs[r] = pmt_merkle_tree_build(ctxs[r], my, per, w, hl, digests_out ? digests_out + 4 * r * dig_l : nullptr, cap_out + 4 * r * cap_l);
+    } else {         // one subtree of height Lr inside a cap subtree of height L: 2 per - 2 contiguous digests
+      rcs[r] = pmt_merkle_tree_build(ctxs[r], my, per, w, 0, digests_out + 4 * plonky2_index(L, 0, r * per), roots.data() + 4 * r);
+    }
+  };
+  {
+    std::vector<std::thread> pool;
+    pool.reserve(n_ctx - 1);
+    for (size_t r = 1; r < n_ctx; r++) pool.emplace_back(work, r);
+    work(0);
+    for (auto& t : pool) t.join();
+  }
+  for (size_t r = 0; r < n_ctx; r++)
+    if (rcs[r] != PMT_OK) {
+      char msg[sizeof ctxs[r]->err];
+      memcpy(msg, ctxs[r]->err, sizeof msg);
+      msg[sizeof msg - 1] = 0;
+      return fail(c0, rcs[r], "multi build: ctx %zu (device %d): %.400s", r, ctxs[r]->device, msg);
+    }
+  if (!gather) return PMT_OK;
+  if (int rc = bind(c0)) return rc;
+  void* t = nullptr;
+  if (int rc = arena_get(c0, 2, 2 * n_ctx * 32, &t)) return rc;
+  uint64_t* d_roots = (uint64_t*)t; uint64_t* d_top = d_roots + 4 * n_ctx;
+  std::vector<uint64_t> top(4 * (n_ctx - n_cap));
+  H2D(c0, d_roots, roots.data(), n_ctx * 32);
+  if (int rc = pmt_top_levels_dev(c0, d_roots, n_ctx, cap_height, d_top)) return rc;
+  D2H(c0, top.data(), d_top, (n_ctx - n_cap) * 32);
+  FINISH(c0);
+  for (size_t k = 0; k < n_ctx; k++) memcpy(digests_out + 4 * plonky2_index(L, Lr, k), roots.data() + 4 * k, 32);
+  const uint64_t* lvl = top.data();
+  int level = Lr + 1;
+  for (size_t cnt = n_ctx / 2; cnt >= n_cap; cnt >>= 1, level++) {
+    for (size_t k = 0; k < cnt; k++)
+      memcpy(level < L ? digests_out + 4 * plonky2_index(L, level, k) : cap_out + 4 * k, lvl + 4 * k, 32);
+    lvl += 4 * cnt;
+    if (cnt == 1) break;
+  }
   return PMT_OK;
 }
 

@@ -66,6 +66,28 @@ class MerkleTree:
         ctx.sync()
         return cls(ctx, n, w, cap_height, d_leaves, d_digests, d_cap)
 
+    @staticmethod
+    def new_multi(leaves, cap_height, ctxs):
+        """MerkleTree::new over several GPUs from ONE process (pmt_merkle_tree_build_multi): `ctxs` is a power-of-two list
+        of distinct Contexts, normally one per device; context r builds the subtree over its n / len(ctxs) leaves on its
+        own device.  Host buffers in, host buffers out: returns upstream's (digests, cap) as numpy arrays, identical to
+        MerkleTree.new(leaves, cap_height).digests / .cap."""
+        import ctypes as C
+        leaves = as_u64(leaves)
+        if leaves.ndim != 2:
+            raise ValueError("leaves must be (n, width)")
+        n, w = leaves.shape
+        if not ctxs:
+            raise ValueError("new_multi needs at least one Context")
+        ncap = 1 << cap_height
+        digests = np.zeros((max(2 * (n - ncap), 0), 4), np.uint64)
+        cap = np.zeros((ncap, 4), np.uint64)
+        handles = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+        rc = ctxs[0].lib.pmt_merkle_tree_build_multi(handles, len(ctxs), _lib.ptr(leaves), n, w, cap_height, _lib.ptr(digests),
+                                                     _lib.ptr(cap))
+        ctxs[0].check(rc)
+        return digests, cap
+
     @property
     def leaves(self):
         return to_host(self.d_leaves)

@@ -216,6 +216,27 @@ static void test_plonky2_merkle_tree(const Engine& e) {
   CHECK(throws([&] { plonky2::MerkleTree::new_(e, std::vector<std::vector<F>>(6, std::vector<F>(4, 1)), 0); }, PMT_E_NOT_POW2));
 }
 
+// MerkleTree::new over several contexts in one process (here all on device 0): equal to the single-context tree
+static void test_plonky2_merkle_tree_multi(const Engine& e) {
+  Engine e1, e2, e3;
+  const std::vector<const Engine*> four{&e, &e1, &e2, &e3}, two{&e2, &e3};
+  struct Shape { size_t n, w, cap; };
+  for (const Shape s : {Shape{4, 4, 0}, Shape{16, 1, 0}, Shape{16, 4, 2}, Shape{64, 9, 1}, Shape{64, 135, 4}, Shape{4096, 4, 0}}) {
+    const auto flat = random_felts(s.n * s.w, 2000 + s.n + s.w, true);
+    std::vector<std::vector<F>> leaves(s.n);
+    for (size_t i = 0; i < s.n; i++) leaves[i].assign(flat.begin() + i * s.w, flat.begin() + (i + 1) * s.w);
+    const plonky2::MerkleTree one = plonky2::MerkleTree::new_(e, leaves, s.cap);
+    for (const auto* pool : {&four, &two}) {
+      const plonky2::MerkleTree t = plonky2::MerkleTree::new_multi(*pool, leaves, s.cap);
+      CHECK(t.digests == one.digests);
+      CHECK(t.cap.hashes == one.cap.hashes);
+    }
+  }
+  CHECK(throws([&] { plonky2::MerkleTree::new_multi({&e, &e}, std::vector<std::vector<F>>(8, std::vector<F>(4, 1)), 0); }, PMT_E_INVALID_ARG));
+  CHECK(throws([&] { plonky2::MerkleTree::new_multi({&e, &e1, &e2}, std::vector<std::vector<F>>(8, std::vector<F>(4, 1)), 0); }, PMT_E_NOT_POW2));
+  CHECK(throws([&] { plonky2::MerkleTree::new_multi(four, std::vector<std::vector<F>>(2, std::vector<F>(4, 1)), 0); }, PMT_E_RANGE));
+}
+
 // Hasher: the asserted known answers of simple_merkle_tree.rs:210-211 and the oracle on random inputs
 static void test_hasher(const Engine& e) {
   CHECK(e.hash_or_noop({156728478ull}) == H(156728478ull, 0, 0, 0));
@@ -251,6 +272,7 @@ int main() {
       {"test_mmr_add_leaf", [&] { test_mmr_add_leaf(e); }},
       {"test_get_proof", [&] { test_get_proof(e); }},
       {"test_plonky2_merkle_tree", [&] { test_plonky2_merkle_tree(e); }},
+      {"test_plonky2_merkle_tree_multi", [&] { test_plonky2_merkle_tree_multi(e); }},
   };
   for (const auto& t : tests) {
     std::printf("%s\n", t.first);

@@ -607,6 +607,61 @@ def test_sharded_virtual_ranks(ctx, api, oracle, lg, w, h, G):
     assert np.array_equal(t.assemble_global(chunks), odg)
 
 
+# ---- single-process multi-GPU build (one ctx per device; here: several ctxs on the devices that exist) ---------------------
+@pytest.fixture(scope="module")
+def ctx_pool():
+    """8 distinct contexts spread over the visible devices (all on cuda:0 on a one-GPU box: the sharding, the slices of
+    upstream's layout and the finish are the same code either way)"""
+    from plonky2_merkle_trees_b200 import _lib
+    ndev = torch.cuda.device_count()
+    pool = [_lib.Context(i % ndev) for i in range(8)]
+    yield pool
+    for c in pool:
+        c.close()
+
+
+@pytest.mark.parametrize("lg,w,h,G", [(10, 4, 0, 8), (10, 4, 1, 4), (10, 4, 3, 8), (9, 135, 4, 8), (8, 4, 5, 8), (6, 1, 0, 2),
+                                      (3, 4, 0, 8), (3, 4, 3, 8), (4, 9, 2, 4), (5, 4, 0, 1), (14, 7, 0, 4)])
+def test_multi_context_build_equals_oracle(ctx_pool, api, oracle, lg, w, h, G):
+    n = 1 << lg
+    rows = splitmix_felts(100 + lg + w + h + G, n * w).reshape(n, w)
+    rows[0, 0] = np.uint64(2**64 - 1)   # non-canonical input
+    dg, cap = api.mt.MerkleTree.new_multi(rows, h, ctx_pool[:G])
+    odg, ocap = oracle.merkle_tree_new(rows, h, threads=4, fast=True)
+    assert np.array_equal(cap, ocap)
+    assert np.array_equal(dg, odg)
+
+
+@pytest.mark.parametrize("lg,w,h,G", [(20, 4, 0, 4), (21, 4, 1, 8), (19, 4, 5, 4), (18, 135, 2, 2)])
+def test_multi_context_build_pipelined_sizes(ctx_pool, api, lg, w, h, G):
+    """every context takes the chunked copy / hash / copy pipeline; result = the one-piece device build (tied to the oracle above)"""
+    n = 1 << lg
+    rows = splitmix_felts(7 + lg + w, n * w).reshape(n, w)
+    dg, cap = api.mt.MerkleTree.new_multi(rows, h, ctx_pool[:G])
+    t = api.mt.MerkleTree.new(rows, h)
+    assert np.array_equal(cap, t.cap) and np.array_equal(dg, t.digests)
+    dg2, cap2 = api.mt.MerkleTree.new_multi(rows, h, ctx_pool[:G])   # arenas and streams are reused
+    assert np.array_equal(dg, dg2) and np.array_equal(cap, cap2)
+
+
+def test_multi_context_build_errors(ctx_pool, api):
+    from plonky2_merkle_trees_b200._lib import PmtError, PMT_E_NOT_POW2, PMT_E_RANGE, PMT_E_INVALID_ARG
+    rows = np.zeros((8, 4), np.uint64)
+    for bad, code in ((ctx_pool[:3], PMT_E_NOT_POW2), ([ctx_pool[0], ctx_pool[0]], PMT_E_INVALID_ARG)):
+        with pytest.raises(PmtError) as e:
+            api.mt.MerkleTree.new_multi(rows, 0, bad)
+        assert e.value.code == code
+    with pytest.raises(PmtError) as e:
+        api.mt.MerkleTree.new_multi(rows[:4], 0, ctx_pool[:8])      # more contexts than leaves
+    assert e.value.code == PMT_E_RANGE
+    with pytest.raises(PmtError) as e:
+        api.mt.MerkleTree.new_multi(rows[:6], 0, ctx_pool[:2])      # log2_strict
+    assert e.value.code == PMT_E_NOT_POW2
+    with pytest.raises(PmtError) as e:
+        api.mt.MerkleTree.new_multi(rows, 4, ctx_pool[:2])          # cap_height > log2 n
+    assert e.value.code == PMT_E_RANGE
+
+
 @pytest.mark.parametrize("n_roots,h", [(2, 0), (2, 1), (8, 0), (8, 2), (64, 0), (1024, 3), (4096, 0), (8192, 1)])
 def test_top_levels_above_gathered_roots(ctx, oracle, n_roots, h):
     """pmt_top_levels_dev: single cooperative launch up to 4096 roots, one launch per level beyond that."""
