@@ -346,10 +346,10 @@ def run_ours(args):
     total_prof_ms = sum(v["ms"] for v in prof.values()) or 1.0
     traffic, hardware = None, None
     try:   # one `ncu --set full` capture of this kernel (profiles/), scaled to the average launch of this run
-        with open(os.path.join(ROOT, "profiles", "ncu_traffic_r1b.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic_r1c.json")) as f:
             cap = json.load(f)
         traffic = cap.get("k_level_dram_bytes_per_permutation") * lvl["units"] / max(lvl["launches"], 1)
-        hardware = dict(cap.get("hardware_view", {}), source="profiles/k_level_r1b_summary.txt (ncu --set full, not this run)")
+        hardware = dict(cap.get("hardware_view", {}), source="profiles/k_level_r1c_summary.txt (ncu --set full, not this run)")
     except Exception:
         pass
     roofline = {

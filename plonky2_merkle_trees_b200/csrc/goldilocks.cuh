@@ -90,8 +90,35 @@ __device__ __forceinline__ uint64_t reduce128(u128 v) {
 
 template <bool ALU = false>
 __device__ __forceinline__ uint64_t mul(uint64_t a, uint64_t b) { return reduce128<ALU>((u128)a * b); }
+// a^2 with THREE IMAD.WIDE instead of four: a0^2 + 2^33 a0 a1 + 2^64 a1^2.  nvcc's (u128)a * a computes a0 a1 twice (the
+// second time as the accumulate that doubles it) and needs an IMAD.X + IMAD.MOV to carry the 65th bit into a1^2; here the
+// cross product is doubled by an add and two funnel shifts, and (2m >> 32) + the carry of the middle word ride on the
+// addend / carry-in of the last multiply: 3 IMAD.WIDE + 1 IMAD.IADD + 11 alu instead of 4 IMAD.WIDE + 2 IMAD + 9 alu --
+// 6 cycles less on the fma-heavy pipe (the busier one in k_level) for 4 more on the alu pipe.  Exact: the
+// sum is a^2 < 2^128, word by word.  PMT_SQR3 selects it (ALU reduction only).
+#ifndef PMT_SQR3
+#define PMT_SQR3 1
+#endif
+__device__ __forceinline__ uint64_t sqr3(uint64_t a) {
+  const uint32_t a0 = lo32(a), a1 = hi32(a);
+  uint32_t p0, p1, m0, m1, w1, w2, w3;
+  asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %2;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(p0), "=r"(p1) : "r"(a0));
+  asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(m0), "=r"(m1) : "r"(a0), "r"(a1));
+#if PMT_SQR3 == 2   // A/B: the low word doubled by a funnel shift (alu pipe) instead of the IMAD.IADD ptxas picks for m0 << 1
+  const uint32_t d0 = __funnelshift_l(0u, m0, 1), d1 = __funnelshift_l(m0, m1, 1), d2 = m1 >> 31;
+#else
+  const uint32_t d0 = m0 << 1, d1 = __funnelshift_l(m0, m1, 1), d2 = m1 >> 31;   // 2m = d0 + 2^32 d1 + 2^64 d2
+#endif
+  asm("add.cc.u32 %0, %3, %4;\n\tmadc.lo.cc.u32 %1, %5, %5, %6;\n\tmadc.hi.u32 %2, %5, %5, %7;"
+      : "=r"(w1), "=r"(w2), "=r"(w3) : "r"(p1), "r"(d0), "r"(a1), "r"(d1), "r"(d2));
+  return reduce128_c(p0, w1, w2, w3);
+}
+
 template <bool ALU = false>
-__device__ __forceinline__ uint64_t sqr(uint64_t a) { return reduce128<ALU>((u128)a * a); }
+__device__ __forceinline__ uint64_t sqr(uint64_t a) {
+  if (ALU && PMT_REDUCE_C && PMT_SQR3) return sqr3(a);
+  return reduce128<ALU>((u128)a * a);
+}
 
 // a * b + c  (c any u64): product <= (2^64-1)^2, plus c still fits 128 bits
 template <bool ALU = false>

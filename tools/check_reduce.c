@@ -44,6 +44,25 @@ int main() {
     if (got % P != (uint64_t)(pr % P)) { if (bad < 5) printf("BAD3 l=%016lx h=%016lx\n", l, h); bad++; }
     cnt++;
   }
+  // gl::sqr3: the 128-bit square assembled from a0^2, a0 a1 (doubled with shifts) and a1^2 + addend + carry-in, word by word
+  for (long it = 0; it < 40000000; it++) {
+    uint64_t a = it < ne ? edge[it] : rnd();
+    if (it % 7 == 0) a |= 0xFFFFFFFF00000000ull; if (it % 11 == 0) a |= 0xFFFFFFFFull; if (it % 13 == 0) a &= 0x80000000FFFFFFFFull;
+    if (it % 17 == 0) a |= 0x8000000080000000ull;
+    const uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32);
+    const uint64_t pp = (uint64_t)a0 * a0, m = (uint64_t)a0 * a1;
+    const uint32_t p0 = (uint32_t)pp, p1 = (uint32_t)(pp >> 32), m0 = (uint32_t)m, m1 = (uint32_t)(m >> 32);
+    const uint32_t d0 = m0 << 1, d1 = (m1 << 1) | (m0 >> 31), d2 = m1 >> 31;
+    const uint64_t s1 = (uint64_t)p1 + d0;                                              // add.cc
+    const uint32_t w1 = (uint32_t)s1;
+    const u128 q = (u128)((uint64_t)a1 * a1) + (((uint64_t)d2 << 32) | d1) + (s1 >> 32);   // madc.lo.cc / madc.hi
+    if (q >> 64) { if (bad < 5) printf("BAD4 overflow a=%016lx\n", a); bad++; }
+    const uint32_t w2 = (uint32_t)q, w3 = (uint32_t)(q >> 32);
+    const u128 sq = (u128)a * a;
+    if ((((u128)w3 << 96) | ((u128)w2 << 64) | ((u128)w1 << 32) | p0) != sq) { if (bad < 5) printf("BAD4 a=%016lx\n", a); bad++; }
+    if (red_v3(p0, w1, w2, w3) % P != (uint64_t)(sq % P)) { if (bad < 5) printf("BAD5 a=%016lx\n", a); bad++; }
+    cnt++;
+  }
   printf("checked %ld, bad %ld\n", cnt, bad);
   return bad != 0;
 }

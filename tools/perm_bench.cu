@@ -142,6 +142,22 @@ __global__ void __launch_bounds__(256) k_pipe(uint64_t* out, uint32_t a, uint32_
           uint64_t w;
           asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w) : "r"(x[j]), "r"(y[j]));
           asm volatile("lop3.b32 %0, %1, %2, %0, 0x96;" : "+r"(x[j]) : "r"((uint32_t)w), "r"((uint32_t)(w >> 32)));
+        } else if (MODE == 40) {  // FFMA, three register operands
+          float f = __uint_as_float(x[j]);
+          asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f) : "f"(__uint_as_float(y[(j + 1) % ILP])), "f"(__uint_as_float(z[j])));
+          x[j] = __float_as_uint(f);
+        } else if (MODE == 41) {  // FFMA2 (fma.rn.f32x2, Blackwell packed fp32): counted as ONE instruction = 2 fp32 FMAs
+          asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(acc[j]) : "l"(acc[(j + 1) % ILP]), "l"((uint64_t)a << 32 | b));
+        } else if (MODE == 42) {  // FFMA2 + LOP3 (1:1): does the packed form leave the alu pipe free?
+          asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(acc[j]) : "l"(acc[(j + 1) % ILP]), "l"((uint64_t)a << 32 | b));
+          asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[j]) : "r"(x[(j + 1) % ILP]), "r"(a));
+        } else if (MODE == 43) {  // FFMA2 + IMAD.WIDE accumulate (1:1): shared pipe or not
+          asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(acc[j]) : "l"(acc[(j + 1) % ILP]), "l"((uint64_t)a << 32 | b));
+          uint64_t w = (uint64_t)z[j] << 32 | y[j];
+          asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w) : "r"(x[j]), "r"(a));
+          y[j] = (uint32_t)w; z[j] = (uint32_t)(w >> 32);
+        } else if (MODE == 44) {  // FADD2 (add.rn.f32x2)
+          asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(acc[j]) : "l"(acc[(j + 1) % ILP]));
         } else if (MODE == 13) {  // SEL
           asm volatile("{ .reg .pred p; setp.lt.u32 p, %0, %1; selp.u32 %0, %1, %2, p; }" : "+r"(x[j]) : "r"(x[(j + 1) % ILP]), "r"(a));
         }
@@ -310,6 +326,14 @@ int main(int argc, char** argv) {
     run_pipe<22>("dfma+imad_lo+lop3 (1:1:1)", 3, sms);
     run_pipe<23>("sub.cc+subc.cc+subc", 3, sms);
     run_pipe<24>("2dfma+lop3 (2:1)", 3, sms);
+  }
+  if (argc > 1 && strstr(argv[1], "f32")) {   // fp32 candidates for a limb-form MDS layer (not used by the product kernels)
+    run_pipe<40>("ffma", 1, sms);
+    run_pipe<41>("ffma2 (f32x2, per instruction)", 1, sms);
+    run_pipe<44>("fadd2 (f32x2, per instruction)", 1, sms);
+    run_pipe<42>("ffma2+lop3 (1:1)", 2, sms);
+    run_pipe<43>("ffma2+imad_wide_acc (1:1)", 2, sms);
+    run_pipe<14>("dfma", 1, sms);
   }
   if (argc > 1 && strstr(argv[1], "lat")) run_latency(sms);
   if (perms) {
