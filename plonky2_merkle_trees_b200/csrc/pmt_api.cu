@@ -35,6 +35,9 @@ struct pmt_ctx {
   std::vector<cudaEvent_t> ev;
   // levels with at most this many nodes run the cooperative kernel (COOP_MAX; PMT_COOP_MAX_LOG2 is a tuning knob)
   size_t coop_max = (size_t)1 << 13;
+  // levels of <= coop_max nodes of a perfect tree run as fused subtree blocks (k_subtree_coop); PMT_FUSE_SUBTREES=0
+  // restores one cooperative launch per level (the A/B knob of tools/bench_configs.py)
+  bool fuse_subtrees = true;
 };
 
 static inline void prof_begin(pmt_ctx* c, const char* name, double units) {
@@ -159,8 +162,19 @@ int launch_level(pmt_ctx* c, const Layout& lay, int l, size_t k0, size_t count) 
 template <class Layout>
 int run_levels(pmt_ctx* c, const Layout& lay, int l0, int top, size_t count) {
   int l = l0;
-  for (; l <= top && count > TOP_FUSE; l++, count >>= 1)
+  for (; l <= top && count > TOP_FUSE && (count > c->coop_max || !c->fuse_subtrees); l++, count >>= 1)
     if (int rc = launch_level(c, lay, l, 0, count)) return rc;
+  // the latency-bound middle (<= coop_max nodes per level): fused subtree blocks, up to five levels per launch
+  while (l <= top && count > TOP_FUSE) {
+    const int levels = top - l + 1 < 5 ? top - l + 1 : 5;
+    size_t units = 0;
+    for (int j = 0; j < levels; j++) units += count >> j;
+    TAG(c, "k_subtree_coop", units);
+    k_subtree_coop<Layout><<<(unsigned)(count / COOP_GROUPS), COOP_BLOCK, 0, c->stream>>>(lay, l, levels);
+    CHECK_LAUNCH(c);
+    l += levels;
+    count >>= levels;
+  }
   if (l <= top) {
     TAG(c, "k_top_coop", 2 * count - 1);
     k_top_coop<Layout><<<1, 256, 0, c->stream>>>(lay, l, top, count);
@@ -200,6 +214,7 @@ int pmt_init(pmt_ctx** out, int device_id) {
     const int lg = atoi(e2);
     if (lg >= 4 && lg <= 24) c->coop_max = (size_t)1 << lg;
   }
+  if (const char* e3 = getenv("PMT_FUSE_SUBTREES")) c->fuse_subtrees = atoi(e3) != 0;
   *out = c;
   return PMT_OK;
 }

@@ -607,6 +607,39 @@ def test_sharded_virtual_ranks(ctx, api, oracle, lg, w, h, G):
     assert np.array_equal(t.assemble_global(chunks), odg)
 
 
+# ---- fused subtree blocks (k_subtree_coop) against one cooperative launch per level ----------------------------------------
+@pytest.mark.parametrize("lg,w,h", [(5, 4, 0), (6, 4, 1), (9, 4, 0), (10, 1, 3), (12, 4, 0), (14, 4, 0), (14, 9, 6), (15, 4, 11), (17, 4, 2)])
+def test_fused_subtree_blocks_equal_per_level_launches(api, oracle, lg, w, h, monkeypatch):
+    """the middle levels (<= 2^13 nodes) of a perfect tree run as fused 16-node subtree blocks; PMT_FUSE_SUBTREES=0 keeps the
+    one-launch-per-level plan: both must give the oracle's tree (plonky2 layout, simple tree) with fewer launches fused"""
+    from plonky2_merkle_trees_b200 import _lib
+    n = 1 << lg
+    rows = splitmix_felts(300 + lg + w + h, n * w).reshape(n, w)
+    monkeypatch.setenv("PMT_FUSE_SUBTREES", "0")
+    plain = _lib.Context(0)
+    monkeypatch.delenv("PMT_FUSE_SUBTREES")
+    fused = _lib.Context(0)
+    try:
+        l0 = plain.launches
+        a = api.mt.MerkleTree.new(rows, h, plain)
+        l_plain = plain.launches - l0
+        l0 = fused.launches
+        b = api.mt.MerkleTree.new(rows, h, fused)
+        l_fused = fused.launches - l0
+        assert np.array_equal(a.digests, b.digests) and np.array_equal(a.cap, b.cap)
+        if lg <= 15:
+            odg, ocap = oracle.merkle_tree_new(rows, h, threads=4, fast=True)
+            assert np.array_equal(b.digests, odg) and np.array_equal(b.cap, ocap)
+        if lg - h >= 7:
+            assert l_fused < l_plain, (l_fused, l_plain)
+        if w == 1:
+            s1 = api.smt.MerkleTree.build(rows[:, 0], plain)
+            s2 = api.smt.MerkleTree.build(rows[:, 0], fused)
+            assert np.array_equal(np.concatenate(s1.tree), np.concatenate(s2.tree)) and np.array_equal(s1.root, s2.root)
+    finally:
+        plain.close(); fused.close()
+
+
 # ---- single-process multi-GPU build (one ctx per device; here: several ctxs on the devices that exist) ---------------------
 @pytest.fixture(scope="module")
 def ctx_pool():
