@@ -397,20 +397,20 @@ __global__ void __launch_bounds__(COOP_BLOCK) k_top_coop(Layout lay, int l0, int
   }
 }
 
-// fused subtree blocks for the latency-bound middle of a perfect tree (levels of <= 2^13 nodes): block b owns the 16
-// nodes [16 b, 16 b + 16) of level l0 and every ancestor of theirs up to `levels` levels (16, 8, 4, 2, 1 nodes), one
+// fused subtree blocks for the latency-bound middle of a tree (levels of <= 2^13 nodes): block b owns the 16 nodes
+// k0 + [16 b, 16 b + 16) of level l0 (k0 a multiple of 16) and every ancestor of theirs up to `levels` levels (16, 8, 4, 2, 1 nodes), one
 // 16-lane group per node, shuffles inside the permutation, a block barrier between levels.  A block only ever reads
 // children it wrote itself (through L1/L2; every level has to be stored anyway, proofs need it), so the blocks are
 // independent and one launch replaces up to five.  Warps whose two groups both have no node skip the permutation.
 template <class Layout>
-__global__ void __launch_bounds__(COOP_BLOCK) k_subtree_coop(Layout lay, int l0, int levels) {
+__global__ void __launch_bounds__(COOP_BLOCK) k_subtree_coop(Layout lay, int l0, int levels, size_t k0) {
   __shared__ uint64_t rc_smem[WIDTH * (PMT_ROUNDS + 1)];
   coop_stage_constants(rc_smem);
   const unsigned g = threadIdx.x & 15, base_lane = threadIdx.x & 16;
   const size_t group = threadIdx.x >> 4;
   size_t per = COOP_GROUPS;                                  // nodes of this block at the current level
   for (int j = 0; j < levels; j++, per >>= 1) {
-    if ((group & ~(size_t)1) < per) coop_node(lay, l0 + j, (size_t)blockIdx.x * per + group, group < per, rc_smem, g, base_lane);
+    if ((group & ~(size_t)1) < per) coop_node(lay, l0 + j, (k0 >> j) + (size_t)blockIdx.x * per + group, group < per, rc_smem, g, base_lane);
     __threadfence_block();
     __syncthreads();
   }

@@ -170,7 +170,7 @@ int run_levels(pmt_ctx* c, const Layout& lay, int l0, int top, size_t count) {
     size_t units = 0;
     for (int j = 0; j < levels; j++) units += count >> j;
     TAG(c, "k_subtree_coop", units);
-    k_subtree_coop<Layout><<<(unsigned)(count / COOP_GROUPS), COOP_BLOCK, 0, c->stream>>>(lay, l, levels);
+    k_subtree_coop<Layout><<<(unsigned)(count / COOP_GROUPS), COOP_BLOCK, 0, c->stream>>>(lay, l, levels, 0);
     CHECK_LAUNCH(c);
     l += levels;
     count >>= levels;
@@ -179,6 +179,33 @@ int run_levels(pmt_ctx* c, const Layout& lay, int l0, int top, size_t count) {
     TAG(c, "k_top_coop", 2 * count - 1);
     k_top_coop<Layout><<<1, 256, 0, c->stream>>>(lay, l, top, count);
     CHECK_LAUNCH(c);
+  }
+  return PMT_OK;
+}
+
+// levels l_first .. l_last over the nodes that the leaves [n0, n1) complete: level l has the nodes k in [n0 >> l, n1 >> l)
+// (a chunk of the pipelined tree build, a batch append to an MMR).  Where such a range is small (<= coop_max nodes) and
+// aligned to 16 nodes it runs as fused subtree blocks, five levels per launch; otherwise one launch per level.
+template <class Layout>
+int launch_level_span(pmt_ctx* c, const Layout& lay, int l_first, int l_last, size_t n0, size_t n1) {
+  for (int l = l_first; l <= l_last;) {
+    const size_t k0 = n0 >> l, k1 = n1 >> l;
+    if (k1 == 0) break;
+    if (k1 <= k0) { l++; continue; }
+    const size_t count = k1 - k0;
+    const int room = l_last - l + 1;
+    if (c->fuse_subtrees && room >= 2 && count > TOP_FUSE && count <= c->coop_max && k0 % COOP_GROUPS == 0 && count % COOP_GROUPS == 0) {
+      const int levels = room < 5 ? room : 5;
+      size_t units = 0;
+      for (int j = 0; j < levels; j++) units += count >> j;
+      TAG(c, "k_subtree_coop", units);
+      k_subtree_coop<Layout><<<(unsigned)(count / COOP_GROUPS), COOP_BLOCK, 0, c->stream>>>(lay, l, levels, k0);
+      CHECK_LAUNCH(c);
+      l += levels;
+      continue;
+    }
+    if (int rc = launch_level(c, lay, l, k0, count)) return rc;
+    l++;
   }
   return PMT_OK;
 }
@@ -539,13 +566,7 @@ int pmt_mmr_extend_dev(pmt_ctx* c, uint64_t* d_elements, size_t n0, const uint64
     k_leaves<Mmr><<<grid_copy(c, m), BLOCK, 0, c->stream>>>(lay, d_new, 1, n0, m);
     CHECK_LAUNCH(c);
   }
-  for (int l = first_level; l < 40; l++) {
-    const size_t k0 = n0 >> l, k1 = (n0 + m) >> l;
-    if (k1 == 0) break;
-    if (k1 > k0)
-      if (int rc = launch_level(c, lay, l, k0, k1 - k0)) return rc;
-  }
-  return PMT_OK;
+  return launch_level_span(c, lay, first_level, 40, n0, n0 + m);
 }
 
 int pmt_mmr_peaks_dev(pmt_ctx* c, const uint64_t* d_elements, size_t n_leaves, uint64_t* d_peaks, uint32_t* n_peaks_out) {
@@ -745,10 +766,7 @@ int pmt_merkle_tree_build(pmt_ctx* c, const uint64_t* leaves, size_t n, size_t w
     TAG(c, "k_leaves", w <= 4 ? 0 : chunk * ((w + 7) / 8));
     k_leaves<Plonky2><<<w <= 4 ? grid_copy(c, chunk) : grid_for(c, chunk), BLOCK, 0, c->stream>>>(lay, d_leaves + i * chunk * w, w, i * chunk, chunk);
     CHECK_LAUNCH(c);
-    for (int l = 1; l <= cb; l++) {
-      const size_t cnt = chunk >> l;
-      if (int rc = launch_level(c, lay, l, i * cnt, cnt)) return rc;
-    }
+    if (int rc = launch_level_span(c, lay, 1, cb, i * chunk, (i + 1) * chunk)) return rc;
     CU(c, cudaEventRecord(c->ev[2 * i + 1], c->stream));
     CU(c, cudaStreamWaitEvent(c->copy_out, c->ev[2 * i + 1], 0));
     if (cb >= 1) {

@@ -640,6 +640,29 @@ def test_fused_subtree_blocks_equal_per_level_launches(api, oracle, lg, w, h, mo
         plain.close(); fused.close()
 
 
+@pytest.mark.parametrize("n0,m", [(0, 1 << 14), (3 << 14, 1 << 14), (1 << 9, 3 << 9), (48, 1 << 10), (5, 40000), (1 << 15, (1 << 15) + 16)])
+def test_fused_subtree_blocks_in_mmr_appends(api, oracle, n0, m, monkeypatch):
+    """batch appends whose level ranges are aligned to 16 nodes take the fused blocks too; ragged ones stay per level"""
+    from plonky2_merkle_trees_b200 import _lib
+    leaves = splitmix_felts(900 + n0 + m, n0 + m)
+    monkeypatch.setenv("PMT_FUSE_SUBTREES", "0")
+    plain = _lib.Context(0)
+    monkeypatch.delenv("PMT_FUSE_SUBTREES")
+    fused = _lib.Context(0)
+    try:
+        got = []
+        for c in (plain, fused):
+            mm = api.mmr.MMR.new(c)
+            if n0:
+                mm.extend(leaves[:n0])
+            mm.extend(leaves[n0:])
+            got.append(mm.elements.copy())
+        assert np.array_equal(got[0], got[1])
+        assert np.array_equal(got[1], oracle.mmr_extend(None, leaves))
+    finally:
+        plain.close(); fused.close()
+
+
 # ---- single-process multi-GPU build (one ctx per device; here: several ctxs on the devices that exist) ---------------------
 @pytest.fixture(scope="module")
 def ctx_pool():
