@@ -16,6 +16,10 @@
  *   - *_dev entry points take DEVICE pointers, only ENQUEUE work on the ctx stream (no host sync) and return; call
  *     pmt_sync() before reading results on the host.  The host-buffer entry points are synchronous.
  *   - there is no CPU fallback: every entry point that computes fails with PMT_E_CUDA when no device is usable.
+ *   - tuning knobs read from the environment at pmt_init / call time (measurement aids; the defaults are the measured
+ *     optima, results never depend on them): PMT_COOP_MAX_LOG2 (levels of at most 2^k nodes run 16 lanes per node,
+ *     default 13), PMT_FUSE_SUBTREES (0: one launch per small level instead of fused subtree blocks),
+ *     PMT_PIPELINE_LOG2_CHUNKS (chunks of the pipelined host-buffer tree build, default 4).
  */
 #ifndef PMT_H
 #define PMT_H
