@@ -136,6 +136,16 @@ size_t pmt_mmr_index(size_t leaf_normal_index);
  * elements: post-order array with capacity >= pmt_mmr_size(n_before + m) digests, first pmt_mmr_size(n_before) valid. */
 int pmt_mmr_extend(pmt_ctx* ctx, uint64_t* elements, size_t n_before, const uint64_t* new_leaves, size_t m);
 int pmt_mmr_extend_dev(pmt_ctx* ctx, uint64_t* d_elements, size_t n_before, const uint64_t* d_new_leaves, size_t m);
+/* The same batch append over SEVERAL GPUs from one host process: n_ctx distinct contexts (any count), normally one per
+ * device.  The appended leaves are cut into aligned blocks of 2^b leaves -- perfect sub-mountains, each one contiguous
+ * slice of `elements` -- which context j mod n_ctx builds from its own host thread; the nodes above the block roots are
+ * finished on ctxs[0].  Host buffers, synchronous, output identical to pmt_mmr_extend (which it calls when there is one
+ * context or fewer than 4096 leaves per context).  pmt_mmr_multi_plan is the pure index math of the cut (no device;
+ * returns 1 and b, the first and the last block boundary if the append is split, else 0). */
+int pmt_mmr_extend_multi(pmt_ctx* const* ctxs, size_t n_ctx, uint64_t* elements, size_t n_before, const uint64_t* new_leaves,
+                         size_t m);
+int pmt_mmr_multi_plan(size_t n_before, size_t m, size_t n_ctx, uint32_t* log2_block, size_t* first_aligned,
+                       size_t* last_aligned);
 /* get_peaks (:179-200): peaks_out up to 64 digests, largest mountain first; *n_peaks_out = popcount(n_leaves) */
 int pmt_mmr_peaks_dev(pmt_ctx* ctx, const uint64_t* d_elements, size_t n_leaves, uint64_t* d_peaks_out,
                       uint32_t* n_peaks_out);

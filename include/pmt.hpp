@@ -213,6 +213,17 @@ struct MMR {
     e.check(pmt_mmr_extend(e.ctx(), detail::words(elements), n_leaves, leaves.data(), leaves.size()));
     n_leaves += leaves.size();
   }
+  // the same batch over several GPUs from this one process (pmt_mmr_extend_multi): distinct engines, normally one per device
+  void extend_multi(const std::vector<const Engine*>& engines, const std::vector<F>& leaves) {
+    if (engines.empty()) throw Error(PMT_E_INVALID_ARG, "MMR::extend_multi: no engine");
+    if (leaves.empty()) return;
+    if (n_leaves + leaves.size() > (size_t(1) << 30)) throw Error(PMT_E_RANGE, "MMR leaf count > 2^30 (merkle_mountain_ranges.rs:264)");
+    std::vector<pmt_ctx*> ctxs;
+    for (const Engine* e : engines) ctxs.push_back(e ? e->ctx() : nullptr);
+    elements.resize(pmt_mmr_size(n_leaves + leaves.size()));
+    engines[0]->check(pmt_mmr_extend_multi(ctxs.data(), ctxs.size(), detail::words(elements), n_leaves, leaves.data(), leaves.size()));
+    n_leaves += leaves.size();
+  }
   void add_leaf(const Engine& e, F leaf) { extend(e, {leaf}); }
 
   // :179-200 -- one peak per set bit of the leaf count, largest mountain first

@@ -146,7 +146,9 @@ def mmr_extend(elements, leaves):
     """sequential add_leaf loop (merkle_mountain_ranges.rs:89-120). elements: (len, 4) or None."""
     leaves = _arr(leaves)
     old = 0 if elements is None else elements.shape[0]
-    buf = np.zeros((old + 2 * leaves.size + 1, 4), np.uint64)
+    # new elements = 2 m + popcount(n_before) - popcount(n_before + m) <= 2 m + 63 (an append can complete up to
+    # popcount(n_before) old mountains on top of its own nodes)
+    buf = np.zeros((old + 2 * leaves.size + 64, 4), np.uint64)
     if old:
         buf[:old] = elements
     ln = C.c_size_t(old)

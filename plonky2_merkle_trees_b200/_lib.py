@@ -56,6 +56,8 @@ _SIGNATURES = {
     "pmt_mmr_index": (_SZ, [_SZ]),
     "pmt_mmr_extend": (_INT, [_VP, u64p, _SZ, u64p, _SZ]),
     "pmt_mmr_extend_dev": (_INT, [_VP, _VP, _SZ, _VP, _SZ]),
+    "pmt_mmr_extend_multi": (_INT, [C.POINTER(_VP), _SZ, u64p, _SZ, u64p, _SZ]),  # first arg: ctx array
+    "pmt_mmr_multi_plan": (_INT, [_SZ, _SZ, _SZ, u32p, C.POINTER(_SZ), C.POINTER(_SZ)]),  # no ctx: pure index math
     "pmt_mmr_peaks_dev": (_INT, [_VP, _VP, _SZ, _VP, u32p]),
     "pmt_mmr_bag_dev": (_INT, [_VP, _VP, _SZ, _VP]),
     "pmt_mmr_prove_dev": (_INT, [_VP, _VP, _SZ, _VP, _SZ, _VP, _VP, _VP]),

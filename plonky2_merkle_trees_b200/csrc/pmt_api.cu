@@ -931,6 +931,109 @@ int pmt_mmr_extend(pmt_ctx* c, uint64_t* elements, size_t n0, const uint64_t* ne
   return PMT_OK;
 }
 
+// ---- single-process multi-GPU batch append ---------------------------------------------------------------------------------
+// post-order position of the node at height l covering leaves [k 2^l, (k + 1) 2^l)
+static size_t mmr_pos(int l, size_t k) {
+  const size_t last = ((k + 1) << l) - 1;
+  return 2 * last - (size_t)__builtin_popcountll((unsigned long long)last) + (size_t)l;
+}
+
+static int check_ctxs(pmt_ctx* const* ctxs, size_t n_ctx, const char* who) {
+  if (!ctxs || n_ctx == 0 || !ctxs[0]) return PMT_E_INVALID_ARG;
+  for (size_t i = 0; i < n_ctx; i++) {
+    if (!ctxs[i]) return fail(ctxs[0], PMT_E_INVALID_ARG, "%s: null ctx %zu", who, i);
+    for (size_t j = 0; j < i; j++)
+      if (ctxs[j] == ctxs[i]) return fail(ctxs[0], PMT_E_INVALID_ARG, "%s: ctx %zu given twice (a ctx is not thread-safe)", who, i);
+  }
+  return PMT_OK;
+}
+
+// The plan of pmt_mmr_extend_multi, pure index math (no device): the appended leaves [n0, n0 + m) are cut into a head up to
+// the first multiple of B = 2^b, aligned blocks of B leaves, and a tail; b = floor(log2(m / n_ctx)) - 2, at least 12, so that
+// the contexts get 4 .. 8 blocks each.  Returns 1 and the plan if there is at least one block and more than one context,
+// 0 if one context should do the whole append.
+int pmt_mmr_multi_plan(size_t n0, size_t m, size_t n_ctx, uint32_t* log2_block, size_t* first_aligned, size_t* last_aligned) {
+  if (n_ctx <= 1 || m / n_ctx < 4096) return 0;
+  int b = 0;
+  while (((size_t)2 << b) <= m / n_ctx) b++;   // floor(log2(m / n_ctx)) >= 12
+  b = b - 2 < 12 ? 12 : b - 2;
+  const size_t A = ((n0 + ((size_t)1 << b) - 1) >> b) << b, Z = ((n0 + m) >> b) << b;
+  if (Z <= A) return 0;
+  if (log2_block) *log2_block = (uint32_t)b;
+  if (first_aligned) *first_aligned = A;
+  if (last_aligned) *last_aligned = Z;
+  return 1;
+}
+
+// Batch append over several GPUs from one process.  An aligned block of B leaves is a perfect sub-mountain whose 2B - 1
+// elements are one contiguous slice of the post-order array at mmr_size(start), identical to a fresh MMR of those leaves:
+// context j mod G builds block j from empty straight into its slice (pmt_mmr_extend, pipelined for big blocks), context 0
+// also appends the head.  The nodes above the block roots are the MMR over the block roots ("coarse" MMR: node (l, k) of
+// it is node (l + b, k) of the fine one): its old peaks (= the fine peaks at the first block boundary) and the block roots
+// go up to context 0, one launch_level_span computes the rest, and the few new nodes come back to their fine positions.
+// The tail (< B leaves) is appended last.  Output identical to pmt_mmr_extend.
+int pmt_mmr_extend_multi(pmt_ctx* const* ctxs, size_t n_ctx, uint64_t* elements, size_t n0, const uint64_t* new_leaves, size_t m) {
+  if (int rc = check_ctxs(ctxs, n_ctx, "mmr extend multi")) return rc;
+  pmt_ctx* c0 = ctxs[0];
+  if (m == 0) return PMT_OK;
+  if (!elements || !new_leaves) return fail(c0, PMT_E_INVALID_ARG, "mmr extend: null pointer");
+  if (n0 + m > ((size_t)1 << 30)) return fail(c0, PMT_E_RANGE, "mmr extend: more than 2^30 leaves (get_mmr_index is i32, merkle_mountain_ranges.rs:264)");
+  uint32_t b = 0;
+  size_t A = 0, Z = 0;
+  if (!pmt_mmr_multi_plan(n0, m, n_ctx, &b, &A, &Z)) return pmt_mmr_extend(c0, elements, n0, new_leaves, m);
+  const size_t B = (size_t)1 << b, C = (Z - A) >> b;
+  std::vector<int> rcs(n_ctx, PMT_OK);
+  auto work = [&](size_t r) {
+    if (r == 0 && A > n0) {
+      rcs[0] = pmt_mmr_extend(ctxs[0], elements, n0, new_leaves, A - n0);
+      if (rcs[0] != PMT_OK) return;
+    }
+    for (size_t j = r; j < C; j += n_ctx) {
+      const size_t start = A + j * B;
+      rcs[r] = pmt_mmr_extend(ctxs[r], elements + 4 * pmt_mmr_size(start), 0, new_leaves + (start - n0), B);
+      if (rcs[r] != PMT_OK) return;
+    }
+  };
+  {
+    std::vector<std::thread> pool;
+    pool.reserve(n_ctx - 1);
+    for (size_t r = 1; r < n_ctx; r++) pool.emplace_back(work, r);
+    work(0);
+    for (auto& t : pool) t.join();
+  }
+  for (size_t r = 0; r < n_ctx; r++)
+    if (rcs[r] != PMT_OK) {
+      char msg[sizeof ctxs[r]->err];
+      memcpy(msg, ctxs[r]->err, sizeof msg);
+      msg[sizeof msg - 1] = 0;
+      return fail(c0, rcs[r], "mmr extend multi: ctx %zu (device %d): %.400s", r, ctxs[r]->device, msg);
+    }
+  // the coarse MMR over the block roots, on context 0
+  if (int rc = bind(c0)) return rc;
+  const size_t s0 = A >> b, s1 = s0 + C;
+  void* t = nullptr;
+  if (int rc = arena_get(c0, 1, pmt_mmr_size(s1) * 32, &t)) return rc;
+  uint64_t* d_sup = (uint64_t*)t;
+  {
+    size_t base = 0;
+    for (int bit = 63; bit >= 0; bit--)
+      if ((s0 >> bit) & 1) {
+        base += (size_t)1 << bit;
+        H2D(c0, d_sup + 4 * (pmt_mmr_size(base) - 1), elements + 4 * (pmt_mmr_size(base << b) - 1), 32);
+      }
+  }
+  for (size_t s = s0; s < s1; s++) H2D(c0, d_sup + 4 * mmr_pos(0, s), elements + 4 * mmr_pos((int)b, s), 32);
+  if (int rc = launch_level_span(c0, Mmr{d_sup}, 1, 40, s0, s1)) return rc;
+  for (int l = 1; l < 40; l++) {
+    const size_t k0 = s0 >> l, k1 = s1 >> l;
+    if (k1 == 0) break;
+    for (size_t k = k0; k < k1; k++) D2H(c0, elements + 4 * mmr_pos(l + (int)b, k), d_sup + 4 * mmr_pos(l, k), 32);
+  }
+  FINISH(c0);
+  if (n0 + m > Z) return pmt_mmr_extend(c0, elements, Z, new_leaves + (Z - n0), n0 + m - Z);
+  return PMT_OK;
+}
+
 // positions of the peaks in the post-order array, largest mountain first (get_peaks, :179-200)
 static uint32_t peak_positions(size_t n_leaves, size_t* pos) {
   uint32_t k = 0;

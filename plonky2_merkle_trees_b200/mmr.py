@@ -96,6 +96,37 @@ def verify_batch(leaves, siblings, on_left, path_len, peaks, root, ctx=None):
     return d_status.cpu().numpy()
 
 
+def multi_plan(n_before, m, n_ctx):
+    """the cut pmt_mmr_extend_multi makes (pure index math in libpmt, no device): None if one context does the whole
+    append, else (log2_block, first_aligned, last_aligned)."""
+    import ctypes as C
+    lib = _lib.load()
+    b, a, z = C.c_uint32(0), C.c_size_t(0), C.c_size_t(0)
+    if not lib.pmt_mmr_multi_plan(n_before, m, n_ctx, C.byref(b), C.byref(a), C.byref(z)):
+        return None
+    return b.value, a.value, z.value
+
+
+def extend_multi(elements, n_before, new_leaves, ctxs):
+    """Batch append over several GPUs from ONE process (pmt_mmr_extend_multi): `elements` is the HOST post-order array of the
+    MMR with n_before leaves (or None), `ctxs` a list of distinct Contexts, normally one per device.  Returns the host
+    array of the MMR with the new leaves appended -- identical to MMR.extend on one device."""
+    import ctypes as C
+    leaves = as_u64(new_leaves).reshape(-1)
+    m = leaves.size
+    s0 = 2 * n_before - bin(n_before).count("1")
+    s1 = 2 * (n_before + m) - bin(n_before + m).count("1")
+    out = np.zeros((s1, 4), np.uint64)
+    if n_before:
+        out[:s0] = as_u64(elements).reshape(-1, 4)[:s0]
+    if m == 0:
+        return out
+    handles = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+    rc = ctxs[0].lib.pmt_mmr_extend_multi(handles, len(ctxs), _lib.ptr(out), n_before, _lib.ptr(leaves), m)
+    ctxs[0].check(rc)
+    return out
+
+
 class MMR:
     GROW = 1 << 12  # minimum capacity, in leaves
 

@@ -232,6 +232,16 @@ static void test_plonky2_merkle_tree_multi(const Engine& e) {
       CHECK(t.cap.hashes == one.cap.hashes);
     }
   }
+  // MMR batch append over several contexts: equal to the single-context append, also onto a non-empty, unaligned MMR
+  for (const size_t n0 : {size_t(0), size_t(777), size_t(8192)}) {
+    const auto lv = random_felts(n0 + 3 * 8192 + 11, 3000 + n0, false);
+    const std::vector<F> head(lv.begin(), lv.begin() + n0), rest(lv.begin() + n0, lv.end());
+    mmr::MMR a = mmr::MMR::new_(), b = mmr::MMR::new_();
+    a.extend(e, head); a.extend(e, rest);
+    b.extend(e, head); b.extend_multi(two, rest);
+    CHECK(a.elements == b.elements);
+    CHECK(a.bagging_the_peaks(e) == b.bagging_the_peaks(e));
+  }
   CHECK(throws([&] { plonky2::MerkleTree::new_multi({&e, &e}, std::vector<std::vector<F>>(8, std::vector<F>(4, 1)), 0); }, PMT_E_INVALID_ARG));
   CHECK(throws([&] { plonky2::MerkleTree::new_multi({&e, &e1, &e2}, std::vector<std::vector<F>>(8, std::vector<F>(4, 1)), 0); }, PMT_E_NOT_POW2));
   CHECK(throws([&] { plonky2::MerkleTree::new_multi(four, std::vector<std::vector<F>>(2, std::vector<F>(4, 1)), 0); }, PMT_E_RANGE));

@@ -167,3 +167,60 @@ def test_sharded_build_two_gloo_ranks(oracle, tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, o
         assert "rank %d ok" % r in o
+
+
+# ---- pmt_mmr_extend_multi: the cut (real index math of libpmt, no device) and the construction it relies on ------------------
+def _mmr_size(n):
+    return 2 * n - bin(n).count("1")
+
+
+def _mmr_pos(l, k):
+    last = ((k + 1) << l) - 1
+    return 2 * last - bin(last).count("1") + l
+
+
+@pytest.mark.parametrize("n0,m,g", [(0, 1 << 15, 2), (0, 1 << 16, 8), (12345, (1 << 15) + 77, 2), (4096, 3 * 4096, 3), (4095, 2 * 4096 + 2, 2),
+                                    (1 << 14, (1 << 16) - 1, 4), (7, 40000, 4), (3 << 12, 1 << 13, 2), (100, 5000, 2)])
+def test_mmr_multi_plan_and_block_construction(oracle, n0, m, g):
+    """The plan pmt_mmr_extend_multi computes (libpmt's own pmt_mmr_multi_plan) and the construction behind it, replayed on the
+    CPU with the oracle standing in for the contexts: head, aligned blocks as fresh MMRs written into their slices, the
+    coarse MMR over the block roots, tail -- must equal the sequential MMR element by element."""
+    from plonky2_merkle_trees_b200 import mmr
+    leaves = splitmix_felts(4000 + n0 + m + g, n0 + m)
+    want = oracle.mmr_extend(None, leaves)
+    plan = mmr.multi_plan(n0, m, g)
+    if m // g < 4096:
+        assert plan is None
+        return
+    assert plan is not None
+    b, a, z = plan
+    big = 1 << b
+    assert b >= 12 and a % big == 0 and z % big == 0 and n0 <= a < z <= n0 + m and a - n0 < big and n0 + m - z < big
+    blocks = (z - a) >> b
+    assert 1 <= blocks <= 8 * g
+    out = np.zeros((_mmr_size(n0 + m), 4), np.uint64)
+    out[:_mmr_size(n0)] = want[:_mmr_size(n0)]                     # the MMR before the append
+    if a > n0:                                                     # head, by context 0
+        out[:_mmr_size(a)] = oracle.mmr_extend(out[:_mmr_size(n0)], leaves[n0:a])
+    for j in range(blocks):                                        # blocks, from empty, into their slices
+        start = a + j * big
+        out[_mmr_size(start):_mmr_size(start) + 2 * big - 1] = oracle.mmr_extend(None, leaves[start:start + big])
+    s0, s1 = a >> b, (a >> b) + blocks                             # coarse MMR over the block roots
+    sup = np.zeros((_mmr_size(s1), 4), np.uint64)
+    base = 0
+    for bit in range(63, -1, -1):
+        if (s0 >> bit) & 1:
+            base += 1 << bit
+            sup[_mmr_size(base) - 1] = out[_mmr_size(base << b) - 1]
+    for s_ in range(s0, s1):
+        sup[_mmr_pos(0, s_)] = out[_mmr_pos(b, s_)]
+    l = 1
+    while (s1 >> l) > 0:
+        for k in range(s0 >> l, s1 >> l):
+            p = _mmr_pos(l, k)
+            sup[p] = oracle.two_to_one(sup[p - (1 << l)], sup[p - 1])
+            out[_mmr_pos(l + b, k)] = sup[p]
+        l += 1
+    if n0 + m > z:                                                 # tail
+        out = oracle.mmr_extend(out[:_mmr_size(z)], leaves[z:])
+    assert np.array_equal(out, want)

@@ -718,6 +718,41 @@ def test_multi_context_build_errors(ctx_pool, api):
     assert e.value.code == PMT_E_RANGE
 
 
+@pytest.mark.parametrize("n0,m,G", [(0, 1 << 15, 2), (0, 1 << 17, 8), (12345, (1 << 15) + 77, 2), (4096, 3 * 4096, 3), (4095, 2 * 4096 + 2, 2),
+                                    (1 << 14, (1 << 16) - 1, 4), (7, 40000, 4), (3 << 12, 1 << 13, 2), (100, 5000, 2), (0, 1 << 13, 1),
+                                    (0, (1 << 18) + 5, 8), (999, 1 << 18, 5)])
+def test_multi_context_mmr_extend_equals_oracle(ctx_pool, api, oracle, n0, m, G):
+    """pmt_mmr_extend_multi: head on context 0, aligned blocks as sub-mountains built from empty by context j mod G, the coarse
+    MMR over the block roots finished on context 0, tail -- element by element the sequential MMR"""
+    leaves = splitmix_felts(5000 + n0 + m + G, n0 + m)
+    leaves[n0] = np.uint64(2**64 - 1)     # non-canonical input
+    if n0 + m <= 1 << 16:
+        want = oracle.mmr_extend(None, leaves)
+    else:                                  # the device-resident single-context append (tied to the oracle by the tests above)
+        one = api.mmr.MMR.new(ctx_pool[0])
+        one.extend(leaves)
+        want = one.elements
+    before = want[:2 * n0 - bin(n0).count("1")].copy()
+    got = api.mmr.extend_multi(before if n0 else None, n0, leaves[n0:], ctx_pool[:G])
+    assert got.shape == want.shape
+    assert np.array_equal(got, want)
+    assert (api.mmr.multi_plan(n0, m, G) is not None) == (G > 1 and m // G >= 4096 and ((n0 + m) >> 12) > ((n0 + 4095) >> 12))
+
+
+def test_multi_context_mmr_extend_errors(ctx_pool, api):
+    from plonky2_merkle_trees_b200._lib import PmtError, PMT_E_INVALID_ARG, PMT_E_RANGE
+    with pytest.raises(PmtError) as e:
+        api.mmr.extend_multi(None, 0, np.arange(10, dtype=np.uint64), [ctx_pool[1], ctx_pool[1]])
+    assert e.value.code == PMT_E_INVALID_ARG
+    assert api.mmr.extend_multi(None, 0, [], ctx_pool[:2]).shape == (0, 4)
+    import ctypes as C
+    handles = (C.c_void_p * 2)(ctx_pool[0].h, ctx_pool[1].h)
+    buf = np.zeros((4, 4), np.uint64)
+    leaves = np.zeros(1, np.uint64)
+    rc = ctx_pool[0].lib.pmt_mmr_extend_multi(handles, 2, buf.ctypes.data_as(C.POINTER(C.c_uint64)), (1 << 30), leaves.ctypes.data_as(C.POINTER(C.c_uint64)), 1)
+    assert rc == PMT_E_RANGE
+
+
 @pytest.mark.parametrize("n_roots,h", [(2, 0), (2, 1), (8, 0), (8, 2), (64, 0), (1024, 3), (4096, 0), (8192, 1)])
 def test_top_levels_above_gathered_roots(ctx, oracle, n_roots, h):
     """pmt_top_levels_dev: single cooperative launch up to 4096 roots, one launch per level beyond that."""
