@@ -35,8 +35,8 @@ def main():
     while g <= ndev:
         handles = (C.c_void_p * g)(*[c.h for c in ctxs[:g]])
         ts = []
-        h_dig.zero_()     # before the first (untimed) call only.  profiles/multi_ctx_2gpu_r1.jsonl zeroed before EVERY call and shows
-        for _ in range(5):  # 27 ms on one device where bench.py's e2e leg measures 22 ms for the same call (suspected: dirty lines)
+        h_dig.zero_()     # before the first (untimed) call only.  profiles/multi_ctx_2gpu_r1.jsonl zeroed before EVERY call: 27.4 ms
+        for _ in range(5):  # on one device against 21.7 ms without (profiles/multi_ctx_1gpu_nozero_r1.jsonl): dirty host cache lines
             t0 = time.perf_counter()
             rc = lib.pmt_merkle_tree_build_multi(handles, g, C.cast(h_leaves.data_ptr(), u64p), n, w, h, C.cast(h_dig.data_ptr(), u64p),
                                                  C.cast(h_cap.data_ptr(), u64p))
