@@ -224,3 +224,50 @@ def test_mmr_multi_plan_and_block_construction(oracle, n0, m, g):
     if n0 + m > z:                                                 # tail
         out = oracle.mmr_extend(out[:_mmr_size(z)], leaves[z:])
     assert np.array_equal(out, want)
+
+
+def test_mmr_multi_plan_invariants_random():
+    """pmt_mmr_multi_plan over 20 000 random (n_before, m, contexts): block size, alignment, head / tail bounds, block count, and
+    that every node the plan assigns (head, blocks, coarse nodes, tail) is a distinct new position of the post-order array."""
+    import random
+    from plonky2_merkle_trees_b200 import mmr
+    rnd = random.Random(7)
+    split = 0
+    for it in range(20000):
+        g = rnd.choice([1, 2, 3, 4, 5, 8, 16])
+        m = rnd.choice([rnd.randrange(1, 1 << 14), rnd.randrange(1, 1 << 20), 1 << rnd.randrange(10, 24), (1 << rnd.randrange(12, 24)) - 1])
+        n0 = rnd.choice([0, rnd.randrange(0, 1 << 22), 1 << rnd.randrange(0, 24), rnd.randrange(0, 1 << 12)])
+        plan = mmr.multi_plan(n0, m, g)
+        if g == 1 or m // g < 4096:
+            assert plan is None
+            continue
+        if plan is None:        # no aligned block of 2^b leaves inside [n0, n0 + m): only possible for the smallest b
+            fl = (m // g).bit_length() - 1
+            b = max(fl - 2, 12)
+            assert ((n0 + m) >> b) <= ((n0 + (1 << b) - 1) >> b)
+            continue
+        split += 1
+        b, a, z = plan
+        big = 1 << b
+        assert b == max((m // g).bit_length() - 1 - 2, 12)
+        assert a % big == 0 and z % big == 0 and n0 <= a < z <= n0 + m and a - n0 < big and n0 + m - z < big
+        blocks = (z - a) >> b
+        assert 1 <= blocks <= 8 * g
+        if it % 50 == 0:        # the positions written by the four parts tile [mmr_size(n0), mmr_size(n0 + m)) exactly
+            new = _mmr_size(n0 + m) - _mmr_size(n0)
+            head = _mmr_size(a) - _mmr_size(n0)
+            tail = _mmr_size(n0 + m) - _mmr_size(z)
+            coarse = set()
+            s0, s1 = a >> b, (a >> b) + blocks
+            l = 1
+            while (s1 >> l) > 0:
+                for k in range(s0 >> l, s1 >> l):
+                    p = _mmr_pos(l + b, k)
+                    assert _mmr_size(a) <= p < _mmr_size(z) and p not in coarse
+                    coarse.add(p)
+                l += 1
+            for j in range(blocks):
+                lo = _mmr_size(a + j * big)
+                assert not any(lo <= p < lo + 2 * big - 1 for p in coarse)
+            assert head + blocks * (2 * big - 1) + len(coarse) + tail == new
+    assert split > 3000
