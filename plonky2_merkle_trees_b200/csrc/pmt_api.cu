@@ -210,6 +210,23 @@ int launch_level_span(pmt_ctx* c, const Layout& lay, int l_first, int l_last, si
   return PMT_OK;
 }
 
+// work(0 .. n-1), one host thread per index (index 0 on the calling thread), all joined before it returns.  Never throws:
+// an exception inside work(r) becomes rcs[r] = PMT_E_OOM, and if no thread can be had that index runs on the caller.
+template <class F>
+void run_per_ctx(std::vector<int>& rcs, F&& work) {
+  const size_t n = rcs.size();
+  auto guarded = [&](size_t r) {
+    try { work(r); } catch (...) { rcs[r] = PMT_E_OOM; }
+  };
+  std::vector<std::thread> pool;
+  try { pool.reserve(n - 1); } catch (...) {}
+  for (size_t r = 1; r < n; r++) {
+    try { pool.emplace_back(guarded, r); } catch (...) { guarded(r); }
+  }
+  guarded(0);
+  for (auto& t : pool) t.join();
+}
+
 }  // namespace
 
 extern "C" {
@@ -812,6 +829,7 @@ int pmt_merkle_tree_build_multi(pmt_ctx* const* ctxs, size_t n_ctx, const uint64
   const size_t n_cap = (size_t)1 << cap_height, n_dig = 2 * (n - n_cap);
   if (!leaves || !cap_out || (!digests_out && n_dig)) return fail(c0, PMT_E_INVALID_ARG, "MerkleTree::new: null pointer");
   if (n_ctx == 1) return pmt_merkle_tree_build(c0, leaves, n, w, cap_height, digests_out, cap_out);
+  try {
   const size_t per = n >> g;
   const int L = lg - (int)cap_height, Lr = lg - g;
   const bool gather = (int)cap_height < g;
@@ -827,13 +845,7 @@ int pmt_merkle_tree_build_multi(pmt_ctx* const* ctxs, size_t n_ctx, const uint64
       rcs[r] = pmt_merkle_tree_build(ctxs[r], my, per, w, 0, digests_out + 4 * plonky2_index(L, 0, r * per), roots.data() + 4 * r);
     }
   };
-  {
-    std::vector<std::thread> pool;
-    pool.reserve(n_ctx - 1);
-    for (size_t r = 1; r < n_ctx; r++) pool.emplace_back(work, r);
-    work(0);
-    for (auto& t : pool) t.join();
-  }
+  run_per_ctx(rcs, work);
   for (size_t r = 0; r < n_ctx; r++)
     if (rcs[r] != PMT_OK) {
       char msg[sizeof ctxs[r]->err];
@@ -861,6 +873,9 @@ int pmt_merkle_tree_build_multi(pmt_ctx* const* ctxs, size_t n_ctx, const uint64
     if (cnt == 1) break;
   }
   return PMT_OK;
+  } catch (const std::bad_alloc&) {
+    return fail(c0, PMT_E_OOM, "multi build: out of host memory");
+  }
 }
 
 // Host-buffer batch append.  Only the old PEAKS are uploaded (a new node's left child is either new or an old peak), and
@@ -981,6 +996,7 @@ int pmt_mmr_extend_multi(pmt_ctx* const* ctxs, size_t n_ctx, uint64_t* elements,
   uint32_t b = 0;
   size_t A = 0, Z = 0;
   if (!pmt_mmr_multi_plan(n0, m, n_ctx, &b, &A, &Z)) return pmt_mmr_extend(c0, elements, n0, new_leaves, m);
+  try {
   const size_t B = (size_t)1 << b, C = (Z - A) >> b;
   std::vector<int> rcs(n_ctx, PMT_OK);
   auto work = [&](size_t r) {
@@ -994,13 +1010,7 @@ int pmt_mmr_extend_multi(pmt_ctx* const* ctxs, size_t n_ctx, uint64_t* elements,
       if (rcs[r] != PMT_OK) return;
     }
   };
-  {
-    std::vector<std::thread> pool;
-    pool.reserve(n_ctx - 1);
-    for (size_t r = 1; r < n_ctx; r++) pool.emplace_back(work, r);
-    work(0);
-    for (auto& t : pool) t.join();
-  }
+  run_per_ctx(rcs, work);
   for (size_t r = 0; r < n_ctx; r++)
     if (rcs[r] != PMT_OK) {
       char msg[sizeof ctxs[r]->err];
@@ -1032,6 +1042,9 @@ int pmt_mmr_extend_multi(pmt_ctx* const* ctxs, size_t n_ctx, uint64_t* elements,
   FINISH(c0);
   if (n0 + m > Z) return pmt_mmr_extend(c0, elements, Z, new_leaves + (Z - n0), n0 + m - Z);
   return PMT_OK;
+  } catch (const std::bad_alloc&) {
+    return fail(c0, PMT_E_OOM, "mmr extend multi: out of host memory");
+  }
 }
 
 // positions of the peaks in the post-order array, largest mountain first (get_peaks, :179-200)
