@@ -15,7 +15,14 @@ all_gather and the log2(N) top levels are finished on every rank ("scaling": "we
 `roofline`   dominant kernel = k_level (one two_to_one per thread).  The path is integer-pipe bound:
              achieved = permutations/s x 10 588 MAC32 / measured IMAD.WIDE.U32 issue peak; the HBM view (96 algorithmic
              bytes per permutation against MEASURED_PEAKS.json) is reported beside it as evidence that HBM is not the limit.
-`cpu_baseline` the CPU oracle's restatement of MerkleTree::new (OpenMP fork-join like rayon's) on the host cores.
+`cpu_baseline` the CPU oracle's restatement of MerkleTree::new (OpenMP fork-join like rayon's) on the host cores, on the
+             FULL workload of one GPU (2^24 leaves: a few seconds) -- the same size the `--impl reference` arm times.
+`parity_checked` every timed number carries its own check: the digests the e2e call left in host memory and a slice of the
+             device-timed build are compared BYTE FOR BYTE with the cpu_baseline leg's output (rank 0: all 2^25 - 2 digests
+             of its tree; other ranks: the subtree over their first 2^16 leaves), and at N > 1 the gathered subtree roots are
+             folded with the oracle's two_to_one and compared with the GPU's root.  A mismatch exits non-zero.
+`strong`     strong scaling on FIXED inputs, measured in this run: one 2^24-leaf tree, one 2^28-leaf tree and an MMR of 2^24
+             leaves, built on rank 0's GPU alone and sharded over all N ranks (speed-up = the ratio; sharded root == single root).
 """
 import argparse
 import json
@@ -161,39 +168,51 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------------
 # CPU arm (oracle = "port" of the reference algorithm; the Rust reference itself cannot be built here)
 # ------------------------------------------------------------------------------------------------------------------
-def cpu_tree_throughput(log2_sample, reps=1):
+def oracle_module():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import numpy as np
     import oracle as orc
+    return orc
+
+
+def cpu_tree(log2_sample, start_leaf=0, threads=None, rows=None):
+    """one MerkleTree::new (cap 0) by the oracle over leaves [start_leaf, start_leaf + 2^log2_sample) of the synthetic input
+    -> (leaves/s, threads, seconds, digests, cap)"""
+    orc = oracle_module()
     orc.build()
     n = 1 << log2_sample
-    rows = splitmix_numpy(0, n * WIDTH).reshape(n, WIDTH)
-    threads = orc.max_threads()
-    best = None
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        orc.merkle_tree_new(rows, CAP_HEIGHT, threads=threads, fast=True)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return n / best, threads, best
+    if rows is None:
+        rows = splitmix_numpy(start_leaf * WIDTH, n * WIDTH).reshape(n, WIDTH)
+    threads = threads or orc.max_threads()
+    t0 = time.perf_counter()
+    digests, cap = orc.merkle_tree_new(rows, CAP_HEIGHT, threads=threads, fast=True)
+    dt = time.perf_counter() - t0
+    return n / dt, threads, dt, digests, cap
+
+
+def cpu_tree_throughput(log2_sample):
+    v, threads, dt, _, _ = cpu_tree(log2_sample)
+    return v, threads, dt
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return None, 0
-    log2_sample = 20
+    # one step = one MerkleTree::new over the FULL per-GPU workload the config names (2^24 x 4 leaves: ~1.5 - 5 s on 32 - 8
+    # host threads, so W + K = 25 steps stay within a couple of minutes); the leaves are generated once, outside the steps
+    log2_sample = LOG2_LEAVES_PER_GPU
+    n = 1 << log2_sample
+    rows = splitmix_numpy(0, n * WIDTH).reshape(n, WIDTH)
     for _ in range(args.warmup):
-        cpu_tree_throughput(log2_sample)
+        cpu_tree(log2_sample, rows=rows)
     times = []
     threads = 1
     for _ in range(args.steps):
-        v, threads, dt = cpu_tree_throughput(log2_sample)
+        v, threads, dt, _, _ = cpu_tree(log2_sample, rows=rows)
         times.append(dt)
     ms = 1e3 * sum(times) / len(times)
     value = (1 << log2_sample) / (ms * 1e-3)
-    sample = "MerkleTree::new on 2^%d x %d leaves per step (bounded sample of the 2^%d workload; throughput is linear in n)" % (
-        log2_sample, WIDTH, LOG2_LEAVES_PER_GPU)
+    sample = "MerkleTree::new on 2^%d x %d leaves per step: the full per-GPU workload of the config, not a sample" % (log2_sample, WIDTH)
     line = {
         "impl": "reference", "metric": "poseidon_goldilocks_merkle_leaves_per_sec", "value": value, "unit": "leaves/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -215,6 +234,115 @@ def workload_config(n_gpus):
             "leaves_per_gpu": 1 << LOG2_LEAVES_PER_GPU, "leaf_width": WIDTH, "cap_height": CAP_HEIGHT,
             "global_leaves": n_gpus << LOG2_LEAVES_PER_GPU, "parallelism": "subtree-shard x%d" % n_gpus,
             "l2_policy": "inputs (512 MiB leaves + 1 GiB digests per GPU) are larger than the 126 MB L2"}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# strong scaling on fixed inputs (BASELINE.json north_star: "2^24-leaf inputs ... scaling >= 7x on 8 GPUs"; C5 = 2^28 leaves)
+# ------------------------------------------------------------------------------------------------------------------
+def strong_scaling(ctx, eng, dev, world, rank, root24=None):
+    """Collective over all ranks.  Three fixed inputs -- a 2^24-leaf tree, a 2^28-leaf tree (4 felts per leaf, cap 0) and an MMR
+    of 2^24 single-felt leaves -- are built (a) on rank 0's GPU alone and (b) sharded over all N ranks (subtree shards, NCCL
+    all_gather of the roots, top levels on every rank), device-resident, timed with CUDA events on each rank's ctx stream,
+    max over ranks, median of 5.  speedup = (a) / (b), both measured here, in this run.  The sharded root / peaks / bag must
+    equal the single-GPU ones (and, for the 2^24 tree, the oracle's root from the parity leg)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from plonky2_merkle_trees_b200 import sharded
+    from plonky2_merkle_trees_b200.device import dev_u64, dptr
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    def fence():
+        torch.cuda.synchronize(); ctx.sync()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, active=True, reps=5, warm=2):
+        res = None
+        for _ in range(warm):
+            if active:
+                res = fn()
+        ts = []
+        for _ in range(reps):
+            fence()
+            ms = 0.0
+            if active:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream); res = fn(); e1.record(stream)
+                ctx.sync(); torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1)
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ts.append(float(t.item()))
+        ts.sort()
+        return ts[len(ts) // 2], ts[0], res
+
+    out = {"n_gpus": world, "ok": True, "how": "device-resident, CUDA events on each rank's stream, max over ranks, median of 5; "
+           "1-GPU time measured on rank 0 alone in the same run", "cases": {}}
+    for name, lg in (("tree_2p24", 24), ("tree_2p28", 28)):
+        n = 1 << lg
+        # (a) one GPU: rank 0 builds the whole tree
+        cap1 = None
+        if rank == 0:
+            d_all = splitmix_torch(0, n * WIDTH, dev).view(n, WIDTH)
+            d_dig, d_cap = dev_u64((2 * n - 2, 4), dev), dev_u64((1, 4), dev)
+        ms1, best1, _ = timed(lambda: ctx.call("pmt_merkle_tree_build_dev", dptr(d_all), n, WIDTH, 0, dptr(d_dig), dptr(d_cap)), active=rank == 0)
+        if rank == 0:
+            cap1 = d_cap.cpu().numpy().view(np.uint64).copy()
+            del d_all, d_dig, d_cap
+        torch.cuda.empty_cache()
+        case = {"leaves": n, "ms_1gpu": ms1, "leaves_per_s_1gpu": n / (ms1 * 1e-3)}
+        if world > 1:
+            per = n // world
+            d_mine = splitmix_torch(rank * per * WIDTH, per * WIDTH, dev).view(per, WIDTH)
+            msn, bestn, tree = timed(lambda: sharded.build_sharded_tree(d_mine, n, 0, eng))
+            capn = tree.cap.cpu().numpy().view(np.uint64)
+            ok = True
+            if rank == 0:
+                ok = bool(np.array_equal(capn, cap1)) and (root24 is None or lg != 24 or bool(np.array_equal(capn, root24)))
+            case.update({"ms_%dgpu" % world: msn, "leaves_per_s_%dgpu" % world: n / (msn * 1e-3), "speedup": ms1 / msn,
+                         "root_equals_single_gpu_build": ok})
+            out["ok"] &= ok
+            del tree, d_mine
+            torch.cuda.empty_cache()
+        elif rank == 0 and lg == 24 and root24 is not None:
+            case["root_equals_oracle"] = bool(np.array_equal(cap1, root24))
+            out["ok"] &= case["root_equals_oracle"]
+        out["cases"][name] = case
+    # MMR of 2^24 single-felt leaves (BASELINE C3): one mountain; batch append from empty
+    n = 1 << 24
+    size = 2 * n - 1
+    if rank == 0:
+        d_leaves = splitmix_torch(0, n, dev)
+        d_el = dev_u64((size, 4), dev)
+    ms1, _, _ = timed(lambda: ctx.call("pmt_mmr_extend_dev", dptr(d_el), 0, dptr(d_leaves), n), active=rank == 0)
+    case = {"leaves": n, "ms_1gpu": ms1, "leaves_per_s_1gpu": n / (ms1 * 1e-3)}
+    if rank == 0:
+        peak1 = d_el[size - 1].cpu().numpy().view(np.uint64).copy()
+        del d_leaves, d_el
+    torch.cuda.empty_cache()
+    if world > 1:
+        rngs = sharded.mmr_shard_ranges(n, world, rank)
+        d_mine = torch.cat([splitmix_torch(a, c, dev) for a, c in rngs])
+        msn, _, sm = timed(lambda: sharded.build_sharded_mmr(d_mine, n, eng))
+        peaks = np.asarray(sm.get_peaks())
+        ok = True
+        if rank == 0:
+            ok = peaks.shape[0] == 1 and bool(np.array_equal(peaks[0], peak1))
+        case.update({"ms_%dgpu" % world: msn, "leaves_per_s_%dgpu" % world: n / (msn * 1e-3), "speedup": ms1 / msn,
+                     "peak_equals_single_gpu_build": ok})
+        out["ok"] &= ok
+        del sm, d_mine
+        torch.cuda.empty_cache()
+    out["cases"]["mmr_2p24"] = case
+    # every rank learns the verdict (the exit code of the whole job)
+    flag = torch.tensor([1 if out["ok"] else 0], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    out["ok"] = bool(flag.item())
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -296,6 +424,12 @@ def run_ours(args):
     n_dig = 2 * (n_local - 1)
     h_digests = torch.empty((n_dig, 4), dtype=torch.int64).pin_memory()
     h_cap = torch.empty((1, 4), dtype=torch.int64).pin_memory()
+    # what the device-timed steps produced, kept for the parity check below: the subtree over this rank's first 2^16
+    # leaves (a contiguous slice of upstream's layout), the local root and, at N > 1, the gathered roots and the final root
+    PAR_LOG2 = 16
+    dev_slice = tree.local_digests[:(2 << PAR_LOG2) - 2].cpu().numpy().view(np.uint64)
+    dev_root = tree.cap.cpu().numpy().view(np.uint64).copy()
+    dev_roots = tree.roots.cpu().numpy().view(np.uint64).copy() if tree.roots is not None else None
     del tree
     torch.cuda.empty_cache()
 
@@ -326,15 +460,63 @@ def run_ours(args):
     if prev_affinity is not None:
         os.sched_setaffinity(0, prev_affinity)
 
-    # parity spot check of what was just measured (size-independent property: leaf digests are the canonical no-op copy)
+    # ---- parity of what was just measured, against the oracle, in this run ------------------------------------------------
+    # rank 0 rebuilds ITS WHOLE 2^24-leaf tree on the host cores (this is also the cpu_baseline measurement) and compares all
+    # 2^25 - 2 digests the e2e call left in host memory; the other ranks compare the subtree over their first 2^16 leaves;
+    # every rank also compares that slice of the device-timed build; at N > 1 rank 0 folds the gathered roots with the
+    # oracle's two_to_one and compares with the GPU's root.
     hd = h_digests.numpy().view(np.uint64)
-    hl = h_leaves.numpy().view(np.uint64)
-    assert np.array_equal(hd[0], hl[0]) and np.array_equal(hd[1], hl[1]) and np.array_equal(hd[4], hl[2]), "leaf digests are not the no-op copy"
+    node = lambda l, k: 2 * (((k >> 1) << (l + 1)) + (1 << l) - 1) + (k & 1)      # upstream's interleaved layout, cap 0
+    orc = oracle_module()
+    if rank == 0:
+        orc.build()
+    if world > 1:
+        dist.barrier()
+    checked, ok, cpu = 0, True, None
+    if rank == 0:
+        cpu_v, cpu_threads, cpu_dt, odg, ocap = cpu_tree(LOG2_LEAVES_PER_GPU, 0)
+        cpu = {"value": cpu_v, "unit": "leaves/s", "cores": cpu_threads, "kind": "port",
+               "sample": "one MerkleTree::new over 2^%d x %d leaves = the full per-GPU workload (%.2f s wall on %d threads) with the "
+                         "oracle's C restatement (OpenMP fork-join, fast partial rounds)" % (LOG2_LEAVES_PER_GPU, WIDTH, cpu_dt, cpu_threads)}
+        ok &= bool(np.array_equal(hd, odg)) and bool(np.array_equal(h_cap.numpy().view(np.uint64), ocap))
+        ok &= bool(np.array_equal(dev_slice, odg[:dev_slice.shape[0]]))
+        ok &= bool(np.array_equal(dev_root if world == 1 else dev_roots[0:1], ocap))
+        checked += odg.shape[0] + 1 + dev_slice.shape[0] + 1
+        del odg
+    else:
+        _, _, _, odg, ocap = cpu_tree(PAR_LOG2, rank * n_local, threads=2)
+        ok &= bool(np.array_equal(hd[:odg.shape[0]], odg)) and bool(np.array_equal(hd[node(PAR_LOG2, 0)], ocap[0]))
+        ok &= bool(np.array_equal(dev_slice, odg))
+        checked += 2 * odg.shape[0] + 1
+    if world > 1 and rank == 0:        # the top of the sharded tree: oracle fold of the N gathered subtree roots
+        lvl = dev_roots
+        while lvl.shape[0] > 1:
+            lvl = orc.two_to_one_batch(lvl[0::2], lvl[1::2])
+            checked += lvl.shape[0]
+        ok &= bool(np.array_equal(lvl, dev_root))
+    flags = torch.tensor([1 if ok else 0, checked], dtype=torch.int64, device=dev)
+    if world > 1:
+        oks = [torch.zeros_like(flags) for _ in range(world)]
+        dist.all_gather(oks, flags)
+        ok = all(int(t[0].item()) == 1 for t in oks)
+        checked = sum(int(t[1].item()) for t in oks)
+    parity = {"ok": bool(ok), "nodes": int(checked),
+              "what": "e2e host digests == oracle (rank 0: all 2^25 - 2 of its tree; other ranks: the 2^17 - 2 under their first 2^16 "
+                      "leaves), the same slice of the device-timed build == oracle, root == oracle"
+                      + (", GPU root == oracle fold of the %d gathered subtree roots" % world if world > 1 else "")}
+
+    # ---- strong scaling on fixed inputs, measured in this run (BASELINE.json: 2^24-leaf inputs, C5 = 2^28) ------------------
+    root24 = ocap if rank == 0 else None              # rank 0's weak-scaling shard is leaves [0, 2^24): the strong 2^24 tree
+    del d_leaves, h_leaves, h_digests, hd
+    torch.cuda.empty_cache()
+    strong = strong_scaling(ctx, eng, dev, world, rank, root24)
+    if strong is not None and not strong.get("ok", True):
+        parity["ok"] = False
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
-        return None, 0
+        return None, 0 if parity["ok"] else 1
 
     # ---- roofline of the dominant kernel ------------------------------------------------------------------------------
     peaks, peak_src = measured_peaks()
@@ -369,13 +551,6 @@ def run_ours(args):
         "hardware_view": hardware,
     }
 
-    # ---- CPU baseline on this box's host cores (bounded sample) ---------------------------------------------------------
-    cpu_log2 = 22
-    cpu_v, cpu_threads, cpu_dt = cpu_tree_throughput(cpu_log2)
-    cpu = {"value": cpu_v, "unit": "leaves/s", "cores": cpu_threads, "kind": "port",
-           "sample": "one MerkleTree::new over 2^%d x %d leaves (%.2f s wall on %d threads) with the oracle's C restatement "
-                     "(OpenMP fork-join, fast partial rounds)" % (cpu_log2, WIDTH, cpu_dt, cpu_threads)}
-
     line = {
         "metric": "poseidon_goldilocks_merkle_leaves_per_sec", "value": value, "unit": "leaves/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
@@ -390,10 +565,14 @@ def run_ours(args):
         "kernels": prof,
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "parity_checked": parity,
+        "strong": strong,
     }
     if world > 1:
         dist.destroy_process_group()
-    return line, 0
+    if not parity["ok"]:
+        sys.stderr.write("bench.py: PARITY MISMATCH against the oracle: %s\n" % json.dumps(parity))
+    return line, 0 if parity["ok"] else 1
 
 
 class StdoutToStderr:

@@ -17,9 +17,11 @@
  *     pmt_sync() before reading results on the host.  The host-buffer entry points are synchronous.
  *   - there is no CPU fallback: every entry point that computes fails with PMT_E_CUDA when no device is usable.
  *   - tuning knobs read from the environment at pmt_init / call time (measurement aids; the defaults are the measured
- *     optima, results never depend on them): PMT_COOP_MAX_LOG2 (levels of at most 2^k nodes run 16 lanes per node,
- *     default 13), PMT_FUSE_SUBTREES (0: one launch per small level instead of fused subtree blocks),
+ *     optima, results never depend on them): PMT_COOP_MAX_LOG2 (levels of at most 2^k nodes run four threads per node,
+ *     default 13), PMT_FUSE_SUBTREES (0: one launch per small level instead of ONE launch for the whole tail of a tree),
  *     PMT_PIPELINE_LOG2_CHUNKS (chunks of the pipelined host-buffer tree build, default 4).
+ *   - every host-buffer entry point that fails has drained its streams first: when it returns, the library no longer
+ *     reads or writes the caller's buffers, whatever the status.
  */
 #ifndef PMT_H
 #define PMT_H
@@ -61,6 +63,17 @@ int pmt_free(pmt_ctx* ctx, void* dptr);
 int pmt_memcpy_h2d(pmt_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
 int pmt_memcpy_d2h(pmt_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
 
+/* Page-locked host memory for the host-buffer entry points.  Those pipeline H2D copies, hashing and D2H copies over chunks;
+ * the overlap needs page-locked ("pinned") host buffers -- from pageable memory (a plain Rust Vec / malloc) the CUDA driver
+ * stages every copy through its own bounce buffer and the pipeline serialises (measured: DESIGN.md 5).  Either lock
+ * buffers the host already owns (pmt_host_register: cudaHostRegister; page-locking costs ~0.2 ms per MiB, so do it once
+ * for buffers that are reused) or let the library allocate them (pmt_host_alloc: cudaHostAlloc, portable across devices;
+ * in Rust the backing store of a Vec<T, A> with a custom allocator).  Results never depend on the kind of memory. */
+int pmt_host_register(pmt_ctx* ctx, void* ptr, size_t bytes);
+int pmt_host_unregister(pmt_ctx* ctx, void* ptr);
+int pmt_host_alloc(pmt_ctx* ctx, size_t bytes, void** ptr_out);
+int pmt_host_free(pmt_ctx* ctx, void* ptr);
+
 /* ---- Hasher: [UPSTREAM] plonk/config.rs Hasher for PoseidonHash ------------------------------------------------------ */
 /* n independent width-12 permutations (parity hook for Poseidon::poseidon); in/out n*12 felts */
 int pmt_permute(pmt_ctx* ctx, const uint64_t* in, size_t n, uint64_t* out);
@@ -81,10 +94,16 @@ int pmt_hash_rows_dev(pmt_ctx* ctx, const uint64_t* d_rows, size_t n_rows, size_
  * (level 0 = n leaf digests, level 1 = n/2, ..., last = 2) = MerkleTree.tree flattened; root_out: 1 digest. */
 int pmt_simple_tree_build(pmt_ctx* ctx, const uint64_t* leaves, size_t n, uint64_t* levels_out, uint64_t* root_out);
 int pmt_simple_tree_build_dev(pmt_ctx* ctx, const uint64_t* d_leaves, size_t n, uint64_t* d_levels, uint64_t* d_root);
-/* get_merkle_proof (:55-74) for a batch: siblings_out n_idx * log2(n) digests, bottom-up.  levels on the DEVICE. */
+/* get_merkle_proof (:55-74) for a batch: siblings_out n_idx * log2(n) digests, bottom-up.  levels on the DEVICE.
+ * The indices are on the device too, so the reference's assert!(leaf_index < n) (:56) cannot be a status code here: an
+ * index >= n yields an all-zero proof (nothing outside `levels` is read).  The same holds for pmt_merkle_prove_dev;
+ * pmt_mmr_prove_dev returns path_len 0 for it.  The host-buffer forms below return PMT_E_RANGE instead. */
 int pmt_simple_tree_prove_dev(pmt_ctx* ctx, const uint64_t* d_levels, size_t n, const uint64_t* d_idx, size_t n_idx,
                               uint64_t* d_siblings_out);
-/* verify_merkle_proof (:91-109) for a batch sharing one root: ok_out[i] = 1/0.  proofs: n_idx * path_len digests */
+/* verify_merkle_proof (:91-109) for a batch sharing one root: ok_out[i] = 1/0.  proofs: n_idx * path_len digests.
+ * Exactly the reference's predicate: it folds by the parities of leaf_index >> i, i < path_len, and never looks at the
+ * index bits above, so leaf_index + k 2^path_len verifies like leaf_index (upstream's verify_merkle_proof_to_cap below
+ * rejects such an index: it selects cap[index >> path_len]). */
 int pmt_simple_tree_verify_dev(pmt_ctx* ctx, const uint64_t* d_leaves, const uint64_t* d_idx, size_t n_idx,
                                const uint64_t* d_root, const uint64_t* d_proofs, size_t path_len, uint8_t* d_ok_out);
 
@@ -133,7 +152,10 @@ size_t pmt_mmr_size(size_t n_leaves);
 /* get_mmr_index (:257-270) = 2i - popcount(i) */
 size_t pmt_mmr_index(size_t leaf_normal_index);
 /* batch of MMR::add_leaf (:89-120): append m single-felt leaves to an MMR that already has n_before leaves.
- * elements: post-order array with capacity >= pmt_mmr_size(n_before + m) digests, first pmt_mmr_size(n_before) valid. */
+ * elements: post-order array with capacity >= pmt_mmr_size(n_before + m) digests, first pmt_mmr_size(n_before) valid.
+ * The host-buffer form reads only the popcount(n_before) old peaks of `elements` and writes only the new elements; the
+ * device holds just those (O(m + log n_before) memory and PCIe traffic, like the O(log n) add_leaf it batches).  It is
+ * one synchronous round trip per call: feed leaves in batches, not one by one. */
 int pmt_mmr_extend(pmt_ctx* ctx, uint64_t* elements, size_t n_before, const uint64_t* new_leaves, size_t m);
 int pmt_mmr_extend_dev(pmt_ctx* ctx, uint64_t* d_elements, size_t n_before, const uint64_t* d_new_leaves, size_t m);
 /* The same batch append over SEVERAL GPUs from one host process: n_ctx distinct contexts (any count), normally one per
@@ -156,7 +178,8 @@ int pmt_mmr_bag_dev(pmt_ctx* ctx, const uint64_t* d_elements, size_t n_leaves, u
 int pmt_mmr_prove_dev(pmt_ctx* ctx, const uint64_t* d_elements, size_t n_leaves, const uint64_t* d_leaf_idx,
                       size_t n_idx, uint64_t* d_siblings_out, uint8_t* d_on_left_out, uint32_t* d_path_len_out);
 /* MMR_proof::verify (:232-252) for a batch sharing peaks + root: status_out[i] = 1 true, 0 false,
- * -1 = the reference would panic (subtree root not among the peaks, assert! at :245) */
+ * -1 = the reference would panic (subtree root not among the peaks, assert! at :245).  A proof is untrusted input:
+ * path_len[i] > 32 (more than the layout holds; an MMR has < 2^30 leaves) is -1 as well and nothing is folded. */
 int pmt_mmr_verify_dev(pmt_ctx* ctx, const uint64_t* d_leaves, size_t n_idx, const uint64_t* d_siblings,
                        const uint8_t* d_on_left, const uint32_t* d_path_len, const uint64_t* d_peaks, uint32_t n_peaks,
                        const uint64_t* d_root, int8_t* d_status_out);

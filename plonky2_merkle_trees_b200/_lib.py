@@ -33,6 +33,10 @@ _SIGNATURES = {
     "pmt_free": (_INT, [_VP, _VP]),
     "pmt_memcpy_h2d": (_INT, [_VP, _VP, _VP, _SZ]),
     "pmt_memcpy_d2h": (_INT, [_VP, _VP, _VP, _SZ]),
+    "pmt_host_register": (_INT, [_VP, _VP, _SZ]),
+    "pmt_host_unregister": (_INT, [_VP, _VP]),
+    "pmt_host_alloc": (_INT, [_VP, _SZ, C.POINTER(_VP)]),
+    "pmt_host_free": (_INT, [_VP, _VP]),
     "pmt_permute": (_INT, [_VP, u64p, _SZ, u64p]),
     "pmt_hash_two_to_one": (_INT, [_VP, u64p, u64p, _SZ, u64p]),
     "pmt_hash_or_noop": (_INT, [_VP, u64p, _SZ, _SZ, u64p]),

@@ -6,7 +6,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "libpmt.so")
 SOURCES = [os.path.join(HERE, "csrc", "pmt_api.cu")]
 DEPS = SOURCES + [os.path.join(HERE, "csrc", f) for f in
-                  ("goldilocks.cuh", "poseidon.cuh", "poseidon_quad.cuh", "poseidon_constants.cuh", "poseidon_freq.cuh",
+                  ("goldilocks.cuh", "poseidon.cuh", "poseidon_coop.cuh", "poseidon_constants.cuh", "poseidon_freq.cuh",
                    "poseidon_freq_constants.cuh", "merkle_kernels.cuh")] + [
     os.path.join(HERE, "..", "include", "pmt.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",

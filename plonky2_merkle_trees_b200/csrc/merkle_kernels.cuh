@@ -12,78 +12,12 @@
 // never re-read by the level that produced them, so HBM traffic is the algorithmic 96 B per two_to_one.
 #pragma once
 #include "poseidon.cuh"
-#include "poseidon_quad.cuh"
+#include "poseidon_coop.cuh"
 
 namespace pmt {
 
 using poseidon::WIDTH;
-
-// the production permutation (see DESIGN.md "Permutation variants" for the measurements behind this choice).
-// PMT_PERM selects the form for A/B runs (tools/ab_level.cu): 0 = permute_fast (sparse partial rounds), 1 = permute_fused,
-// 2 = permute_rounds (30 x S-box + DFMA MDS), 3 = permute_paired (partial rounds in pairs; round-1 production until the
-// frequency form), 4 = permute_paired_freq (3 with the MDS layers as frequency-domain convolutions, poseidon_freq.cuh;
-// production: 1.55 against 1.29 G permutations/s, profiles/ab_freq_r1.jsonl).
-#ifndef PMT_PERM
-#define PMT_PERM 4
-#endif
-#ifndef PMT_SBOX_FMA_MASK
-#define PMT_SBOX_FMA_MASK 0
-#endif
-#ifndef PMT_PART_FMA_MASK
-#define PMT_PART_FMA_MASK 0
-#endif
-#ifndef PMT_MULADD_ALU
-#define PMT_MULADD_ALU 1
-#endif
-#ifndef PMT_DOT_ALU
-#define PMT_DOT_ALU 0
-#endif
-#ifndef PMT_CVT_I2F
-#define PMT_CVT_I2F 1   // I2F.F64.U32 (conversion pipe) instead of the 2^52 magic-number subtraction (fma pipe)
-#endif
-#ifndef PMT_COMBINE_ALU
-#define PMT_COMBINE_ALU 1
-#endif
-#ifndef PMT_COLUMN
-#define PMT_COLUMN 0
-#endif
-#ifndef PMT_PIPE
-#define PMT_PIPE 0
-#endif
-#ifndef PMT_PPIPE
-#define PMT_PPIPE 0
-#endif
-#ifndef PMT_FQ_COMBINE
-#define PMT_FQ_COMBINE 0   // recombination of the fp64 sums: 0 = ALU only, 1 = IMAD.WIDE folds, 2 = IMAD.WIDE in full layers only, 3 = in pairs only
-#endif
-#ifndef PMT_FQ_SPLIT
-#define PMT_FQ_SPLIT 0   // 1: fence the high halves behind the low halves (measured slower: 1.51 against 1.55)
-#endif
-#ifndef PMT_COMPRESS_SPECIALISED
-#define PMT_COMPRESS_SPECIALISED 0
-#endif
-template <bool CAP_ZERO, bool OUT4>
-__device__ __forceinline__ void permute_impl(uint64_t (&s)[WIDTH]) {
-#if PMT_PERM == 0
-  poseidon::permute_fast<true, true, 2, CAP_ZERO, OUT4>(s);
-#elif PMT_PERM == 3
-  poseidon::permute_paired<PMT_SBOX_FMA_MASK, PMT_PART_FMA_MASK, PMT_COLUMN != 0, PMT_CVT_I2F != 0, PMT_COMBINE_ALU != 0, CAP_ZERO,
-                           OUT4>(s);
-#elif PMT_PERM == 4
-  poseidon::permute_paired_freq<PMT_SBOX_FMA_MASK, PMT_PART_FMA_MASK, PMT_CVT_I2F != 0, CAP_ZERO, OUT4, PMT_FQ_SPLIT, PMT_FQ_COMBINE>(s);
-#elif PMT_PERM == 2
-  poseidon::permute_rounds<PMT_SBOX_FMA_MASK, PMT_PART_FMA_MASK, PMT_COLUMN != 0, PMT_CVT_I2F != 0, PMT_COMBINE_ALU != 0, CAP_ZERO,
-                           OUT4>(s);
-#else
-  poseidon::permute_fused<PMT_SBOX_FMA_MASK, PMT_PART_FMA_MASK, PMT_MULADD_ALU != 0, PMT_DOT_ALU != 0, PMT_CVT_I2F != 0,
-                          PMT_COMBINE_ALU != 0, CAP_ZERO, OUT4, PMT_PIPE, PMT_PPIPE>(s);
-#endif
-}
-__device__ __forceinline__ void permute(uint64_t (&s)[WIDTH]) { permute_impl<false, false>(s); }
-// two_to_one: zero capacity lanes on entry, only the digest lanes are read afterwards
-__device__ __forceinline__ void permute_compress(uint64_t (&s)[WIDTH]) {
-  permute_impl<PMT_COMPRESS_SPECIALISED != 0, PMT_COMPRESS_SPECIALISED != 0>(s);
-}
+using poseidon::permute;   // one state per thread (poseidon.cuh); the four-threads-per-state form is poseidon::coop
 
 struct Digest { uint64_t v[4]; };
 
@@ -101,7 +35,7 @@ __device__ __forceinline__ void store_digest(uint64_t* __restrict__ p, const Dig
 // [UPSTREAM hash/hashing.rs compress]: perm(l || r || 0^4)[0..4)
 __device__ __forceinline__ Digest two_to_one(const Digest& l, const Digest& r) {
   uint64_t s[WIDTH] = {l.v[0], l.v[1], l.v[2], l.v[3], r.v[0], r.v[1], r.v[2], r.v[3], 0, 0, 0, 0};
-  permute_compress(s);
+  permute(s);
   Digest d;
 #pragma unroll
   for (int i = 0; i < 4; i++) d.v[i] = gl::canonical(s[i]);
@@ -151,6 +85,7 @@ struct LevelMajor {
   __device__ __forceinline__ void children(int l, size_t k, const uint64_t*& a, const uint64_t*& b) const {
     a = at(l - 1, 2 * k); b = a + 4;
   }
+  __device__ __forceinline__ LevelMajor for_set(unsigned) const { return *this; }
 };
 
 struct Plonky2 {
@@ -168,6 +103,7 @@ struct Plonky2 {
   __device__ __forceinline__ void children(int l, size_t k, const uint64_t*& a, const uint64_t*& b) const {
     a = at(l - 1, 2 * k); b = a + 4;                      // siblings are adjacent in this layout
   }
+  __device__ __forceinline__ Plonky2 for_set(unsigned) const { return *this; }
 };
 
 struct Mmr {
@@ -182,6 +118,51 @@ struct Mmr {
     a = elements + 4 * (p - ((size_t)1 << l));
     b = elements + 4 * (p - 1);
   }
+  __device__ __forceinline__ Mmr for_set(unsigned) const { return *this; }
+};
+
+// What an append to an MMR of n0 leaves touches, compact: the n_peaks = popcount(n0) old peaks (largest mountain first),
+// then the new elements (post-order positions s0 = mmr_size(n0) and up).  A new node's right child is always new; its
+// left child is new or the old peak of that height (bit l - 1 of n0), whose slot is the number of set bits above it.
+// Device memory for an append of m leaves is O(m + log n0), like the reference's add_leaf (:89-120), not O(n0).
+struct MmrAppend {
+  uint64_t* buf;
+  size_t n0, s0;
+  uint32_t n_peaks;
+  __device__ __forceinline__ uint64_t* slot(size_t p) const { return buf + 4 * ((size_t)n_peaks + p - s0); }
+  __device__ __forceinline__ uint64_t* at(int l, size_t k) const { return slot(Mmr::pos(l, k)); }
+  __device__ __forceinline__ void children(int l, size_t k, const uint64_t*& a, const uint64_t*& b) const {
+    const size_t p = Mmr::pos(l, k), pa = p - ((size_t)1 << l);
+    a = pa >= s0 ? slot(pa) : buf + 4 * (size_t)__popcll((unsigned long long)(n0 >> l));
+    b = slot(p - 1);
+  }
+  __device__ __forceinline__ MmrAppend for_set(unsigned) const { return *this; }
+};
+
+// The levels above a gathered array of subtree roots (the finish of a subtree-sharded tree): level 0 = the
+// n_roots roots (read only), levels 1 .. log2(n_roots) level-major in `out` (n_roots/2, n_roots/4, ... digests).
+// A batch of independent sets (blockIdx.y; the rounds of a sharded MMR) lies roots_stride / out_stride digests apart.
+struct TopRoots {
+  const uint64_t* roots;
+  uint64_t* out;
+  size_t n_roots, roots_stride, out_stride;
+  __device__ __forceinline__ uint64_t* at(int l, size_t k) const {
+    if (l == 0) return const_cast<uint64_t*>(roots) + 4 * k;
+    return out + 4 * (n_roots - (n_roots >> (l - 1)) + k);
+  }
+  __device__ __forceinline__ void children(int l, size_t k, const uint64_t*& a, const uint64_t*& b) const {
+    a = at(l - 1, 2 * k); b = a + 4;
+  }
+  __device__ __forceinline__ TopRoots for_set(unsigned set) const {
+    return TopRoots{roots + 4 * roots_stride * set, out + 4 * out_stride * set, n_roots, roots_stride, out_stride};
+  }
+};
+
+// a plain array of digests (outputs of the Hasher batch calls): node (0, k) at out + 4 k
+struct Flat {
+  uint64_t* out;
+  __device__ __forceinline__ uint64_t* at(int, size_t k) const { return out + 4 * k; }
+  __device__ __forceinline__ Flat for_set(unsigned) const { return *this; }
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -259,213 +240,145 @@ __global__ void __launch_bounds__(BLOCK, PMT_MINB) k_leaves_columns(Layout lay, 
   }
 }
 
-// one level: digest(l, k) = two_to_one(children) for k in [k0, k0 + count)
-// PMT_QUAD = 0 (production): one node per thread (poseidon.cuh permute_paired).
-// PMT_QUAD = 1: 32 nodes per warp in the quad layout of poseidon_quad.cuh, MDS layers on the fp64 tensor pipe (DMMA).
-// Thread (q, j) loads / stores element j of the digests of nodes 8 mb + q: the four threads of a quad cover one 32-byte
-// digest.  Bit-exact and 30 % fewer instructions, but not faster on B200 (1.26 vs 1.29 G permutations/s):
-// both forms are bound by the S-boxes' integer work, which the MDS engine does not change.
-#ifndef PMT_QUAD
-#define PMT_QUAD 0
-#endif
-#ifndef PMT_QUAD_SBOX_FMA_MASK
-#define PMT_QUAD_SBOX_FMA_MASK 0
-#endif
-#ifndef PMT_QUAD_PART_FMA_MASK
-#define PMT_QUAD_PART_FMA_MASK 0
-#endif
-#ifndef PMT_QUAD_COMBINE_ALU
-#define PMT_QUAD_COMBINE_ALU 1
-#endif
-__device__ __forceinline__ void permute_quad(uint64_t (&e)[4][3], const poseidon::QuadTables& T, const poseidon::QuadFrags& f,
-                                             unsigned lane) {
-  poseidon::permute_quad<PMT_QUAD_SBOX_FMA_MASK, PMT_QUAD_PART_FMA_MASK, PMT_QUAD_COMBINE_ALU != 0>(e, T, f, lane);
-}
-
+// one level: digest(l, k) = two_to_one(children) for k in [k0, k0 + count), one node per thread
 template <class Layout>
 __global__ void __launch_bounds__(BLOCK, PMT_MINB) k_level(Layout lay, int l, size_t k0, size_t count) {
-#if PMT_QUAD
-  __shared__ poseidon::QuadTables T;
-  poseidon::quad_stage_tables(T);
-  const unsigned lane = threadIdx.x & 31, q = lane >> 2, j = lane & 3;
-  poseidon::QuadFrags f;
-  poseidon::quad_load_frags(f, q, j);
-#if PMT_QUAD_FRAGS_SMEM
-  poseidon::quad_publish_frags(T, f, lane);
-#endif
-  for (size_t base = (size_t)blockIdx.x * BLOCK; base < count; base += (size_t)gridDim.x * BLOCK) {
-    const size_t wbase = base + (threadIdx.x & ~31u);
-    if (wbase >= count) continue;                       // warp-uniform
-    uint64_t e[4][3];
-#pragma unroll
-    for (int mb = 0; mb < 4; mb++) {
-      size_t i = wbase + 8 * mb + q;
-      if (i >= count) i = count - 1;                    // ragged tail: recompute the last node, store nothing
-      const uint64_t *a, *b;
-      lay.children(l, k0 + i, a, b);
-      e[mb][0] = a[j]; e[mb][1] = b[j]; e[mb][2] = 0;
-    }
-    permute_quad(e, T, f, lane);
-#pragma unroll
-    for (int mb = 0; mb < 4; mb++) {
-      const size_t i = wbase + 8 * mb + q;
-      if (i < count) lay.at(l, k0 + i)[j] = gl::canonical(e[mb][0]);
-    }
-  }
-#else
   for (size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x; i < count; i += (size_t)gridDim.x * BLOCK) {
     const uint64_t *a, *b;
     lay.children(l, k0 + i, a, b);
     store_digest(lay.at(l, k0 + i), two_to_one(load_digest(a), load_digest(b)));
   }
-#endif
 }
 
-constexpr int TOP_BLOCK = 256;  // 256 x ~100 registers fits one SM's register file without spilling the state
+// ---------------------------------------------------------------------------------------------------------------
+// cooperative kernels (several threads per permutation, poseidon_coop.cuh) for everything that is a chain of dependent
+// permutations: levels too small to fill the GPU with one thread per node, proof paths, sponges over few rows.
+// Two forms (Form = Quad: 4 threads per state, throughput; Wide: 16 lanes per state, latency), one kernel body.
+// Block = 256 threads = 8 warps = 64 Quad states or 16 Wide states in flight.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int COOP_BLOCK = 256;
+constexpr int COOP_WARPS = COOP_BLOCK / 32;
+constexpr int COOP_NODES = COOP_BLOCK / 4;     // Quad states a block holds at once
+constexpr int WIDE_NODES = COOP_BLOCK / 16;    // Wide states a block holds at once
+constexpr int COOP_LOCAL_LEVELS = 7;           // 64, 32, 16, 8, 4, 2, 1 nodes: the subtree a block reduces on its own
+using CoopShared = poseidon::coop::Shared<COOP_WARPS>;
+using poseidon::coop::Quad;
+using poseidon::coop::Wide;
 
-// fused upper levels, ONE block: levels l0 .. l1 (inclusive); level l has count0 >> (l - l0) nodes starting at node 0.
-// Children written by this block in the previous iteration are read back through L2 after a block barrier.
-template <class Layout>
-__global__ void __launch_bounds__(TOP_BLOCK) k_top(Layout lay, int l0, int l1, size_t count0) {
-  size_t count = count0;
-  for (int l = l0; l <= l1; l++, count >>= 1) {
-    for (size_t i = threadIdx.x; i < count; i += blockDim.x) {
-      const uint64_t *a, *b;
-      lay.children(l, i, a, b);
-      store_digest(lay.at(l, i), two_to_one(load_digest(a), load_digest(b)));
-    }
-    __threadfence_block();
-    __syncthreads();
+// one two_to_one by one group of threads; groups without a node (`active` false) still run the permutation's warp-wide
+// operations.  Children are read with ld.global.cg: they may have been written by another SM earlier in the same launch.
+template <class Form, class Layout>
+__device__ __forceinline__ void coop_node(const Layout& lay, int l, size_t k, bool active, const Form& t, const CoopShared& sh) {
+  uint64_t e[Form::ELEMS];
+  const uint64_t *a = nullptr, *b = nullptr;
+  if (active) lay.children(l, k, a, b);
+#pragma unroll
+  for (int i = 0; i < Form::ELEMS; i++) {
+    const unsigned idx = t.elem(i);
+    e[i] = (active && idx < 8) ? __ldcg(idx < 4 ? a + idx : b + (idx - 4)) : 0ull;
+  }
+  t.permute(e, sh);
+#pragma unroll
+  for (int i = 0; i < Form::ELEMS; i++) {
+    const unsigned idx = t.elem(i);
+    if (active && idx < 4) lay.at(l, k)[idx] = gl::canonical(e[i]);
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// cooperative (16 lanes per permutation) kernels for levels too small to fill the GPU with one thread per node
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int COOP_BLOCK = 256;          // 16 permutations in flight per block
-constexpr int COOP_GROUPS = COOP_BLOCK / 16;
+// the nodes k_first + [0, nb) of level l by one block: in passes of 64 by quads, or -- when there are at most 16, where
+// only latency counts -- in one pass by 16-lane groups.  Warps all of whose groups have no node skip the permutation
+// (its exchanges never cross a warp).  nb is the same for all threads of the block.
+template <class Layout>
+__device__ __forceinline__ void coop_level(const Layout& lay, int l, size_t k_first, size_t nb, const Quad& q, const Wide& w,
+                                           const CoopShared& sh) {
+  const unsigned warp = threadIdx.x >> 5;
+  if (nb > (size_t)WIDE_NODES) {
+    for (size_t base = 0; base < nb; base += COOP_NODES)
+      if (base + warp * 8 < nb) coop_node(lay, l, k_first + base + q.state(), base + q.state() < nb, q, sh);
+  } else if (warp * 2 < nb) {
+    coop_node(lay, l, k_first + w.state(), w.state() < nb, w, sh);
+  }
+}
 
-__device__ __forceinline__ void coop_stage_constants(uint64_t* rc_smem) {
-  for (int i = threadIdx.x; i < WIDTH * (PMT_ROUNDS + 1); i += blockDim.x) rc_smem[i] = PMT_RC[i];
+// The latency-bound part of a tree in ONE launch.  Level l0 has the nodes k0 + [0, count0); block b owns the 64 nodes
+// k0 + [64 b, 64 b + 64) of it and every ancestor of theirs for `local_levels` levels (64, 32, ..., 1 nodes; needs k0 and
+// count0 to be multiples of 2^(local_levels - 1)), a block barrier between levels: a block only reads children it wrote
+// itself, every level is still stored once (proofs need it).  Then, for a perfect subtree (count0 a power of two, k0 a
+// multiple of it), the LAST block to finish -- a ticket taken after a device-wide fence -- continues with the
+// `top_levels` levels above the block roots (count0 >> local_levels nodes, halving), so the whole tail of the tree is one
+// launch instead of three and there is no grid-wide barrier.  local_levels = 1, top_levels = 0: a plain level.
+template <class Layout>
+__global__ void __launch_bounds__(COOP_BLOCK) k_tree_coop(Layout lay_in, int l0, size_t k0, size_t count0, int local_levels,
+                                                           int top_levels, unsigned* __restrict__ ticket) {
+  __shared__ CoopShared sh;
+  __shared__ bool is_last;
+  const Layout lay = lay_in.for_set(blockIdx.y);
+  const Quad q = Quad::make(sh);
+  const Wide w = Wide::make(sh);
+  poseidon::coop::stage(sh);
+  for (int j = 0; j < local_levels; j++) {
+    const size_t per = (size_t)COOP_NODES >> j, cnt = count0 >> j;
+    const size_t base = ((size_t)blockIdx.x * COOP_NODES) >> j;
+    const size_t nb = base >= cnt ? 0 : (cnt - base < per ? cnt - base : per);
+    coop_level(lay, l0 + j, (k0 >> j) + base, nb, q, w, sh);
+    if (j + 1 < local_levels) { __threadfence_block(); __syncthreads(); }
+  }
+  if (top_levels <= 0) return;
+  // ticket: the block roots must be visible device-wide before the ticket is taken
+  __threadfence();
   __syncthreads();
-}
-
-// one two_to_one by a 16-lane group; `active` = this group has a node (inactive groups still run the shuffles)
-template <class Layout>
-__device__ __forceinline__ void coop_node(const Layout& lay, int l, size_t k, bool active, const uint64_t* rc_smem,
-                                          unsigned g, unsigned base_lane) {
-  uint64_t v = 0;
-  if (active && g < 8) {
-    const uint64_t *a, *b;
-    lay.children(l, k, a, b);
-    v = g < 4 ? a[g] : b[g - 4];
+  if (threadIdx.x == 0) {
+    const unsigned got = atomicAdd(ticket + blockIdx.y, 1u);
+    is_last = got == gridDim.x - 1;
+    if (is_last) ticket[blockIdx.y] = 0;     // ready for the next launch on this stream
   }
-  v = poseidon::permute_coop(v, rc_smem, g, base_lane);
-  if (active && g < 4) lay.at(l, k)[g] = gl::canonical(v);
-}
-
-template <class Layout>
-__global__ void __launch_bounds__(COOP_BLOCK) k_level_coop(Layout lay, int l, size_t k0, size_t count) {
-  __shared__ uint64_t rc_smem[WIDTH * (PMT_ROUNDS + 1)];
-  coop_stage_constants(rc_smem);
-  const unsigned g = threadIdx.x & 15, base_lane = threadIdx.x & 16;
-  const size_t group = (size_t)blockIdx.x * COOP_GROUPS + (threadIdx.x >> 4);
-  const size_t stride = (size_t)gridDim.x * COOP_GROUPS;
-  // trip count is uniform across the block so every warp executes the same shuffles
-  for (size_t base = 0; base < count; base += stride) {
-    const size_t i = base + group;
-    coop_node(lay, l, k0 + i, i < count, rc_smem, g, base_lane);
-  }
-}
-
-// fused upper levels in ONE block of 256 threads (16 groups): levels l0 .. l1, level l has count0 >> (l - l0) nodes.
-// Warps whose two groups both have no node skip the permutation (shuffles never cross a warp).
-template <class Layout>
-__global__ void __launch_bounds__(COOP_BLOCK) k_top_coop(Layout lay, int l0, int l1, size_t count0) {
-  __shared__ uint64_t rc_smem[WIDTH * (PMT_ROUNDS + 1)];
-  coop_stage_constants(rc_smem);
-  const unsigned g = threadIdx.x & 15, base_lane = threadIdx.x & 16;
-  const size_t group = threadIdx.x >> 4, groups = blockDim.x >> 4;
-  size_t count = count0;
-  for (int l = l0; l <= l1; l++, count >>= 1) {
-    for (size_t base = 0; base < count; base += groups) {
-      const size_t first_of_warp = base + (group & ~(size_t)1);
-      if (first_of_warp < count) coop_node(lay, l, base + group, base + group < count, rc_smem, g, base_lane);
-    }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  size_t cnt = count0 >> local_levels;
+  for (int j = local_levels; j < local_levels + top_levels; j++, cnt >>= 1) {
+    coop_level(lay, l0 + j, k0 >> j, cnt, q, w, sh);
     __threadfence_block();
     __syncthreads();
   }
 }
 
-// fused subtree blocks for the latency-bound middle of a tree (levels of <= 2^13 nodes): block b owns the 16 nodes
-// k0 + [16 b, 16 b + 16) of level l0 (k0 a multiple of 16) and every ancestor of theirs up to `levels` levels (16, 8, 4, 2, 1 nodes), one
-// 16-lane group per node, shuffles inside the permutation, a block barrier between levels.  A block only ever reads
-// children it wrote itself (through L1/L2; every level has to be stored anyway, proofs need it), so the blocks are
-// independent and one launch replaces up to five.  Warps whose two groups both have no node skip the permutation.
-template <class Layout>
-__global__ void __launch_bounds__(COOP_BLOCK) k_subtree_coop(Layout lay, int l0, int levels, size_t k0) {
-  __shared__ uint64_t rc_smem[WIDTH * (PMT_ROUNDS + 1)];
-  coop_stage_constants(rc_smem);
-  const unsigned g = threadIdx.x & 15, base_lane = threadIdx.x & 16;
-  const size_t group = threadIdx.x >> 4;
-  size_t per = COOP_GROUPS;                                  // nodes of this block at the current level
-  for (int j = 0; j < levels; j++, per >>= 1) {
-    if ((group & ~(size_t)1) < per) coop_node(lay, l0 + j, (k0 >> j) + (size_t)blockIdx.x * per + group, group < per, rc_smem, g, base_lane);
-    __threadfence_block();
-    __syncthreads();
-  }
-}
-
-// multi-GPU finish: the levels above n_roots gathered subtree roots, ONE block, 16 lanes per permutation (the levels are
-// sequential and tiny: G - 1 permutations for G ranks).  out is level-major: n_roots/2, n_roots/4, ..., n_cap digests.
-// blockIdx.x = which set of roots (a batch of independent finishes: the rounds of a sharded MMR); sets are n_roots digests
-// apart in `roots` and n_roots - n_cap digests apart in `out`.
-__global__ void __launch_bounds__(COOP_BLOCK) k_top_roots_coop(const uint64_t* __restrict__ roots, size_t n_roots, size_t n_cap,
-                                                               uint64_t* __restrict__ out) {
-  __shared__ uint64_t rc_smem[WIDTH * (PMT_ROUNDS + 1)];
-  coop_stage_constants(rc_smem);
-  roots += 4 * n_roots * blockIdx.x;
-  out += 4 * (n_roots - n_cap) * blockIdx.x;
-  const unsigned g = threadIdx.x & 15, base_lane = threadIdx.x & 16;
-  const size_t group = threadIdx.x >> 4, groups = blockDim.x >> 4;
-  const uint64_t* cur = roots;
-  uint64_t* dst = out;
-  for (size_t m = n_roots / 2; m >= n_cap && m >= 1; m >>= 1) {
-    for (size_t base = 0; base < m; base += groups) {
-      const size_t first_of_warp = base + (group & ~(size_t)1);
-      if (first_of_warp < m) {                       // warp-uniform: both groups of a warp run the shuffles
-        const size_t k = base + group;
-        const bool active = k < m;
-        uint64_t v = 0;
-        if (active && g < 8) v = cur[8 * k + g];     // children 2k and 2k + 1 are adjacent
-        v = poseidon::permute_coop(v, rc_smem, g, base_lane);
-        if (active && g < 4) dst[4 * k + g] = gl::canonical(v);
+// level 0 by groups of threads: digest(0, k0 + i) = hash_or_noop(row i) (NOOP_RULE) or hash_no_pad(row i).  The sponge's
+// permutations are sequential, so for few rows (a small FRI commitment, one bag of peaks) the cooperative forms cut the
+// latency 3 - 6x; the owner of element idx < 8 reads felt off + idx of every 8-felt block.  blockDim.x / Form::LANES rows
+// per block and pass.
+template <class Layout, bool NOOP_RULE, class Form>
+__global__ void __launch_bounds__(COOP_BLOCK) k_rows_coop(Layout lay, const uint64_t* __restrict__ rows, size_t w, size_t k0, size_t count) {
+  __shared__ CoopShared sh;
+  const Form t = Form::make(sh);
+  poseidon::coop::stage(sh);
+  const size_t per_block = blockDim.x / Form::LANES, warp_first = (threadIdx.x >> 5) * (32 / Form::LANES);
+  for (size_t base = (size_t)blockIdx.x * per_block; base < count; base += (size_t)gridDim.x * per_block) {
+    if (base + warp_first >= count) continue;                  // warp-uniform
+    const size_t i = base + t.state();
+    const bool active = i < count;
+    const uint64_t* row = rows + (active ? i : 0) * w;
+    uint64_t e[Form::ELEMS];
+#pragma unroll
+    for (int a = 0; a < Form::ELEMS; a++) e[a] = 0;
+    if (NOOP_RULE && w <= 4) {
+#pragma unroll
+      for (int a = 0; a < Form::ELEMS; a++)
+        if (active && t.elem(a) < w) e[a] = row[t.elem(a)];
+    } else {
+      for (size_t off = 0; off < w; off += 8) {                // overwrite mode: lanes past the row's end keep their state
+#pragma unroll
+        for (int a = 0; a < Form::ELEMS; a++) {
+          const unsigned idx = t.elem(a);
+          if (active && idx < 8 && off + idx < w) e[a] = row[off + idx];
+        }
+        t.permute(e, sh);
       }
     }
-    __threadfence_block();
-    __syncthreads();
-    cur = dst;
-    dst += 4 * m;
-    if (m == 1) break;
+#pragma unroll
+    for (int a = 0; a < Form::ELEMS; a++)
+      if (active && t.elem(a) < 4) lay.at(0, k0 + i)[t.elem(a)] = gl::canonical(e[a]);
   }
-}
-
-// hash_or_noop of ONE row by one 16-lane group (bagging the peaks): the sponge's permutations are sequential, so the
-// cooperative form cuts the latency by ~10x
-__global__ void __launch_bounds__(32) k_hash_one_coop(const uint64_t* __restrict__ felts, size_t w, uint64_t* __restrict__ out) {
-  __shared__ uint64_t rc_smem[WIDTH * (PMT_ROUNDS + 1)];
-  coop_stage_constants(rc_smem);
-  const unsigned g = threadIdx.x & 15, base_lane = threadIdx.x & 16;
-  if (w <= 4) {
-    if (threadIdx.x < 4) out[threadIdx.x] = threadIdx.x < w ? gl::canonical(felts[threadIdx.x]) : 0ull;
-    return;
-  }
-  uint64_t v = 0;
-  for (size_t off = 0; off < w; off += 8) {
-    if (g < 8 && off + g < w) v = felts[off + g];      // overwrite mode: lanes past the chunk keep their state
-    v = poseidon::permute_coop(v, rc_smem, g, base_lane);
-  }
-  if (threadIdx.x < 4) out[threadIdx.x] = gl::canonical(v);
 }
 
 // generic batches (parity hooks of the Hasher trait)
@@ -477,6 +390,26 @@ __global__ void __launch_bounds__(BLOCK, PMT_MINB) k_permute(const uint64_t* __r
     permute(s);
 #pragma unroll
     for (int j = 0; j < WIDTH; j++) out[i * WIDTH + j] = gl::canonical(s[j]);
+  }
+}
+
+// the same by quads (small batches): all 12 output elements
+__global__ void __launch_bounds__(COOP_BLOCK) k_permute_coop(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, size_t n) {
+  __shared__ CoopShared sh;
+  const Quad t = Quad::make(sh);
+  poseidon::coop::stage(sh);
+  const size_t warp_first = (threadIdx.x >> 5) * 8;
+  for (size_t base = (size_t)blockIdx.x * COOP_NODES; base < n; base += (size_t)gridDim.x * COOP_NODES) {
+    if (base + warp_first >= n) continue;
+    const size_t i = base + t.state();
+    uint64_t e[3] = {0, 0, 0};
+    if (i < n)
+#pragma unroll
+      for (int a = 0; a < 3; a++) e[a] = in[i * WIDTH + t.elem(a)];
+    t.permute(e, sh);
+    if (i < n)
+#pragma unroll
+      for (int a = 0; a < 3; a++) out[i * WIDTH + t.elem(a)] = gl::canonical(e[a]);
   }
 }
 
@@ -495,7 +428,8 @@ __global__ void __launch_bounds__(BLOCK, PMT_MINB) k_hash_rows(const uint64_t* _
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// proofs: pure gathers, one thread per (proof, level)
+// proofs: pure gathers, one thread per (proof, level).  An index the reference would panic on (assert!
+// simple_merkle_tree.rs:56, :77) yields an all-zero proof here; the host-buffer forms and the mirrors reject it first.
 // ---------------------------------------------------------------------------------------------------------------
 // simple_merkle_tree.rs:55-74 get_merkle_proof: level_i[idx_i ^ 1], i = 0 .. log2(n) - 1
 __global__ void k_simple_prove(LevelMajor lay, const uint64_t* __restrict__ idx, size_t n_idx, uint64_t* __restrict__ out) {
@@ -503,22 +437,24 @@ __global__ void k_simple_prove(LevelMajor lay, const uint64_t* __restrict__ idx,
   const int depth = lay.top;
   if (t >= n_idx * (size_t)depth) return;
   const size_t q = t / depth; const int l = (int)(t % depth);
-  const size_t k = (idx[q] >> l) ^ 1;
-  store_digest(out + 4 * t, load_digest(lay.at(l, k)));
+  Digest d = {{0, 0, 0, 0}};
+  if (idx[q] < lay.n) d = load_digest(lay.at(l, (idx[q] >> l) ^ 1));
+  store_digest(out + 4 * t, d);
 }
 
 // [UPSTREAM hash/merkle_tree.rs MerkleTree::prove]
-__global__ void k_plonky2_prove(Plonky2 lay, const uint64_t* __restrict__ idx, size_t n_idx, uint64_t* __restrict__ out) {
+__global__ void k_plonky2_prove(Plonky2 lay, size_t n, const uint64_t* __restrict__ idx, size_t n_idx, uint64_t* __restrict__ out) {
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int depth = lay.sub_levels;
   if (t >= n_idx * (size_t)depth) return;
   const size_t q = t / depth; const int l = (int)(t % depth);
-  const size_t k = (idx[q] >> l) ^ 1;
-  store_digest(out + 4 * t, load_digest(lay.at(l, k)));
+  Digest d = {{0, 0, 0, 0}};
+  if (idx[q] < n) d = load_digest(lay.at(l, (idx[q] >> l) ^ 1));
+  store_digest(out + 4 * t, d);
 }
 
 // merkle_mountain_ranges.rs:147-176 get_subtree_proof_elm, closed form: the leaf's mountain has height H = the bit of
-// n_leaves that covers it; entry j = (node (j, (i >> j) ^ 1), sibling_on_left = bit j of i)
+// n_leaves that covers it; entry j = (node (j, (i >> j) ^ 1), sibling_on_left = bit j of i).  i >= n_leaves: path_len 0.
 __global__ void k_mmr_prove(Mmr lay, size_t n_leaves, const uint64_t* __restrict__ idx, size_t n_idx,
                             uint64_t* __restrict__ sib_out, uint8_t* __restrict__ left_out, uint32_t* __restrict__ len_out) {
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -527,12 +463,13 @@ __global__ void k_mmr_prove(Mmr lay, size_t n_leaves, const uint64_t* __restrict
   const size_t i = idx[q];
   // mountains from the largest: the leaf is in the first mountain whose end exceeds i
   int H = 0; size_t base = 0;
-  for (int b = 63 - __clzll((unsigned long long)n_leaves); b >= 0; b--) {
-    if ((n_leaves >> b) & 1) {
-      if (i < base + ((size_t)1 << b)) { H = b; break; }
-      base += (size_t)1 << b;
+  if (i < n_leaves)
+    for (int b = 63 - __clzll((unsigned long long)n_leaves); b >= 0; b--) {
+      if ((n_leaves >> b) & 1) {
+        if (i < base + ((size_t)1 << b)) { H = b; break; }
+        base += (size_t)1 << b;
+      }
     }
-  }
   if (j == 0) len_out[q] = (uint32_t)H;
   if (j < H) {
     store_digest(sib_out + 4 * t, load_digest(lay.at(j, (i >> j) ^ 1)));
@@ -552,13 +489,8 @@ __global__ void k_mmr_peaks(Mmr lay, size_t n_leaves, uint64_t* __restrict__ out
   }
 }
 
-// merkle_mountain_ranges.rs:122-127 bagging_the_peaks = hash_or_noop(flattened peaks); one thread (<= 32 permutations)
-__global__ void k_hash_one(const uint64_t* __restrict__ felts, size_t w, uint64_t* __restrict__ out) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) store_digest(out, hash_or_noop(felts, w));
-}
-
 // ---------------------------------------------------------------------------------------------------------------
-// verification: one thread folds one path
+// verification, big batches: one thread folds one path
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool digest_eq(const Digest& a, const Digest& b) {
   return a.v[0] == b.v[0] && a.v[1] == b.v[1] && a.v[2] == b.v[2] && a.v[3] == b.v[3];
@@ -569,17 +501,20 @@ __device__ __forceinline__ Digest load_digest_canonical(const uint64_t* __restri
   for (int i = 0; i < 4; i++) d.v[i] = gl::canonical(d.v[i]);
   return d;
 }
+constexpr uint32_t MMR_MAX_PATH = 32;   // entries per proof in the batch layout (an MMR has < 2^30 leaves, :264)
 
 // simple_merkle_tree.rs:91-109 verify_merkle_proof and [UPSTREAM hash/merkle_proofs.rs verify_merkle_proof_to_cap]:
-// fold by index parity, compare with cap[index >> path_len] (cap_height 0 + width 1 = the simple tree's root)
+// fold by index parity, compare with cap[index >> path_len].  idx_mask: the simple tree's verifier only ever looks at
+// the parities of the low path_len index bits (:97-105) and has one root, so its index is masked to those bits; upstream's
+// compares with cap[index >> path_len] and gets all ones.
 __global__ void __launch_bounds__(BLOCK, PMT_MINB) k_verify_to_cap(const uint64_t* __restrict__ rows, size_t w,
-                                                         const uint64_t* __restrict__ idx, size_t n_idx,
+                                                         const uint64_t* __restrict__ idx, size_t idx_mask, size_t n_idx,
                                                          const uint64_t* __restrict__ cap, uint32_t cap_height,
                                                          const uint64_t* __restrict__ proofs, size_t path_len,
                                                          uint8_t* __restrict__ ok) {
   const size_t q = (size_t)blockIdx.x * BLOCK + threadIdx.x;
   if (q >= n_idx) return;
-  size_t index = idx[q];
+  size_t index = idx[q] & idx_mask;
   Digest cur = hash_or_noop(rows + q * w, w);
   for (size_t j = 0; j < path_len; j++) {
     const Digest sib = load_digest(proofs + 4 * (q * path_len + j));
@@ -590,7 +525,7 @@ __global__ void __launch_bounds__(BLOCK, PMT_MINB) k_verify_to_cap(const uint64_
 }
 
 // merkle_mountain_ranges.rs:232-252 MMR_proof::verify: fold by sibling_on_left, membership in peaks (else the
-// reference panics: status -1), re-bag, compare with root
+// reference panics: status -1), re-bag, compare with root.  A path longer than the batch layout holds is -1 as well.
 __global__ void __launch_bounds__(BLOCK, PMT_MINB) k_mmr_verify(const uint64_t* __restrict__ leaves, size_t n_idx,
                                                       const uint64_t* __restrict__ sib, const uint8_t* __restrict__ left,
                                                       const uint32_t* __restrict__ len, const uint64_t* __restrict__ peaks,
@@ -598,97 +533,140 @@ __global__ void __launch_bounds__(BLOCK, PMT_MINB) k_mmr_verify(const uint64_t* 
                                                       const uint64_t* __restrict__ root, int8_t* __restrict__ status) {
   const size_t q = (size_t)blockIdx.x * BLOCK + threadIdx.x;
   if (q >= n_idx) return;
-  Digest cur = hash_or_noop(leaves + q, 1);
   const uint32_t L = len[q];
+  if (L > MMR_MAX_PATH) { status[q] = -1; return; }
+  Digest cur = hash_or_noop(leaves + q, 1);
   for (uint32_t j = 0; j < L; j++) {
-    const Digest s = load_digest(sib + 4 * (q * 32 + j));
-    cur = left[q * 32 + j] ? two_to_one(s, cur) : two_to_one(cur, s);
+    const Digest s = load_digest(sib + 4 * (q * MMR_MAX_PATH + j));
+    cur = left[q * MMR_MAX_PATH + j] ? two_to_one(s, cur) : two_to_one(cur, s);
   }
   bool found = false;
   for (uint32_t k = 0; k < n_peaks; k++) found |= digest_eq(cur, load_digest_canonical(peaks + 4 * k));
   if (!found) { status[q] = -1; return; }
-  // the re-bagged root is identical for every proof of the batch: computed once by k_hash_one into `bagged`
+  // the re-bagged root is identical for every proof of the batch: computed once (k_rows_coop) into `bagged`
   status[q] = digest_eq(load_digest(bagged), load_digest_canonical(root)) ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// cooperative verification (batches too small to fill the GPU with one thread per proof): 16 lanes fold one path, so a
-// proof of length L costs L x 6.6 us instead of L x 38 us.  Lanes 0..3 of a group carry the running digest.
+// cooperative verification (batches too small to fill the GPU with one thread per proof): a group of threads folds one
+// path (Form = Wide for batches where only the latency of the chain counts, Quad for bigger ones).  The owners of
+// elements 0..3 carry the running digest; placing it on the right-hand side of two_to_one moves it to elements 4..7 -- a
+// register move in the quad form (element 4 + j lives in thread j), one shuffle pair in the 16-lane form.
+// blockDim.x / Form::LANES proofs per block.
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool group_all(bool pred, unsigned base_lane) {
-  const unsigned b = __ballot_sync(0xffffffffu, pred), mask = 0xFFFFu << base_lane;
-  return (b & mask) == mask;
+// element idx of the running digest (idx < 4; others 0) as held by the owner of element idx, and the same digest as seen
+// by the owners of elements 4..7 (idx - 4)
+__device__ __forceinline__ uint64_t digest_shifted(const Quad&, const uint64_t (&cur)[3]) { return cur[0]; }   // e[1] <- e[0]
+__device__ __forceinline__ uint64_t digest_shifted(const Wide& t, const uint64_t (&cur)[1]) {                    // lane g <- lane g - 4
+  const unsigned src = t.lane0 + ((t.g - 4) & 15);
+  return gl::pack(__shfl_sync(0xffffffffu, gl::lo32(cur[0]), src), __shfl_sync(0xffffffffu, gl::hi32(cur[0]), src));
 }
-// one fold step: v <- two_to_one(sibling, v) if on_left else two_to_one(v, sibling); `sib` points at the sibling digest
-__device__ __forceinline__ uint64_t coop_fold(uint64_t v, const uint64_t* __restrict__ sib, bool on_left, bool active,
-                                              const uint64_t* rc_smem, unsigned g, unsigned base_lane) {
-  const uint64_t moved = gl::pack(__shfl_sync(0xffffffffu, gl::lo32(v), base_lane + ((g - 4) & 15)),
-                                  __shfl_sync(0xffffffffu, gl::hi32(v), base_lane + ((g - 4) & 15)));   // lane g <- lane g - 4
-  uint64_t st = 0;
-  if (on_left) { if (g < 4) st = active ? sib[g] : 0; else if (g < 8) st = moved; }
-  else         { if (g < 4) st = v; else if (g < 8) st = active ? sib[g - 4] : 0; }
-  return poseidon::permute_coop(st, rc_smem, g, base_lane);
+// one fold step: digest <- two_to_one(sibling, digest) if on_left else two_to_one(digest, sibling).  `sib` = the sibling
+// digest (or nullptr: zeros).  cur holds the digest in the owners of elements 0..3 before and after.
+template <class Form>
+__device__ __forceinline__ void coop_fold(uint64_t (&cur)[Form::ELEMS], const uint64_t* __restrict__ sib, bool on_left, const Form& t,
+                                          const CoopShared& sh) {
+  const uint64_t moved = digest_shifted(t, cur);
+  uint64_t e[Form::ELEMS];
+#pragma unroll
+  for (int a = 0; a < Form::ELEMS; a++) {
+    const unsigned idx = t.elem(a);
+    const uint64_t s_lo = (sib && idx < 4) ? sib[idx] : 0ull, s_hi = (sib && idx >= 4 && idx < 8) ? sib[idx - 4] : 0ull;
+    e[a] = idx < 4 ? (on_left ? s_lo : cur[a]) : idx < 8 ? (on_left ? moved : s_hi) : 0ull;
+  }
+  t.permute(e, sh);
+#pragma unroll
+  for (int a = 0; a < Form::ELEMS; a++) cur[a] = e[a];
 }
 
 // merkle_mountain_ranges.rs:232-252, same contract as k_mmr_verify
+template <class Form>
 __global__ void __launch_bounds__(COOP_BLOCK) k_mmr_verify_coop(const uint64_t* __restrict__ leaves, size_t n_idx,
                                                                 const uint64_t* __restrict__ sib, const uint8_t* __restrict__ left,
                                                                 const uint32_t* __restrict__ len, const uint64_t* __restrict__ peaks,
                                                                 uint32_t n_peaks, const uint64_t* __restrict__ bagged,
                                                                 const uint64_t* __restrict__ root, int8_t* __restrict__ status) {
-  __shared__ uint64_t rc_smem[WIDTH * (PMT_ROUNDS + 1)];
-  coop_stage_constants(rc_smem);
-  const unsigned g = threadIdx.x & 15, base_lane = threadIdx.x & 16;
-  const size_t q = (size_t)blockIdx.x * COOP_GROUPS + (threadIdx.x >> 4);
+  __shared__ CoopShared sh;
+  const Form t = Form::make(sh);
+  poseidon::coop::stage(sh);
+  const size_t q = (size_t)blockIdx.x * (blockDim.x / Form::LANES) + t.state();
   const bool have = q < n_idx;
-  const uint32_t L = have ? len[q] : 0;
-  const uint32_t Lw = max(L, __shfl_xor_sync(0xffffffffu, L, 16));     // both groups of the warp run the same trip count
-  uint64_t v = (have && g == 0) ? gl::canonical(leaves[q]) : 0ull;     // hash_or_noop(&[leaf]) = [leaf, 0, 0, 0]
+  const uint32_t L_raw = have ? len[q] : 0;
+  const bool too_long = L_raw > MMR_MAX_PATH;
+  const uint32_t L = too_long ? 0 : L_raw;
+  const uint32_t Lw = __reduce_max_sync(0xffffffffu, L);              // every group of the warp runs the same trip count
+  uint64_t cur[Form::ELEMS];
+#pragma unroll
+  for (int a = 0; a < Form::ELEMS; a++) cur[a] = (have && t.elem(a) == 0) ? leaves[q] : 0ull;   // hash_or_noop(&[leaf]) = [leaf, 0, 0, 0]
   for (uint32_t j = 0; j < Lw; j++) {
     const bool act = j < L;
-    const bool on_left = act && left[q * 32 + j] != 0;
-    const uint64_t p = coop_fold(v, sib + 4 * (q * 32 + j), on_left, act, rc_smem, g, base_lane);
-    v = act ? p : v;
+    uint64_t nxt[Form::ELEMS];
+#pragma unroll
+    for (int a = 0; a < Form::ELEMS; a++) nxt[a] = cur[a];
+    coop_fold(nxt, act ? sib + 4 * (q * MMR_MAX_PATH + j) : nullptr, act && left[q * MMR_MAX_PATH + j] != 0, t, sh);
+#pragma unroll
+    for (int a = 0; a < Form::ELEMS; a++) cur[a] = act ? nxt[a] : cur[a];
   }
-  v = gl::canonical(v);
   bool found = false;
-  for (uint32_t k = 0; k < n_peaks; k++) found |= group_all(g >= 4 || v == gl::canonical(peaks[4 * k + g]), base_lane);
-  if (have && g == 0) {
-    if (!found) status[q] = -1;
+  for (uint32_t k = 0; k < n_peaks; k++) {
+    bool eq = true;
+#pragma unroll
+    for (int a = 0; a < Form::ELEMS; a++)
+      if (t.elem(a) < 4) eq = eq && gl::canonical(cur[a]) == gl::canonical(peaks[4 * k + t.elem(a)]);
+    found |= t.all(eq);
+  }
+  if (have && t.elem(0) == 0) {
+    if (!found || too_long) status[q] = -1;
     else status[q] = digest_eq(load_digest(bagged), load_digest_canonical(root)) ? 1 : 0;
   }
 }
 
 // simple_merkle_tree.rs:91-109 / [UPSTREAM hash/merkle_proofs.rs verify_merkle_proof_to_cap], same contract as k_verify_to_cap
+template <class Form>
 __global__ void __launch_bounds__(COOP_BLOCK) k_verify_to_cap_coop(const uint64_t* __restrict__ rows, size_t w,
-                                                                   const uint64_t* __restrict__ idx, size_t n_idx,
+                                                                   const uint64_t* __restrict__ idx, size_t idx_mask, size_t n_idx,
                                                                    const uint64_t* __restrict__ cap, uint32_t cap_height,
                                                                    const uint64_t* __restrict__ proofs, size_t path_len,
                                                                    uint8_t* __restrict__ ok) {
-  __shared__ uint64_t rc_smem[WIDTH * (PMT_ROUNDS + 1)];
-  coop_stage_constants(rc_smem);
-  const unsigned g = threadIdx.x & 15, base_lane = threadIdx.x & 16;
-  const size_t q = (size_t)blockIdx.x * COOP_GROUPS + (threadIdx.x >> 4);
+  __shared__ CoopShared sh;
+  const Form t = Form::make(sh);
+  poseidon::coop::stage(sh);
+  const size_t q = (size_t)blockIdx.x * (blockDim.x / Form::LANES) + t.state();
   const bool have = q < n_idx;
   const uint64_t* row = rows + (have ? q : 0) * w;
-  uint64_t v = 0;
+  uint64_t cur[Form::ELEMS];
+#pragma unroll
+  for (int a = 0; a < Form::ELEMS; a++) cur[a] = 0;
   if (w <= 4) {
-    if (have && g < w) v = gl::canonical(row[g]);
+#pragma unroll
+    for (int a = 0; a < Form::ELEMS; a++)
+      if (have && t.elem(a) < w) cur[a] = row[t.elem(a)];
   } else {
     for (size_t off = 0; off < w; off += 8) {            // overwrite-mode sponge; w is uniform, so is the trip count
-      if (have && g < 8 && off + g < w) v = row[off + g];
-      v = poseidon::permute_coop(v, rc_smem, g, base_lane);
+#pragma unroll
+      for (int a = 0; a < Form::ELEMS; a++) {
+        const unsigned e_idx = t.elem(a);
+        if (have && e_idx < 8 && off + e_idx < w) cur[a] = row[off + e_idx];
+      }
+      t.permute(cur, sh);
     }
+#pragma unroll
+    for (int a = 0; a < Form::ELEMS; a++)
+      if (t.elem(a) >= 4) cur[a] = 0;                    // the digest is elements 0..3
   }
-  size_t index = have ? idx[q] : 0;
+  size_t index = have ? idx[q] & idx_mask : 0;
+  const uint64_t* pr = proofs + 4 * (have ? q : 0) * path_len;
   for (size_t j = 0; j < path_len; j++) {
-    v = coop_fold(v, proofs + 4 * ((have ? q : 0) * path_len + j), (index & 1) != 0, have, rc_smem, g, base_lane);
+    coop_fold(cur, have ? pr + 4 * j : nullptr, (index & 1) != 0, t, sh);
     index >>= 1;
   }
-  v = gl::canonical(v);
   const bool in_cap = index < ((size_t)1 << cap_height);
-  const bool eq = group_all(g >= 4 || (in_cap && have && v == gl::canonical(cap[4 * index + g])), base_lane);
-  if (have && g == 0) ok[q] = in_cap && eq;
+  bool eq = in_cap && have;
+#pragma unroll
+  for (int a = 0; a < Form::ELEMS; a++)
+    if (t.elem(a) < 4) eq = eq && gl::canonical(cur[a]) == gl::canonical(cap[4 * index + t.elem(a)]);
+  const bool all_eq = t.all(eq);
+  if (have && t.elem(0) == 0) ok[q] = in_cap && all_eq;
 }
 
 }  // namespace pmt

@@ -35,10 +35,15 @@ struct pmt_ctx {
   std::vector<cudaEvent_t> ev;
   // levels with at most this many nodes run the cooperative kernel (COOP_MAX; PMT_COOP_MAX_LOG2 is a tuning knob)
   size_t coop_max = (size_t)1 << 13;
-  // levels of <= coop_max nodes of a perfect tree run as fused subtree blocks (k_subtree_coop); PMT_FUSE_SUBTREES=0
-  // restores one cooperative launch per level (the A/B knob of tools/bench_configs.py)
+  // the latency-bound levels of a perfect (sub)tree run as ONE launch (k_tree_coop: block-local subtrees, then the last
+  // block to finish takes the levels above); PMT_FUSE_SUBTREES=0 restores one cooperative launch per level (A/B knob)
   bool fuse_subtrees = true;
+  // tickets of k_tree_coop: a ring of zero-initialised device counters, one per launch in flight (the last block of a
+  // launch resets its counter); rotating them keeps launches that overlap on different streams apart
+  unsigned* tickets = nullptr;
+  unsigned ticket_next = 0;
 };
+constexpr unsigned TICKET_RING = 256;
 
 static inline void prof_begin(pmt_ctx* c, const char* name, double units) {
   if (!c->profiling) return;
@@ -135,57 +140,75 @@ int arena_get(pmt_ctx* c, int slot, size_t bytes, void** out) {
 // cooperative one; per permutation the cooperative form issues 2.4x more instructions, so it only wins while the level
 // is latency-bound: <= 2^13 nodes.
 constexpr size_t COOP_MAX = (size_t)1 << 13;
-// proof batches up to this size are verified 16 lanes per proof (the GPU holds 148 x 8 x 16 = 18 944 such groups at once;
-// beyond that the thread-per-proof kernel's 2.4x lower instruction count wins)
+// proof batches up to this size are verified by quads (the GPU holds 148 x 3 x 64 = 28 416 such states at once; beyond
+// that the thread-per-proof kernel's lower instruction count wins)
 constexpr size_t COOP_VERIFY_MAX = (size_t)1 << 14;
-constexpr size_t TOP_FUSE = 16;   // levels with <= 16 nodes are fused into one block (k_top_coop)
+// Hasher batches (rows, permutations) up to this size run by quads: latency instead of throughput
+constexpr size_t COOP_ROWS_MAX = (size_t)1 << 12;
 
+// n independent chains of dependent permutations (proof paths, sponge rows) by groups of threads: while one block per SM
+// holds them all only latency counts -- 16-lane groups, 8 per block (one warp per sub-partition) or 16 per block; beyond
+// that quads (4 threads per chain, 64 per block), the throughput form
+struct CoopPlan { bool wide; unsigned threads, blocks; };
+CoopPlan coop_plan(const pmt_ctx* c, size_t n) {
+  const size_t sms = (size_t)c->sms;
+  if (n <= sms * 8) return {true, 128, (unsigned)((n + 7) / 8)};
+  if (n <= sms * WIDE_NODES) return {true, COOP_BLOCK, (unsigned)((n + WIDE_NODES - 1) / WIDE_NODES)};
+  return {false, COOP_BLOCK, (unsigned)((n + COOP_NODES - 1) / COOP_NODES)};
+}
+
+int log2_floor(size_t x) { int l = 0; while (((size_t)2 << l) <= x) l++; return l; }
+int ctz_cap(size_t x, int cap) { int z = 0; while (z < cap && !((x >> z) & 1)) z++; return z; }
+
+unsigned* next_ticket(pmt_ctx* c, unsigned sets) {
+  if (c->ticket_next + sets > TICKET_RING) c->ticket_next = 0;
+  unsigned* t = c->tickets + c->ticket_next;
+  c->ticket_next += sets;
+  return t;
+}
+
+// The cooperative plan for the nodes k0 + [0, count) of level l (count <= coop_max) and up to `room` levels from there:
+// returns how many levels the ONE launch covers.  Block-local subtrees need k0 and count aligned to their size; the
+// ticket phase on top needs a perfect subtree (count a power of two, k0 a multiple of it).
+template <class Layout>
+int launch_coop(pmt_ctx* c, const Layout& lay, int l, int room, size_t k0, size_t count, unsigned sets = 1) {
+  int local = 1, top = 0;
+  if (c->fuse_subtrees && room > 1) {
+    const int align = k0 ? (ctz_cap(k0, 6) < ctz_cap(count, 6) ? ctz_cap(k0, 6) : ctz_cap(count, 6)) : ctz_cap(count, 6);
+    local = align + 1 < room ? align + 1 : room;
+    if (local > COOP_LOCAL_LEVELS) local = COOP_LOCAL_LEVELS;
+    const bool perfect = (count & (count - 1)) == 0 && k0 % count == 0;
+    if (perfect && local == COOP_LOCAL_LEVELS && count > (size_t)COOP_NODES) {
+      const int height = log2_floor(count) + 1;           // levels of the subtree, its root included
+      top = (height < room ? height : room) - local;
+    }
+  }
+  const size_t blocks = (count + COOP_NODES - 1) / COOP_NODES;
+  size_t units = 0;
+  for (int j = 0; j < local + top; j++) units += count >> j;
+  TAG(c, top ? "k_tree_coop" : (local > 1 ? "k_subtree_coop" : "k_level_coop"), units * sets);
+  k_tree_coop<Layout><<<dim3((unsigned)blocks, sets), COOP_BLOCK, 0, c->stream>>>(lay, l, k0, count, local, top,
+                                                                                   top ? next_ticket(c, sets) : nullptr);
+  CHECK_LAUNCH(c);
+  return local + top;
+}
+
+// One tree level of `count` nodes starting at node k0, one thread per node: levels that fill the GPU.
 template <class Layout>
 int launch_level(pmt_ctx* c, const Layout& lay, int l, size_t k0, size_t count) {
   if (count == 0) return PMT_OK;
-  if (count > c->coop_max) {
-    TAG(c, "k_level", count);
-    k_level<Layout><<<grid_for(c, count), BLOCK, 0, c->stream>>>(lay, l, k0, count);
-  } else {
-    size_t blocks = (count + COOP_GROUPS - 1) / COOP_GROUPS;
-    const size_t cap = (size_t)c->sms * 8;
-    if (blocks > cap) blocks = cap;
-    TAG(c, "k_level_coop", count);
-    k_level_coop<Layout><<<(unsigned)blocks, COOP_BLOCK, 0, c->stream>>>(lay, l, k0, count);
-  }
+  TAG(c, "k_level", count);
+  k_level<Layout><<<grid_for(c, count), BLOCK, 0, c->stream>>>(lay, l, k0, count);
   CHECK_LAUNCH(c);
   return PMT_OK;
 }
 
-// levels l0 .. top of a perfect tree whose level l0 has `count` nodes starting at node 0; the last levels
-// (<= TOP_FUSE nodes) are fused into one single-block launch.
-template <class Layout>
-int run_levels(pmt_ctx* c, const Layout& lay, int l0, int top, size_t count) {
-  int l = l0;
-  for (; l <= top && count > TOP_FUSE && (count > c->coop_max || !c->fuse_subtrees); l++, count >>= 1)
-    if (int rc = launch_level(c, lay, l, 0, count)) return rc;
-  // the latency-bound middle (<= coop_max nodes per level): fused subtree blocks, up to five levels per launch
-  while (l <= top && count > TOP_FUSE) {
-    const int levels = top - l + 1 < 5 ? top - l + 1 : 5;
-    size_t units = 0;
-    for (int j = 0; j < levels; j++) units += count >> j;
-    TAG(c, "k_subtree_coop", units);
-    k_subtree_coop<Layout><<<(unsigned)(count / COOP_GROUPS), COOP_BLOCK, 0, c->stream>>>(lay, l, levels, 0);
-    CHECK_LAUNCH(c);
-    l += levels;
-    count >>= levels;
-  }
-  if (l <= top) {
-    TAG(c, "k_top_coop", 2 * count - 1);
-    k_top_coop<Layout><<<1, 256, 0, c->stream>>>(lay, l, top, count);
-    CHECK_LAUNCH(c);
-  }
-  return PMT_OK;
-}
-
 // levels l_first .. l_last over the nodes that the leaves [n0, n1) complete: level l has the nodes k in [n0 >> l, n1 >> l)
-// (a chunk of the pipelined tree build, a batch append to an MMR).  Where such a range is small (<= coop_max nodes) and
-// aligned to 16 nodes it runs as fused subtree blocks, five levels per launch; otherwise one launch per level.
+// (a whole tree, a chunk of the pipelined tree build, a batch append to an MMR).  Big levels: one thread per node, one
+// launch per level (the level has to be written anyway -- proofs need it -- and re-reading it costs 1/50 of the time its
+// permutations take).  Levels that cannot fill the GPU that way (<= coop_max nodes) are latency-bound (a lone warp needs
+// 38 us per thread-per-state permutation, ~6 us per cooperative one): cooperative launches, fused as far as the range's
+// alignment allows -- for a perfect subtree all the way to its root in one launch.
 template <class Layout>
 int launch_level_span(pmt_ctx* c, const Layout& lay, int l_first, int l_last, size_t n0, size_t n1) {
   for (int l = l_first; l <= l_last;) {
@@ -193,30 +216,77 @@ int launch_level_span(pmt_ctx* c, const Layout& lay, int l_first, int l_last, si
     if (k1 == 0) break;
     if (k1 <= k0) { l++; continue; }
     const size_t count = k1 - k0;
-    const int room = l_last - l + 1;
-    if (c->fuse_subtrees && room >= 2 && count > TOP_FUSE && count <= c->coop_max && k0 % COOP_GROUPS == 0 && count % COOP_GROUPS == 0) {
-      const int levels = room < 5 ? room : 5;
-      size_t units = 0;
-      for (int j = 0; j < levels; j++) units += count >> j;
-      TAG(c, "k_subtree_coop", units);
-      k_subtree_coop<Layout><<<(unsigned)(count / COOP_GROUPS), COOP_BLOCK, 0, c->stream>>>(lay, l, levels, k0);
-      CHECK_LAUNCH(c);
-      l += levels;
+    if (count > c->coop_max) {
+      if (int rc = launch_level(c, lay, l, k0, count)) return rc;
+      l++;
       continue;
     }
-    if (int rc = launch_level(c, lay, l, k0, count)) return rc;
-    l++;
+    const int done = launch_coop(c, lay, l, l_last - l + 1, k0, count);
+    if (done < 0) return done;
+    l += done;
   }
   return PMT_OK;
 }
 
+// levels l0 .. top of a perfect tree whose level l0 has `count` nodes starting at node 0
+template <class Layout>
+int run_levels(pmt_ctx* c, const Layout& lay, int l0, int top, size_t count) {
+  return launch_level_span(c, lay, l0, top, 0, count << l0);
+}
+
+// level 0: digest(0, k0 + i) = hash_or_noop(row i).  Narrow rows (<= 4 felts) are a canonicalising copy (HBM-bound); wide
+// rows are sponge-hashed, one row per thread when there are enough rows to fill the GPU, else one row per quad (the
+// 17 permutations of a 135-column row are sequential: 0.65 ms per row-per-thread pass, ~0.1 ms by quads).
+template <class Layout>
+int launch_leaves(pmt_ctx* c, const Layout& lay, const uint64_t* d_rows, size_t w, size_t k0, size_t count) {
+  if (count == 0) return PMT_OK;
+  if (w > 4 && count <= c->coop_max) {
+    const CoopPlan p = coop_plan(c, count);
+    TAG(c, "k_rows_coop", count * ((w + 7) / 8));
+    if (p.wide) k_rows_coop<Layout, true, Wide><<<p.blocks, p.threads, 0, c->stream>>>(lay, d_rows, w, k0, count);
+    else k_rows_coop<Layout, true, Quad><<<p.blocks, p.threads, 0, c->stream>>>(lay, d_rows, w, k0, count);
+  } else {
+    TAG(c, "k_leaves", w <= 4 ? 0 : count * ((w + 7) / 8));
+    k_leaves<Layout><<<w <= 4 ? grid_copy(c, count) : grid_for(c, count), BLOCK, 0, c->stream>>>(lay, d_rows, w, k0, count);
+  }
+  CHECK_LAUNCH(c);
+  return PMT_OK;
+}
+
+// Layout = Mmr (the whole post-order array is on the device) or MmrAppend (only the old peaks and the new elements are).
+template <class Layout>
+int mmr_extend_plan(pmt_ctx* c, const Layout& lay, size_t n0, const uint64_t* d_new, size_t m) {
+  int first_level = 1;
+  if ((n0 & 1) == 0 && m / 2 > c->coop_max) {   // every level-1 node has two NEW leaves: copy them and hash in one pass
+    TAG(c, "k_level", m / 2);
+    k_leaves_level1<Layout><<<grid_for(c, m / 2), BLOCK, 0, c->stream>>>(lay, d_new, 1, n0 / 2, m / 2);
+    CHECK_LAUNCH(c);
+    if (m & 1) {                             // the unpaired last leaf
+      TAG(c, "k_leaves", 0);
+      k_leaves<Layout><<<1, BLOCK, 0, c->stream>>>(lay, d_new + (m - 1), 1, n0 + m - 1, 1);
+      CHECK_LAUNCH(c);
+    }
+    first_level = 2;
+  } else {
+    TAG(c, "k_leaves", 0);
+    k_leaves<Layout><<<grid_copy(c, m), BLOCK, 0, c->stream>>>(lay, d_new, 1, n0, m);
+    CHECK_LAUNCH(c);
+  }
+  return launch_level_span(c, lay, first_level, 40, n0, n0 + m);
+}
+
 // work(0 .. n-1), one host thread per index (index 0 on the calling thread), all joined before it returns.  Never throws:
-// an exception inside work(r) becomes rcs[r] = PMT_E_OOM, and if no thread can be had that index runs on the caller.
+// an exception inside work(r) becomes rcs[r] = PMT_E_OOM with a message on ctxs[r], and if no thread can be had that index
+// runs on the caller.
 template <class F>
-void run_per_ctx(std::vector<int>& rcs, F&& work) {
+void run_per_ctx(pmt_ctx* const* ctxs, std::vector<int>& rcs, F&& work) {
   const size_t n = rcs.size();
   auto guarded = [&](size_t r) {
-    try { work(r); } catch (...) { rcs[r] = PMT_E_OOM; }
+    try { work(r); } catch (const std::exception& e) {
+      rcs[r] = fail(ctxs[r], PMT_E_OOM, "worker of ctx %zu threw: %s", r, e.what());
+    } catch (...) {
+      rcs[r] = fail(ctxs[r], PMT_E_OOM, "worker of ctx %zu threw", r);
+    }
   };
   std::vector<std::thread> pool;
   try { pool.reserve(n - 1); } catch (...) {}
@@ -259,6 +329,11 @@ int pmt_init(pmt_ctx** out, int device_id) {
     if (lg >= 4 && lg <= 24) c->coop_max = (size_t)1 << lg;
   }
   if (const char* e3 = getenv("PMT_FUSE_SUBTREES")) c->fuse_subtrees = atoi(e3) != 0;
+  if (cudaMalloc(&c->tickets, TICKET_RING * sizeof(unsigned)) != cudaSuccess ||
+      cudaMemset(c->tickets, 0, TICKET_RING * sizeof(unsigned)) != cudaSuccess) {
+    pmt_destroy(c);
+    return PMT_E_OOM;
+  }
   *out = c;
   return PMT_OK;
 }
@@ -269,6 +344,7 @@ void pmt_destroy(pmt_ctx* c) {
   cudaStreamSynchronize(c->stream);
   for (void* p : c->arena) if (p) cudaFree(p);
   for (void* p : c->user_allocs) cudaFree(p);
+  if (c->tickets) cudaFree(c->tickets);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   if (c->copy_in) cudaStreamDestroy(c->copy_in);
   if (c->copy_out) cudaStreamDestroy(c->copy_out);
@@ -360,13 +436,46 @@ int pmt_memcpy_d2h(pmt_ctx* c, void* dst, const void* src, size_t bytes) {
   return PMT_OK;
 }
 
+// ---- page-locked host memory for the pipelined host-buffer entry points ---------------------------------------------------
+int pmt_host_register(pmt_ctx* c, void* ptr, size_t bytes) {
+  if (int rc = bind(c)) return rc;
+  if (!ptr || bytes == 0) return fail(c, PMT_E_INVALID_ARG, "pmt_host_register: null pointer / zero size");
+  CU(c, cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+  return PMT_OK;
+}
+int pmt_host_unregister(pmt_ctx* c, void* ptr) {
+  if (int rc = bind(c)) return rc;
+  if (!ptr) return fail(c, PMT_E_INVALID_ARG, "pmt_host_unregister: null pointer");
+  CU(c, cudaHostUnregister(ptr));
+  return PMT_OK;
+}
+int pmt_host_alloc(pmt_ctx* c, size_t bytes, void** out) {
+  if (int rc = bind(c)) return rc;
+  if (!out) return fail(c, PMT_E_INVALID_ARG, "pmt_host_alloc: null out");
+  void* p = nullptr;
+  CU(c, cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable));
+  *out = p;
+  return PMT_OK;
+}
+int pmt_host_free(pmt_ctx* c, void* ptr) {
+  if (int rc = bind(c)) return rc;
+  if (!ptr) return PMT_OK;
+  CU(c, cudaFreeHost(ptr));
+  return PMT_OK;
+}
+
 // ---- device-pointer entry points ---------------------------------------------------------------------------------------
 int pmt_permute_dev(pmt_ctx* c, const uint64_t* d_in, size_t n, uint64_t* d_out) {
   if (int rc = bind(c)) return rc;
   if (n == 0) return PMT_OK;
   if (!d_in || !d_out) return fail(c, PMT_E_INVALID_ARG, "pmt_permute: null pointer");
-  TAG(c, "k_permute", n);
-  k_permute<<<grid_for(c, n), BLOCK, 0, c->stream>>>(d_in, d_out, n);
+  if (n <= COOP_ROWS_MAX) {
+    TAG(c, "k_permute_coop", n);
+    k_permute_coop<<<(unsigned)((n + COOP_NODES - 1) / COOP_NODES), COOP_BLOCK, 0, c->stream>>>(d_in, d_out, n);
+  } else {
+    TAG(c, "k_permute", n);
+    k_permute<<<grid_for(c, n), BLOCK, 0, c->stream>>>(d_in, d_out, n);
+  }
   CHECK_LAUNCH(c);
   return PMT_OK;
 }
@@ -385,9 +494,19 @@ int pmt_hash_rows_dev(pmt_ctx* c, const uint64_t* d_rows, size_t n, size_t w, in
   if (int rc = bind(c)) return rc;
   if (n == 0) return PMT_OK;
   if (!d_out || (!d_rows && w)) return fail(c, PMT_E_INVALID_ARG, "pmt_hash_rows: null pointer");
-  TAG(c, "k_hash_rows", w <= 4 && noop_rule ? 0 : n * ((w + 7) / 8));
-  if (noop_rule) k_hash_rows<true><<<grid_for(c, n), BLOCK, 0, c->stream>>>(d_rows, n, w, d_out);
-  else k_hash_rows<false><<<grid_for(c, n), BLOCK, 0, c->stream>>>(d_rows, n, w, d_out);
+  const bool permuted = !(w <= 4 && noop_rule);
+  if (permuted && n <= COOP_ROWS_MAX) {   // few rows: the sponge's sequential permutations by groups of threads
+    const CoopPlan p = coop_plan(c, n);
+    TAG(c, "k_rows_coop", n * ((w + 7) / 8));
+    if (noop_rule && p.wide) k_rows_coop<Flat, true, Wide><<<p.blocks, p.threads, 0, c->stream>>>(Flat{d_out}, d_rows, w, 0, n);
+    else if (noop_rule) k_rows_coop<Flat, true, Quad><<<p.blocks, p.threads, 0, c->stream>>>(Flat{d_out}, d_rows, w, 0, n);
+    else if (p.wide) k_rows_coop<Flat, false, Wide><<<p.blocks, p.threads, 0, c->stream>>>(Flat{d_out}, d_rows, w, 0, n);
+    else k_rows_coop<Flat, false, Quad><<<p.blocks, p.threads, 0, c->stream>>>(Flat{d_out}, d_rows, w, 0, n);
+  } else {
+    TAG(c, "k_hash_rows", permuted ? n * ((w + 7) / 8) : 0);
+    if (noop_rule) k_hash_rows<true><<<grid_for(c, n), BLOCK, 0, c->stream>>>(d_rows, n, w, d_out);
+    else k_hash_rows<false><<<grid_for(c, n), BLOCK, 0, c->stream>>>(d_rows, n, w, d_out);
+  }
   CHECK_LAUNCH(c);
   return PMT_OK;
 }
@@ -399,7 +518,7 @@ int pmt_simple_tree_build_dev(pmt_ctx* c, const uint64_t* d_leaves, size_t n, ui
   if (lg < 1) return fail(c, PMT_E_INVALID_ARG, "simple tree: needs at least 2 leaves (simple_merkle_tree.rs:38)");
   if (!d_leaves || !d_levels || !d_root) return fail(c, PMT_E_INVALID_ARG, "simple tree: null pointer");
   LevelMajor lay{d_levels, d_root, n, lg};
-  if (n / 2 > COOP_MAX) {   // big tree: the leaf copy rides along with level 1
+  if (n / 2 > c->coop_max) {   // big tree: the leaf copy rides along with level 1
     TAG(c, "k_level", n / 2);
     k_leaves_level1<LevelMajor><<<grid_for(c, n / 2), BLOCK, 0, c->stream>>>(lay, d_leaves, 1, 0, n / 2);
     CHECK_LAUNCH(c);
@@ -425,30 +544,41 @@ int pmt_simple_tree_prove_dev(pmt_ctx* c, const uint64_t* d_levels, size_t n, co
   return PMT_OK;
 }
 
-int pmt_merkle_verify_dev(pmt_ctx* c, const uint64_t* d_rows, size_t w, const uint64_t* d_idx, size_t n_idx,
-                          const uint64_t* d_cap, uint32_t cap_height, const uint64_t* d_proofs, size_t path_len,
-                          uint8_t* d_ok) {
+// idx_mask: see k_verify_to_cap (all ones for upstream's verifier, the low path_len bits for the simple tree's)
+static int verify_to_cap_dev(pmt_ctx* c, const uint64_t* d_rows, size_t w, const uint64_t* d_idx, size_t idx_mask, size_t n_idx,
+                             const uint64_t* d_cap, uint32_t cap_height, const uint64_t* d_proofs, size_t path_len,
+                             uint8_t* d_ok) {
   if (int rc = bind(c)) return rc;
   if (n_idx == 0) return PMT_OK;
   if (!d_rows || !d_idx || !d_cap || !d_ok || (!d_proofs && path_len)) return fail(c, PMT_E_INVALID_ARG, "verify: null pointer");
   if (w == 0 || cap_height > 40 || path_len > 63) return fail(c, PMT_E_INVALID_ARG, "verify: bad width / cap_height / path_len");
-  if (n_idx <= COOP_VERIFY_MAX) {   // latency-bound batch: 16 lanes per proof
+  if (n_idx <= COOP_VERIFY_MAX) {   // latency-bound batch: a group of threads per proof
+    const CoopPlan p = coop_plan(c, n_idx);
     TAG(c, "k_verify_to_cap_coop", n_idx * (path_len + (w <= 4 ? 0 : (w + 7) / 8)));
-    k_verify_to_cap_coop<<<(unsigned)((n_idx + COOP_GROUPS - 1) / COOP_GROUPS), COOP_BLOCK, 0, c->stream>>>(
-        d_rows, w, d_idx, n_idx, d_cap, cap_height, d_proofs, path_len, d_ok);
+    if (p.wide) k_verify_to_cap_coop<Wide><<<p.blocks, p.threads, 0, c->stream>>>(d_rows, w, d_idx, idx_mask, n_idx, d_cap, cap_height, d_proofs, path_len, d_ok);
+    else k_verify_to_cap_coop<Quad><<<p.blocks, p.threads, 0, c->stream>>>(d_rows, w, d_idx, idx_mask, n_idx, d_cap, cap_height, d_proofs, path_len, d_ok);
   } else {
     TAG(c, "k_verify_to_cap", n_idx * (path_len + (w <= 4 ? 0 : (w + 7) / 8)));
-    k_verify_to_cap<<<(unsigned)((n_idx + BLOCK - 1) / BLOCK), BLOCK, 0, c->stream>>>(d_rows, w, d_idx, n_idx, d_cap, cap_height,
-                                                                                     d_proofs, path_len, d_ok);
+    k_verify_to_cap<<<(unsigned)((n_idx + BLOCK - 1) / BLOCK), BLOCK, 0, c->stream>>>(d_rows, w, d_idx, idx_mask, n_idx, d_cap,
+                                                                                     cap_height, d_proofs, path_len, d_ok);
   }
   CHECK_LAUNCH(c);
   return PMT_OK;
 }
 
+int pmt_merkle_verify_dev(pmt_ctx* c, const uint64_t* d_rows, size_t w, const uint64_t* d_idx, size_t n_idx,
+                          const uint64_t* d_cap, uint32_t cap_height, const uint64_t* d_proofs, size_t path_len,
+                          uint8_t* d_ok) {
+  return verify_to_cap_dev(c, d_rows, w, d_idx, ~(size_t)0, n_idx, d_cap, cap_height, d_proofs, path_len, d_ok);
+}
+
 int pmt_simple_tree_verify_dev(pmt_ctx* c, const uint64_t* d_leaves, const uint64_t* d_idx, size_t n_idx,
                                const uint64_t* d_root, const uint64_t* d_proofs, size_t path_len, uint8_t* d_ok) {
-  // verify_merkle_proof == verify_to_cap with width 1 and a one-entry cap; an index beyond 2^path_len simply fails
-  return pmt_merkle_verify_dev(c, d_leaves, 1, d_idx, n_idx, d_root, 0, d_proofs, path_len, d_ok);
+  // verify_merkle_proof == verify_to_cap with width 1 and a one-entry cap.  The reference folds by the parities of
+  // leaf_index >> i for i < path_len and never looks at the bits above (simple_merkle_tree.rs:97-105): an index of
+  // leaf_index + k 2^path_len verifies there, so it does here -- the index is masked to its low path_len bits.
+  if (path_len > 63) return fail(c, PMT_E_INVALID_ARG, "verify: bad path_len");
+  return verify_to_cap_dev(c, d_leaves, 1, d_idx, ((size_t)1 << path_len) - 1, n_idx, d_root, 0, d_proofs, path_len, d_ok);
 }
 
 int pmt_merkle_tree_build_dev(pmt_ctx* c, const uint64_t* d_leaves, size_t n, size_t w, uint32_t cap_height,
@@ -461,16 +591,14 @@ int pmt_merkle_tree_build_dev(pmt_ctx* c, const uint64_t* d_leaves, size_t n, si
   if (!d_leaves || !d_cap || (!d_digests && (size_t)lg > cap_height)) return fail(c, PMT_E_INVALID_ARG, "MerkleTree::new: null pointer");
   const int L = lg - (int)cap_height;
   Plonky2 lay{d_digests, d_cap, L};
-  if (w <= 4 && L >= 1 && n / 2 > COOP_MAX) {   // narrow leaves, big tree: the leaf copy rides along with level 1
+  if (w <= 4 && L >= 1 && n / 2 > c->coop_max) {   // narrow leaves, big tree: the leaf copy rides along with level 1
     TAG(c, "k_level", n / 2);
     k_leaves_level1<Plonky2><<<grid_for(c, n / 2), BLOCK, 0, c->stream>>>(lay, d_leaves, w, 0, n / 2);
     CHECK_LAUNCH(c);
     if (L == 1) return PMT_OK;
     return run_levels(c, lay, 2, L, n / 4);
   }
-  TAG(c, "k_leaves", w <= 4 ? 0 : n * ((w + 7) / 8));
-  k_leaves<Plonky2><<<w <= 4 ? grid_copy(c, n) : grid_for(c, n), BLOCK, 0, c->stream>>>(lay, d_leaves, w, 0, n);
-  CHECK_LAUNCH(c);
+  if (int rc = launch_leaves(c, lay, d_leaves, w, 0, n)) return rc;
   // levels 1 .. L over all subtrees at once: level l has n >> l nodes (2^h subtrees x 2^(L-l))
   if (L == 0) return PMT_OK;
   return run_levels(c, lay, 1, L, n / 2);
@@ -506,7 +634,7 @@ int pmt_merkle_prove_dev(pmt_ctx* c, const uint64_t* d_digests, size_t n, uint32
   if (!d_digests || !d_idx || !d_out) return fail(c, PMT_E_INVALID_ARG, "prove: null pointer");
   Plonky2 lay{const_cast<uint64_t*>(d_digests), nullptr, L};
   const size_t total = n_idx * (size_t)L;
-  k_plonky2_prove<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(lay, d_idx, n_idx, d_out);
+  k_plonky2_prove<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(lay, n, d_idx, n_idx, d_out);
   CHECK_LAUNCH(c);
   return PMT_OK;
 }
@@ -514,43 +642,30 @@ int pmt_merkle_prove_dev(pmt_ctx* c, const uint64_t* d_digests, size_t n, uint32
 // top of a sharded tree: the g - h levels above the gathered subtree roots.  d_top_out is level-major: n_roots/2,
 // n_roots/4, ..., 2^h digests (n_roots - 2^h in total); its last 2^h digests are the cap.
 int pmt_top_levels_dev(pmt_ctx* c, const uint64_t* d_roots, size_t n_roots, uint32_t cap_height, uint64_t* d_top_out) {
-  if (int rc = bind(c)) return rc;
-  const int g = log2_strict(n_roots);
-  if (g < 0) return fail(c, PMT_E_NOT_POW2, "top levels: %zu roots is not a power of two", n_roots);
-  if ((int)cap_height > g) return fail(c, PMT_E_RANGE, "top levels: cap_height %u > log2(roots)", cap_height);
-  if ((int)cap_height == g) return PMT_OK;  // the roots are the cap
-  if (!d_roots || !d_top_out) return fail(c, PMT_E_INVALID_ARG, "top levels: null pointer");
-  if (n_roots <= 4096) {   // always, in practice (one root per rank): one single-block cooperative launch for all levels
-    TAG(c, "k_top_roots_coop", n_roots - ((size_t)1 << cap_height));
-    k_top_roots_coop<<<1, COOP_BLOCK, 0, c->stream>>>(d_roots, n_roots, (size_t)1 << cap_height, d_top_out);
-    CHECK_LAUNCH(c);
-    return PMT_OK;
-  }
-  const uint64_t* cur = d_roots;
-  uint64_t* out = d_top_out;
-  for (size_t m = n_roots / 2; m >= ((size_t)1 << cap_height); m >>= 1) {
-    TAG(c, "k_two_to_one", m);
-    k_two_to_one<<<grid_for(c, m), BLOCK, 0, c->stream>>>(cur, cur + 4, out, m, 8);
-    CHECK_LAUNCH(c);
-    cur = out;
-    out += 4 * m;
-    if (m == 1) break;
-  }
-  return PMT_OK;
+  return pmt_top_levels_batch_dev(c, d_roots, 1, n_roots, cap_height, d_top_out);
 }
 
-// `batch` independent finishes of the same shape in ONE launch (one block each): the rounds of a sharded MMR
+// `batch` independent finishes of the same shape (the rounds of a sharded MMR): one launch for all sets when a set fits
+// one block (<= 64 roots: always, with one root per rank), else one launch per set
 int pmt_top_levels_batch_dev(pmt_ctx* c, const uint64_t* d_roots, size_t batch, size_t n_roots, uint32_t cap_height, uint64_t* d_top_out) {
   if (int rc = bind(c)) return rc;
   const int g = log2_strict(n_roots);
   if (g < 0) return fail(c, PMT_E_NOT_POW2, "top levels: %zu roots is not a power of two", n_roots);
   if ((int)cap_height > g) return fail(c, PMT_E_RANGE, "top levels: cap_height %u > log2(roots)", cap_height);
-  if (n_roots > 4096 || batch > 65535) return fail(c, PMT_E_RANGE, "top levels batch: at most 4096 roots x 65535 sets");
-  if ((int)cap_height == g || batch == 0) return PMT_OK;
+  if (batch > 65535) return fail(c, PMT_E_RANGE, "top levels batch: at most 65535 sets");
+  if ((int)cap_height == g || batch == 0) return PMT_OK;   // the roots are the cap
   if (!d_roots || !d_top_out) return fail(c, PMT_E_INVALID_ARG, "top levels: null pointer");
-  TAG(c, "k_top_roots_coop", batch * (n_roots - ((size_t)1 << cap_height)));
-  k_top_roots_coop<<<(unsigned)batch, COOP_BLOCK, 0, c->stream>>>(d_roots, n_roots, (size_t)1 << cap_height, d_top_out);
-  CHECK_LAUNCH(c);
+  const size_t n_cap = (size_t)1 << cap_height;
+  const int levels = g - (int)cap_height;                  // levels 1 .. levels of TopRoots
+  if (n_roots / 2 <= (size_t)COOP_NODES) {
+    TopRoots lay{d_roots, d_top_out, n_roots, n_roots, n_roots - n_cap};
+    const int done = launch_coop(c, lay, 1, levels, 0, n_roots / 2, (unsigned)batch);
+    return done < 0 ? done : PMT_OK;
+  }
+  for (size_t b = 0; b < batch; b++) {
+    TopRoots lay{d_roots + 4 * n_roots * b, d_top_out + 4 * (n_roots - n_cap) * b, n_roots, 0, 0};
+    if (int rc = launch_level_span(c, lay, 1, levels, 0, n_roots)) return rc;
+  }
   return PMT_OK;
 }
 
@@ -566,24 +681,7 @@ int pmt_mmr_extend_dev(pmt_ctx* c, uint64_t* d_elements, size_t n0, const uint64
   if (m == 0) return PMT_OK;
   if (!d_elements || !d_new) return fail(c, PMT_E_INVALID_ARG, "mmr extend: null pointer");
   if (n0 + m > ((size_t)1 << 30)) return fail(c, PMT_E_RANGE, "mmr extend: more than 2^30 leaves (get_mmr_index is i32, merkle_mountain_ranges.rs:264)");
-  Mmr lay{d_elements};
-  int first_level = 1;
-  if ((n0 & 1) == 0 && m / 2 > COOP_MAX) {   // every level-1 node has two NEW leaves: copy them and hash in one pass
-    TAG(c, "k_level", m / 2);
-    k_leaves_level1<Mmr><<<grid_for(c, m / 2), BLOCK, 0, c->stream>>>(lay, d_new, 1, n0 / 2, m / 2);
-    CHECK_LAUNCH(c);
-    if (m & 1) {                             // the unpaired last leaf
-      TAG(c, "k_leaves", 0);
-      k_leaves<Mmr><<<1, BLOCK, 0, c->stream>>>(lay, d_new + (m - 1), 1, n0 + m - 1, 1);
-      CHECK_LAUNCH(c);
-    }
-    first_level = 2;
-  } else {
-    TAG(c, "k_leaves", 0);
-    k_leaves<Mmr><<<grid_copy(c, m), BLOCK, 0, c->stream>>>(lay, d_new, 1, n0, m);
-    CHECK_LAUNCH(c);
-  }
-  return launch_level_span(c, lay, first_level, 40, n0, n0 + m);
+  return mmr_extend_plan(c, Mmr{d_elements}, n0, d_new, m);
 }
 
 int pmt_mmr_peaks_dev(pmt_ctx* c, const uint64_t* d_elements, size_t n_leaves, uint64_t* d_peaks, uint32_t* n_peaks_out) {
@@ -598,6 +696,15 @@ int pmt_mmr_peaks_dev(pmt_ctx* c, const uint64_t* d_elements, size_t n_leaves, u
   return PMT_OK;
 }
 
+// bagging_the_peaks (:122-127) = hash_or_noop over the flattened peaks: ONE row of 4 k felts, hashed by one quad (the
+// sponge's permutations are sequential)
+static int bag_peaks(pmt_ctx* c, const uint64_t* d_peaks, uint32_t k, uint64_t* d_root) {
+  TAG(c, "k_rows_coop", k <= 1 ? 0 : (4 * k + 7) / 8);
+  k_rows_coop<Flat, true, Wide><<<1, 32, 0, c->stream>>>(Flat{d_root}, d_peaks, (size_t)4 * k, 0, 1);
+  CHECK_LAUNCH(c);
+  return PMT_OK;
+}
+
 int pmt_mmr_bag_dev(pmt_ctx* c, const uint64_t* d_elements, size_t n_leaves, uint64_t* d_root) {
   if (int rc = bind(c)) return rc;
   if (n_leaves == 0) return fail(c, PMT_E_INVALID_ARG, "mmr bag: empty MMR");
@@ -606,10 +713,7 @@ int pmt_mmr_bag_dev(pmt_ctx* c, const uint64_t* d_elements, size_t n_leaves, uin
   if (int rc = arena_get(c, 2, 64 * 32 + 64, &peaks)) return rc;
   uint32_t k = 0;
   if (int rc = pmt_mmr_peaks_dev(c, d_elements, n_leaves, (uint64_t*)peaks, &k)) return rc;
-  TAG(c, "k_hash_one_coop", (4 * k + 7) / 8);
-  k_hash_one_coop<<<1, 32, 0, c->stream>>>((const uint64_t*)peaks, (size_t)4 * k, d_root);
-  CHECK_LAUNCH(c);
-  return PMT_OK;
+  return bag_peaks(c, (const uint64_t*)peaks, k, d_root);
 }
 
 int pmt_mmr_prove_dev(pmt_ctx* c, const uint64_t* d_elements, size_t n_leaves, const uint64_t* d_idx, size_t n_idx,
@@ -635,13 +739,12 @@ int pmt_mmr_verify_dev(pmt_ctx* c, const uint64_t* d_leaves, size_t n_idx, const
   void* bag = nullptr;
   if (int rc = arena_get(c, 2, 64 * 32 + 64, &bag)) return rc;
   uint64_t* d_bag = (uint64_t*)bag + 64 * 4;
-  TAG(c, "k_hash_one_coop", (4 * n_peaks + 7) / 8);
-  k_hash_one_coop<<<1, 32, 0, c->stream>>>(d_peaks, (size_t)4 * n_peaks, d_bag);
-  CHECK_LAUNCH(c);
+  if (int rc = bag_peaks(c, d_peaks, n_peaks, d_bag)) return rc;
   if (n_idx <= COOP_VERIFY_MAX) {
+    const CoopPlan p = coop_plan(c, n_idx);
     TAG(c, "k_mmr_verify_coop", n_idx);
-    k_mmr_verify_coop<<<(unsigned)((n_idx + COOP_GROUPS - 1) / COOP_GROUPS), COOP_BLOCK, 0, c->stream>>>(
-        d_leaves, n_idx, d_sib, d_left, d_len, d_peaks, n_peaks, d_bag, d_root, d_status);
+    if (p.wide) k_mmr_verify_coop<Wide><<<p.blocks, p.threads, 0, c->stream>>>(d_leaves, n_idx, d_sib, d_left, d_len, d_peaks, n_peaks, d_bag, d_root, d_status);
+    else k_mmr_verify_coop<Quad><<<p.blocks, p.threads, 0, c->stream>>>(d_leaves, n_idx, d_sib, d_left, d_len, d_peaks, n_peaks, d_bag, d_root, d_status);
   } else {
     TAG(c, "k_mmr_verify", n_idx);
     k_mmr_verify<<<(unsigned)((n_idx + BLOCK - 1) / BLOCK), BLOCK, 0, c->stream>>>(d_leaves, n_idx, d_sib, d_left, d_len, d_peaks,
@@ -656,7 +759,38 @@ int pmt_mmr_verify_dev(pmt_ctx* c, const uint64_t* d_leaves, size_t n_idx, const
 #define D2H(c, dst, src, bytes) CU(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (c)->stream))
 #define FINISH(c) CU(c, cudaStreamSynchronize((c)->stream))
 
-int pmt_permute(pmt_ctx* c, const uint64_t* in, size_t n, uint64_t* out) {
+// Every host-buffer entry point returns through this: on an error nothing of the ctx may still be reading or writing the
+// caller's buffers (DMA queued on the copy streams before the failing call would otherwise outlive the function, and a
+// caller that frees its buffers after an error would race the copy engines).  Errors of the drain itself are ignored.
+static int drained(pmt_ctx* c, int rc) {
+  if (rc != PMT_OK) {
+    if (c->copy_in) cudaStreamSynchronize(c->copy_in);
+    if (c->copy_out) cudaStreamSynchronize(c->copy_out);
+    cudaStreamSynchronize(c->stream);
+    cudaGetLastError();
+  }
+  return rc;
+}
+
+// the copy streams + events of the pipelined builders (created on first use); the copy streams are ordered behind the
+// work already queued on the compute stream (earlier users of the arenas)
+static int pipeline_streams(pmt_ctx* c, size_t chunks) {
+  if (!c->copy_in) CU(c, cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
+  if (!c->copy_out) CU(c, cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
+  while (c->ev.size() < 2 * chunks + 2) {
+    cudaEvent_t e;
+    CU(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->ev.push_back(e);
+  }
+  CU(c, cudaEventRecord(c->ev[2 * chunks], c->stream));
+  CU(c, cudaStreamWaitEvent(c->copy_in, c->ev[2 * chunks], 0));
+  CU(c, cudaStreamWaitEvent(c->copy_out, c->ev[2 * chunks], 0));
+  return PMT_OK;
+}
+
+static int pmt_permute_impl(pmt_ctx* c, const uint64_t* in, size_t n, uint64_t* out);
+int pmt_permute(pmt_ctx* c, const uint64_t* in, size_t n, uint64_t* out) { return c ? drained(c, pmt_permute_impl(c, in, n, out)) : PMT_E_INVALID_ARG; }
+static int pmt_permute_impl(pmt_ctx* c, const uint64_t* in, size_t n, uint64_t* out) {
   if (int rc = bind(c)) return rc;
   if (n == 0) return PMT_OK;
   if (!in || !out) return fail(c, PMT_E_INVALID_ARG, "pmt_permute: null pointer");
@@ -670,7 +804,9 @@ int pmt_permute(pmt_ctx* c, const uint64_t* in, size_t n, uint64_t* out) {
   return PMT_OK;
 }
 
-int pmt_hash_two_to_one(pmt_ctx* c, const uint64_t* l, const uint64_t* r, size_t n, uint64_t* out) {
+static int pmt_hash_two_to_one_impl(pmt_ctx* c, const uint64_t* l, const uint64_t* r, size_t n, uint64_t* out);
+int pmt_hash_two_to_one(pmt_ctx* c, const uint64_t* l, const uint64_t* r, size_t n, uint64_t* out) { return c ? drained(c, pmt_hash_two_to_one_impl(c, l, r, n, out)) : PMT_E_INVALID_ARG; }
+static int pmt_hash_two_to_one_impl(pmt_ctx* c, const uint64_t* l, const uint64_t* r, size_t n, uint64_t* out) {
   if (int rc = bind(c)) return rc;
   if (n == 0) return PMT_OK;
   if (!l || !r || !out) return fail(c, PMT_E_INVALID_ARG, "pmt_hash_two_to_one: null pointer");
@@ -699,10 +835,16 @@ static int hash_rows_host(pmt_ctx* c, const uint64_t* rows, size_t n, size_t w, 
   FINISH(c);
   return PMT_OK;
 }
-int pmt_hash_or_noop(pmt_ctx* c, const uint64_t* rows, size_t n, size_t w, uint64_t* out) { return hash_rows_host(c, rows, n, w, 1, out); }
-int pmt_hash_no_pad(pmt_ctx* c, const uint64_t* rows, size_t n, size_t w, uint64_t* out) { return hash_rows_host(c, rows, n, w, 0, out); }
+int pmt_hash_or_noop(pmt_ctx* c, const uint64_t* rows, size_t n, size_t w, uint64_t* out) {
+  return c ? drained(c, hash_rows_host(c, rows, n, w, 1, out)) : PMT_E_INVALID_ARG;
+}
+int pmt_hash_no_pad(pmt_ctx* c, const uint64_t* rows, size_t n, size_t w, uint64_t* out) {
+  return c ? drained(c, hash_rows_host(c, rows, n, w, 0, out)) : PMT_E_INVALID_ARG;
+}
 
-int pmt_simple_tree_build(pmt_ctx* c, const uint64_t* leaves, size_t n, uint64_t* levels_out, uint64_t* root_out) {
+static int pmt_simple_tree_build_impl(pmt_ctx* c, const uint64_t* leaves, size_t n, uint64_t* levels_out, uint64_t* root_out);
+int pmt_simple_tree_build(pmt_ctx* c, const uint64_t* leaves, size_t n, uint64_t* levels_out, uint64_t* root_out) { return c ? drained(c, pmt_simple_tree_build_impl(c, leaves, n, levels_out, root_out)) : PMT_E_INVALID_ARG; }
+static int pmt_simple_tree_build_impl(pmt_ctx* c, const uint64_t* leaves, size_t n, uint64_t* levels_out, uint64_t* root_out) {
   if (int rc = bind(c)) return rc;
   const int lg = log2_strict(n);
   if (lg < 0) return fail(c, PMT_E_NOT_POW2, "simple tree: %zu leaves is not a power of two (log2_strict, simple_merkle_tree.rs:30)", n);
@@ -731,7 +873,13 @@ static size_t plonky2_index(int L, int l, size_t k) {
 // on the copy-in stream while chunk i-1's subtree is hashed on the compute stream and chunk i-2's digests (one
 // contiguous slice of upstream's layout) go down on the copy-out stream, so PCIe traffic in both directions hides
 // behind the permutations.  The few digests above the chunk roots are finished and downloaded at the end.
+static int pmt_merkle_tree_build_impl(pmt_ctx* c, const uint64_t* leaves, size_t n, size_t w, uint32_t cap_height,
+                          uint64_t* digests_out, uint64_t* cap_out);
 int pmt_merkle_tree_build(pmt_ctx* c, const uint64_t* leaves, size_t n, size_t w, uint32_t cap_height,
+                          uint64_t* digests_out, uint64_t* cap_out) {
+  return c ? drained(c, pmt_merkle_tree_build_impl(c, leaves, n, w, cap_height, digests_out, cap_out)) : PMT_E_INVALID_ARG;
+}
+static int pmt_merkle_tree_build_impl(pmt_ctx* c, const uint64_t* leaves, size_t n, size_t w, uint32_t cap_height,
                           uint64_t* digests_out, uint64_t* cap_out) {
   if (int rc = bind(c)) return rc;
   const int lg = log2_strict(n);
@@ -763,26 +911,14 @@ int pmt_merkle_tree_build(pmt_ctx* c, const uint64_t* leaves, size_t n, size_t w
     FINISH(c);
     return PMT_OK;
   }
-  if (!c->copy_in) CU(c, cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
-  if (!c->copy_out) CU(c, cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
   const size_t chunks = n >> cb, chunk = (size_t)1 << cb;
-  while (c->ev.size() < 2 * chunks + 2) {
-    cudaEvent_t e;
-    CU(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    c->ev.push_back(e);
-  }
-  // the copy streams must not start before earlier work on the compute stream that used the arenas has finished
-  CU(c, cudaEventRecord(c->ev[2 * chunks], c->stream));
-  CU(c, cudaStreamWaitEvent(c->copy_in, c->ev[2 * chunks], 0));
-  CU(c, cudaStreamWaitEvent(c->copy_out, c->ev[2 * chunks], 0));
+  if (int rc = pipeline_streams(c, chunks)) return rc;
   Plonky2 lay{d_dig, d_cap, L};
   for (size_t i = 0; i < chunks; i++) {
     CU(c, cudaMemcpyAsync(d_leaves + i * chunk * w, leaves + i * chunk * w, chunk * w * 8, cudaMemcpyHostToDevice, c->copy_in));
     CU(c, cudaEventRecord(c->ev[2 * i], c->copy_in));
     CU(c, cudaStreamWaitEvent(c->stream, c->ev[2 * i], 0));
-    TAG(c, "k_leaves", w <= 4 ? 0 : chunk * ((w + 7) / 8));
-    k_leaves<Plonky2><<<w <= 4 ? grid_copy(c, chunk) : grid_for(c, chunk), BLOCK, 0, c->stream>>>(lay, d_leaves + i * chunk * w, w, i * chunk, chunk);
-    CHECK_LAUNCH(c);
+    if (int rc = launch_leaves(c, lay, d_leaves + i * chunk * w, w, i * chunk, chunk)) return rc;
     if (int rc = launch_level_span(c, lay, 1, cb, i * chunk, (i + 1) * chunk)) return rc;
     CU(c, cudaEventRecord(c->ev[2 * i + 1], c->stream));
     CU(c, cudaStreamWaitEvent(c->copy_out, c->ev[2 * i + 1], 0));
@@ -845,7 +981,7 @@ int pmt_merkle_tree_build_multi(pmt_ctx* const* ctxs, size_t n_ctx, const uint64
       rcs[r] = pmt_merkle_tree_build(ctxs[r], my, per, w, 0, digests_out + 4 * plonky2_index(L, 0, r * per), roots.data() + 4 * r);
     }
   };
-  run_per_ctx(rcs, work);
+  run_per_ctx(ctxs, rcs, work);
   for (size_t r = 0; r < n_ctx; r++)
     if (rcs[r] != PMT_OK) {
       char msg[sizeof ctxs[r]->err];
@@ -859,10 +995,14 @@ int pmt_merkle_tree_build_multi(pmt_ctx* const* ctxs, size_t n_ctx, const uint64
   if (int rc = arena_get(c0, 2, 2 * n_ctx * 32, &t)) return rc;
   uint64_t* d_roots = (uint64_t*)t; uint64_t* d_top = d_roots + 4 * n_ctx;
   std::vector<uint64_t> top(4 * (n_ctx - n_cap));
-  H2D(c0, d_roots, roots.data(), n_ctx * 32);
-  if (int rc = pmt_top_levels_dev(c0, d_roots, n_ctx, cap_height, d_top)) return rc;
-  D2H(c0, top.data(), d_top, (n_ctx - n_cap) * 32);
-  FINISH(c0);
+  auto finish = [&]() -> int {
+    H2D(c0, d_roots, roots.data(), n_ctx * 32);
+    if (int rc = pmt_top_levels_dev(c0, d_roots, n_ctx, cap_height, d_top)) return rc;
+    D2H(c0, top.data(), d_top, (n_ctx - n_cap) * 32);
+    FINISH(c0);
+    return PMT_OK;
+  };
+  if (int rc = drained(c0, finish())) return rc;
   for (size_t k = 0; k < n_ctx; k++) memcpy(digests_out + 4 * plonky2_index(L, Lr, k), roots.data() + 4 * k, 32);
   const uint64_t* lvl = top.data();
   int level = Lr + 1;
@@ -878,54 +1018,43 @@ int pmt_merkle_tree_build_multi(pmt_ctx* const* ctxs, size_t n_ctx, const uint64
   }
 }
 
-// Host-buffer batch append.  Only the old PEAKS are uploaded (a new node's left child is either new or an old peak), and
-// large batches run as a 3-stage pipeline over aligned power-of-two chunks: appending chunk i to the MMR of the leaves
-// before it creates exactly the elements [mmr_size(n0 + i*chunk), mmr_size(n0 + (i+1)*chunk)) -- the chunk's perfect
-// sub-mountain followed by every ancestor it completes -- ONE contiguous slice of the post-order array, so it is
-// downloaded while the next chunk is hashed and the one after that is uploaded.
-int pmt_mmr_extend(pmt_ctx* c, uint64_t* elements, size_t n0, const uint64_t* new_leaves, size_t m) {
-  if (int rc = bind(c)) return rc;
-  if (m == 0) return PMT_OK;
-  if (!elements || !new_leaves) return fail(c, PMT_E_INVALID_ARG, "mmr extend: null pointer");
-  if (n0 + m > ((size_t)1 << 30)) return fail(c, PMT_E_RANGE, "mmr extend: more than 2^30 leaves (get_mmr_index is i32, merkle_mountain_ranges.rs:264)");
+// Host-buffer batch append.  The device holds only the old PEAKS (a new node's left child is either new or an old peak)
+// and the new elements (MmrAppend: O(m + log n) device memory, whatever the size of the MMR appended to), and large batches
+// run as a 3-stage pipeline over aligned power-of-two chunks: appending chunk i to the MMR of the leaves before it creates
+// exactly the elements [mmr_size(n0 + i*chunk), mmr_size(n0 + (i+1)*chunk)) -- the chunk's perfect sub-mountain followed by
+// every ancestor it completes -- ONE contiguous slice of the post-order array, so it is downloaded while the next chunk is
+// hashed and the one after that is uploaded.
+static int mmr_extend_host(pmt_ctx* c, uint64_t* elements, size_t n0, const uint64_t* new_leaves, size_t m) {
   const size_t s0 = pmt_mmr_size(n0), s1 = pmt_mmr_size(n0 + m);
+  const uint32_t n_peaks = (uint32_t)__builtin_popcountll((unsigned long long)n0);
   void *a, *b;
   if (int rc = arena_get(c, 0, m * 8, &a)) return rc;
-  if (int rc = arena_get(c, 1, s1 * 32, &b)) return rc;
+  if (int rc = arena_get(c, 1, (n_peaks + (s1 - s0)) * 32, &b)) return rc;
   uint64_t* d_leaves = (uint64_t*)a;
-  uint64_t* d_el = (uint64_t*)b;
-  // old peaks: one per set bit of n0, at the last position of its mountain (get_peaks, :179-200)
+  const MmrAppend lay{(uint64_t*)b, n0, s0, n_peaks};
+  uint64_t* d_new = lay.buf + 4 * (size_t)n_peaks;       // element at post-order position p >= s0: d_new + 4 (p - s0)
+  // old peaks: one per set bit of n0, at the last position of its mountain (get_peaks, :179-200), largest first
   {
     size_t base = 0;
+    uint32_t slot = 0;
     for (int bit = 63; bit >= 0; bit--)
       if ((n0 >> bit) & 1) {
         base += (size_t)1 << bit;
-        const size_t pos = pmt_mmr_size(base) - 1;
-        H2D(c, d_el + 4 * pos, elements + 4 * pos, 32);
+        H2D(c, lay.buf + 4 * (size_t)slot++, elements + 4 * (pmt_mmr_size(base) - 1), 32);
       }
   }
-  int lgm = 0;
-  while (((size_t)2 << lgm) <= m) lgm++;                 // floor(log2 m)
+  const int lgm = log2_floor(m);
   const size_t chunk = lgm >= 20 ? (size_t)1 << (lgm - 4) : m;   // 16 .. 31 chunks for big batches, else one shot
   if (chunk >= m) {
     H2D(c, d_leaves, new_leaves, m * 8);
-    if (int rc = pmt_mmr_extend_dev(c, d_el, n0, d_leaves, m)) return rc;
-    D2H(c, elements + 4 * s0, d_el + 4 * s0, (s1 - s0) * 32);
+    if (int rc = mmr_extend_plan(c, lay, n0, d_leaves, m)) return rc;
+    D2H(c, elements + 4 * s0, d_new, (s1 - s0) * 32);
     FINISH(c);
     return PMT_OK;
   }
   // first piece: up to the next multiple of `chunk` so that every later piece is an aligned perfect sub-mountain
   const size_t chunks = (m + chunk - 1) / chunk + 1;
-  if (!c->copy_in) CU(c, cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
-  if (!c->copy_out) CU(c, cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
-  while (c->ev.size() < 2 * chunks + 2) {
-    cudaEvent_t e;
-    CU(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    c->ev.push_back(e);
-  }
-  CU(c, cudaEventRecord(c->ev[2 * chunks], c->stream));   // the peaks above (and earlier arena users) come first
-  CU(c, cudaStreamWaitEvent(c->copy_in, c->ev[2 * chunks], 0));
-  CU(c, cudaStreamWaitEvent(c->copy_out, c->ev[2 * chunks], 0));
+  if (int rc = pipeline_streams(c, chunks)) return rc;
   size_t done = 0, i = 0;
   while (done < m) {
     size_t len = chunk - ((n0 + done) & (chunk - 1));     // to the next chunk boundary
@@ -933,17 +1062,25 @@ int pmt_mmr_extend(pmt_ctx* c, uint64_t* elements, size_t n0, const uint64_t* ne
     CU(c, cudaMemcpyAsync(d_leaves + done, new_leaves + done, len * 8, cudaMemcpyHostToDevice, c->copy_in));
     CU(c, cudaEventRecord(c->ev[2 * i], c->copy_in));
     CU(c, cudaStreamWaitEvent(c->stream, c->ev[2 * i], 0));
-    if (int rc = pmt_mmr_extend_dev(c, d_el, n0 + done, d_leaves + done, len)) return rc;
+    if (int rc = mmr_extend_plan(c, lay, n0 + done, d_leaves + done, len)) return rc;
     CU(c, cudaEventRecord(c->ev[2 * i + 1], c->stream));
     CU(c, cudaStreamWaitEvent(c->copy_out, c->ev[2 * i + 1], 0));
     const size_t p0 = pmt_mmr_size(n0 + done), p1 = pmt_mmr_size(n0 + done + len);
-    CU(c, cudaMemcpyAsync(elements + 4 * p0, d_el + 4 * p0, (p1 - p0) * 32, cudaMemcpyDeviceToHost, c->copy_out));
+    CU(c, cudaMemcpyAsync(elements + 4 * p0, d_new + 4 * (p0 - s0), (p1 - p0) * 32, cudaMemcpyDeviceToHost, c->copy_out));
     done += len;
     i++;
   }
   CU(c, cudaStreamSynchronize(c->copy_out));
   FINISH(c);
   return PMT_OK;
+}
+
+int pmt_mmr_extend(pmt_ctx* c, uint64_t* elements, size_t n0, const uint64_t* new_leaves, size_t m) {
+  if (int rc = bind(c)) return rc;
+  if (m == 0) return PMT_OK;
+  if (!elements || !new_leaves) return fail(c, PMT_E_INVALID_ARG, "mmr extend: null pointer");
+  if (n0 + m > ((size_t)1 << 30)) return fail(c, PMT_E_RANGE, "mmr extend: more than 2^30 leaves (get_mmr_index is i32, merkle_mountain_ranges.rs:264)");
+  return drained(c, mmr_extend_host(c, elements, n0, new_leaves, m));
 }
 
 // ---- single-process multi-GPU batch append ---------------------------------------------------------------------------------
@@ -1010,7 +1147,7 @@ int pmt_mmr_extend_multi(pmt_ctx* const* ctxs, size_t n_ctx, uint64_t* elements,
       if (rcs[r] != PMT_OK) return;
     }
   };
-  run_per_ctx(rcs, work);
+  run_per_ctx(ctxs, rcs, work);
   for (size_t r = 0; r < n_ctx; r++)
     if (rcs[r] != PMT_OK) {
       char msg[sizeof ctxs[r]->err];
@@ -1018,28 +1155,34 @@ int pmt_mmr_extend_multi(pmt_ctx* const* ctxs, size_t n_ctx, uint64_t* elements,
       msg[sizeof msg - 1] = 0;
       return fail(c0, rcs[r], "mmr extend multi: ctx %zu (device %d): %.400s", r, ctxs[r]->device, msg);
     }
-  // the coarse MMR over the block roots, on context 0
+  // the coarse MMR over the block roots, on context 0: its old peaks, the block roots and what the append creates
   if (int rc = bind(c0)) return rc;
   const size_t s0 = A >> b, s1 = s0 + C;
+  const size_t cs0 = pmt_mmr_size(s0), cs1 = pmt_mmr_size(s1);
+  const uint32_t n_peaks = (uint32_t)__builtin_popcountll((unsigned long long)s0);
   void* t = nullptr;
-  if (int rc = arena_get(c0, 1, pmt_mmr_size(s1) * 32, &t)) return rc;
-  uint64_t* d_sup = (uint64_t*)t;
-  {
+  if (int rc = arena_get(c0, 1, (n_peaks + (cs1 - cs0)) * 32, &t)) return rc;
+  const MmrAppend sup{(uint64_t*)t, s0, cs0, n_peaks};
+  uint64_t* d_new = sup.buf + 4 * (size_t)n_peaks;     // coarse element at post-order position p >= cs0: d_new + 4 (p - cs0)
+  auto coarse = [&]() -> int {
     size_t base = 0;
+    uint32_t slot = 0;
     for (int bit = 63; bit >= 0; bit--)
       if ((s0 >> bit) & 1) {
         base += (size_t)1 << bit;
-        H2D(c0, d_sup + 4 * (pmt_mmr_size(base) - 1), elements + 4 * (pmt_mmr_size(base << b) - 1), 32);
+        H2D(c0, sup.buf + 4 * (size_t)slot++, elements + 4 * (pmt_mmr_size(base << b) - 1), 32);
       }
-  }
-  for (size_t s = s0; s < s1; s++) H2D(c0, d_sup + 4 * mmr_pos(0, s), elements + 4 * mmr_pos((int)b, s), 32);
-  if (int rc = launch_level_span(c0, Mmr{d_sup}, 1, 40, s0, s1)) return rc;
-  for (int l = 1; l < 40; l++) {
-    const size_t k0 = s0 >> l, k1 = s1 >> l;
-    if (k1 == 0) break;
-    for (size_t k = k0; k < k1; k++) D2H(c0, elements + 4 * mmr_pos(l + (int)b, k), d_sup + 4 * mmr_pos(l, k), 32);
-  }
-  FINISH(c0);
+    for (size_t s = s0; s < s1; s++) H2D(c0, d_new + 4 * (mmr_pos(0, s) - cs0), elements + 4 * mmr_pos((int)b, s), 32);
+    if (int rc = launch_level_span(c0, sup, 1, 40, s0, s1)) return rc;
+    for (int l = 1; l < 40; l++) {
+      const size_t k0 = s0 >> l, k1 = s1 >> l;
+      if (k1 == 0) break;
+      for (size_t k = k0; k < k1; k++) D2H(c0, elements + 4 * mmr_pos(l + (int)b, k), d_new + 4 * (mmr_pos(l, k) - cs0), 32);
+    }
+    FINISH(c0);
+    return PMT_OK;
+  };
+  if (int rc = drained(c0, coarse())) return rc;
   if (n0 + m > Z) return pmt_mmr_extend(c0, elements, Z, new_leaves + (Z - n0), n0 + m - Z);
   return PMT_OK;
   } catch (const std::bad_alloc&) {
@@ -1078,7 +1221,11 @@ int pmt_mmr_peaks(pmt_ctx* c, const uint64_t* elements, size_t n_leaves, uint64_
 }
 
 // bagging_the_peaks on a HOST array: only the peaks travel to the GPU (the old form uploaded all of `elements`)
+static int pmt_mmr_bag_impl(pmt_ctx* c, const uint64_t* elements, size_t n_leaves, uint64_t* root_out);
 int pmt_mmr_bag(pmt_ctx* c, const uint64_t* elements, size_t n_leaves, uint64_t* root_out) {
+  return c ? drained(c, pmt_mmr_bag_impl(c, elements, n_leaves, root_out)) : PMT_E_INVALID_ARG;
+}
+static int pmt_mmr_bag_impl(pmt_ctx* c, const uint64_t* elements, size_t n_leaves, uint64_t* root_out) {
   if (int rc = bind(c)) return rc;
   if (n_leaves == 0) return fail(c, PMT_E_INVALID_ARG, "mmr bag: empty MMR");
   if (!elements || !root_out) return fail(c, PMT_E_INVALID_ARG, "mmr bag: null pointer");
@@ -1090,9 +1237,7 @@ int pmt_mmr_bag(pmt_ctx* c, const uint64_t* elements, size_t n_leaves, uint64_t*
   uint64_t* d_peaks = (uint64_t*)p;
   uint64_t* d_root = d_peaks + 64 * 4;
   for (uint32_t i = 0; i < k; i++) H2D(c, d_peaks + 4 * i, elements + 4 * pos[i], 32);
-  TAG(c, "k_hash_one_coop", (4 * k + 7) / 8);
-  k_hash_one_coop<<<1, 32, 0, c->stream>>>(d_peaks, (size_t)4 * k, d_root);
-  CHECK_LAUNCH(c);
+  if (int rc = bag_peaks(c, d_peaks, k, d_root)) return rc;
   D2H(c, root_out, d_root, 32);
   FINISH(c);
   return PMT_OK;
@@ -1168,8 +1313,14 @@ int pmt_mmr_prove(pmt_ctx* c, const uint64_t* elements, size_t n_leaves, const u
 }
 
 // ---- host-buffer verification: upload the batch, fold every path on the GPU, download the verdicts ------------------------
+static int verify_to_cap_host(pmt_ctx* c, const uint64_t* leaf_rows, size_t w, const uint64_t* idx, size_t idx_mask, size_t n_idx,
+                              const uint64_t* cap, uint32_t cap_height, const uint64_t* proofs, size_t path_len, uint8_t* ok_out);
 int pmt_merkle_verify(pmt_ctx* c, const uint64_t* leaf_rows, size_t w, const uint64_t* idx, size_t n_idx, const uint64_t* cap,
                       uint32_t cap_height, const uint64_t* proofs, size_t path_len, uint8_t* ok_out) {
+  return c ? drained(c, verify_to_cap_host(c, leaf_rows, w, idx, ~(size_t)0, n_idx, cap, cap_height, proofs, path_len, ok_out)) : PMT_E_INVALID_ARG;
+}
+static int verify_to_cap_host(pmt_ctx* c, const uint64_t* leaf_rows, size_t w, const uint64_t* idx, size_t idx_mask, size_t n_idx,
+                              const uint64_t* cap, uint32_t cap_height, const uint64_t* proofs, size_t path_len, uint8_t* ok_out) {
   if (int rc = bind(c)) return rc;
   if (n_idx == 0) return PMT_OK;
   if (!leaf_rows || !idx || !cap || !ok_out || (!proofs && path_len)) return fail(c, PMT_E_INVALID_ARG, "verify: null pointer");
@@ -1188,7 +1339,7 @@ int pmt_merkle_verify(pmt_ctx* c, const uint64_t* leaf_rows, size_t w, const uin
   H2D(c, d_idx, idx, b_idx);
   H2D(c, d_cap, cap, b_cap);
   if (b_pr) H2D(c, d_pr, proofs, b_pr);
-  if (int rc = pmt_merkle_verify_dev(c, d_rows, w, d_idx, n_idx, d_cap, cap_height, d_pr, path_len, d_ok)) return rc;
+  if (int rc = verify_to_cap_dev(c, d_rows, w, d_idx, idx_mask, n_idx, d_cap, cap_height, d_pr, path_len, d_ok)) return rc;
   D2H(c, ok_out, d_ok, n_idx);
   FINISH(c);
   return PMT_OK;
@@ -1196,10 +1347,19 @@ int pmt_merkle_verify(pmt_ctx* c, const uint64_t* leaf_rows, size_t w, const uin
 
 int pmt_simple_tree_verify(pmt_ctx* c, const uint64_t* leaves, const uint64_t* idx, size_t n_idx, const uint64_t* root,
                            const uint64_t* proofs, size_t path_len, uint8_t* ok_out) {
-  return pmt_merkle_verify(c, leaves, 1, idx, n_idx, root, 0, proofs, path_len, ok_out);
+  if (!c) return PMT_E_INVALID_ARG;
+  if (path_len > 63) return fail(c, PMT_E_INVALID_ARG, "verify: bad path_len");
+  // index masked to its low path_len bits: see pmt_simple_tree_verify_dev
+  return drained(c, verify_to_cap_host(c, leaves, 1, idx, ((size_t)1 << path_len) - 1, n_idx, root, 0, proofs, path_len, ok_out));
 }
 
+static int pmt_mmr_verify_impl(pmt_ctx* c, const uint64_t* leaves, size_t n_idx, const uint64_t* siblings, const uint8_t* on_left,
+                   const uint32_t* path_len, const uint64_t* peaks, uint32_t n_peaks, const uint64_t* root, int8_t* status_out);
 int pmt_mmr_verify(pmt_ctx* c, const uint64_t* leaves, size_t n_idx, const uint64_t* siblings, const uint8_t* on_left,
+                   const uint32_t* path_len, const uint64_t* peaks, uint32_t n_peaks, const uint64_t* root, int8_t* status_out) {
+  return c ? drained(c, pmt_mmr_verify_impl(c, leaves, n_idx, siblings, on_left, path_len, peaks, n_peaks, root, status_out)) : PMT_E_INVALID_ARG;
+}
+static int pmt_mmr_verify_impl(pmt_ctx* c, const uint64_t* leaves, size_t n_idx, const uint64_t* siblings, const uint8_t* on_left,
                    const uint32_t* path_len, const uint64_t* peaks, uint32_t n_peaks, const uint64_t* root, int8_t* status_out) {
   if (int rc = bind(c)) return rc;
   if (n_idx == 0) return PMT_OK;

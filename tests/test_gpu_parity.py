@@ -868,3 +868,225 @@ def test_dev_entry_points_wait_for_torch_stream(api, ctx, oracle):
         dg, cap = oracle.merkle_tree_new(rows, 0, threads=oracle.max_threads(), fast=True)
         assert np.array_equal(t.cap, cap), rep
         assert np.array_equal(t.digests, dg), rep
+
+
+# =====================================================================================================================
+# round 2: the four-threads-per-state cooperative kernels, the one-launch tree tail, ABI hardening, full-size parity
+# =====================================================================================================================
+def test_hasher_small_and_big_batches_agree(api, oracle):
+    """Hasher batches of <= 2^12 rows run by quads (k_permute_coop / k_rows_coop), bigger ones one row per thread: both against
+    the oracle and against each other, incl. non-canonical inputs"""
+    st = edge_states(6000, 11)
+    big = api.hasher.permute(st)                       # thread-per-state
+    small = np.concatenate([api.hasher.permute(st[a:a + 1500]) for a in range(0, 6000, 1500)])   # quads
+    assert np.array_equal(big, small)
+    for i in range(0, 6000, 37):
+        assert big[i].tolist() == oracle.permute(st[i]).tolist()
+    for w in (5, 8, 9, 135):
+        rows = splitmix_felts(40 + w, 5000 * w).reshape(5000, w)
+        rows[7, :] = np.uint64(2**64 - 1)
+        big = api.hasher.hash_or_noop(rows)
+        small = np.concatenate([api.hasher.hash_or_noop(rows[a:a + 1000]) for a in range(0, 5000, 1000)])
+        assert np.array_equal(big, small)
+        assert np.array_equal(api.hasher.hash_no_pad(rows[:100]), big[:100])
+        for i in (0, 7, 63, 64, 999, 4999):
+            assert big[i].tolist() == oracle.hash_no_pad(rows[i]).tolist()
+    rows = splitmix_felts(3, 100 * 3).reshape(100, 3)
+    assert api.hasher.hash_no_pad(rows)[5].tolist() == oracle.hash_no_pad(rows[5]).tolist()     # sponge also for width <= 4
+
+
+@pytest.mark.parametrize("coop_log2", [6, 7, 10, 15, 17])
+def test_tree_tail_for_every_cooperative_threshold(api, oracle, coop_log2, monkeypatch):
+    """k_tree_coop (block-local subtrees of 64 nodes, then the last block to finish takes the levels above) for trees whose
+    cooperative part starts at 2^6 .. 2^17 nodes: 1, 2, 16, 512, 2048 blocks in the ticket.  Plonky2 layout with and without
+    a cap, the simple tree, MMR appends (aligned, ragged, onto old peaks) -- all against the oracle."""
+    from plonky2_merkle_trees_b200 import _lib
+    monkeypatch.setenv("PMT_COOP_MAX_LOG2", str(coop_log2))
+    c = _lib.Context(0)
+    monkeypatch.delenv("PMT_COOP_MAX_LOG2")
+    try:
+        for lg, w, h in [(3, 4, 0), (7, 4, 0), (8, 4, 1), (12, 4, 0), (14, 3, 5), (16, 4, 0), (18, 1, 0), (11, 9, 0)]:
+            n = 1 << lg
+            rows = splitmix_felts(1000 * coop_log2 + lg + w, n * w).reshape(n, w)
+            t = api.mt.MerkleTree.new(rows, h, c)
+            dg, cap = oracle.merkle_tree_new(rows, h, threads=oracle.max_threads(), fast=True)
+            assert np.array_equal(t.digests, dg) and np.array_equal(t.cap, cap), (lg, w, h)
+            t2 = api.mt.MerkleTree.new(rows, h, c)      # the tickets are reset by the launch that used them
+            assert np.array_equal(t2.digests, dg) and np.array_equal(t2.cap, cap)
+        leaves = splitmix_felts(coop_log2, 1 << 13)
+        s = api.smt.MerkleTree.build(leaves, c)
+        levels, root = oracle.simple_tree_build(leaves)
+        assert np.array_equal(np.concatenate(s.tree), levels) and np.array_equal(s.root, root)
+        for n0, m in [(0, 1 << 13), (1 << 12, 1 << 12), (3 << 10, 5 << 10), (77, 9000), (1 << 14, 64), (4032, 64 + 4096)]:
+            lv = splitmix_felts(n0 + m + coop_log2, n0 + m)
+            mm = api.mmr.MMR.new(c)
+            if n0:
+                mm.extend(lv[:n0])
+            mm.extend(lv[n0:])
+            assert np.array_equal(mm.elements, oracle.mmr_extend(None, lv)), (n0, m)
+    finally:
+        c.close()
+
+
+def test_mmr_verify_rejects_overlong_path(ctx, api):
+    """a proof is the verifier's untrusted input: path_len beyond the 32 entries of the batch layout is status -1 (the
+    reference would fail its assert! :245 on such a path), not an out-of-bounds walk -- both kernels"""
+    n = 1000
+    leaves = splitmix_felts(8, n)
+    m = api.mmr.MMR.new(ctx); m.extend(leaves)
+    peaks, root = m.get_peaks(), m.bagging_the_peaks()
+    for q in (64, 20000):      # cooperative / thread-per-proof kernel
+        idx = (splitmix_felts(q, q) % np.uint64(n)).astype(np.uint64)
+        sib, left, ln = m.prove_batch(idx)
+        ln = ln.copy()
+        ln[3] = 33; ln[5] = 0xFFFFFFFF; ln[q - 1] = 1 << 20
+        st = api.mmr.verify_batch(leaves[idx.astype(np.int64)], sib, left, ln, peaks, root, ctx)
+        bad = np.zeros(q, bool); bad[[3, 5, q - 1]] = True
+        assert (st[bad] == -1).all() and (st[~bad] == 1).all()
+
+
+def test_simple_tree_verify_index_semantics_and_prove_bounds(ctx, api, oracle):
+    """verify_merkle_proof (simple_merkle_tree.rs:91-109) folds by the parities of the low path_len index bits and never
+    looks above them: leaf_index + k 2^path_len verifies in the reference, so it does here (device and host forms), while
+    upstream's verify_merkle_proof_to_cap rejects it.  A device prove with an index >= n returns zeros, never reads outside."""
+    from plonky2_merkle_trees_b200._lib import ptr, u8p
+    from plonky2_merkle_trees_b200.device import dev_u64, dptr, to_device, to_host
+    n, lg = 1 << 6, 6
+    leaves = splitmix_felts(21, n)
+    t = api.smt.MerkleTree.build(leaves, ctx)
+    proof = t.get_merkle_proof(9)
+    for idx in (9, 9 + n, 9 + 5 * n, 9 + (1 << 40)):
+        assert api.smt.verify_merkle_proof(int(leaves[9]), idx, t.root, proof, ctx)
+        assert oracle.simple_tree_verify(int(leaves[9]), idx, t.root, proof)
+    assert not api.smt.verify_merkle_proof(int(leaves[9]), 8, t.root, proof, ctx)
+    ok = np.zeros(2, np.uint8)
+    ctx.call("pmt_simple_tree_verify", ptr(np.array([leaves[9], leaves[9]], np.uint64)), ptr(np.array([9 + n, 8], np.uint64)), 2, ptr(t.root),
+             ptr(np.concatenate([proof, proof])), lg, ok.ctypes.data_as(u8p))
+    assert list(ok) == [1, 0]
+    levels = to_device(np.concatenate(t.tree), "cuda:0")
+    d_idx = to_device(np.array([5, n, 2**63], np.uint64), "cuda:0")
+    d_out = dev_u64((3, lg, 4), "cuda:0")
+    ctx.call("pmt_simple_tree_prove_dev", dptr(levels), n, dptr(d_idx), 3, dptr(d_out)); ctx.sync()
+    out = to_host(d_out)
+    assert np.array_equal(out[0], t.get_merkle_proof(5)) and not out[1].any() and not out[2].any()
+    rows = splitmix_felts(22, n * 4).reshape(n, 4)
+    pt = api.mt.MerkleTree.new(rows, 2, ctx)
+    d_out = dev_u64((2, lg - 2, 4), "cuda:0")
+    ctx.call("pmt_merkle_prove_dev", dptr(pt.d_digests), n, 2, dptr(to_device(np.array([7, n + 7], np.uint64), "cuda:0")), 2, dptr(d_out)); ctx.sync()
+    out = to_host(d_out)
+    assert np.array_equal(out[0], pt.prove(7)) and not out[1].any()
+    m = api.mmr.MMR.new(ctx); m.extend(leaves[:50])
+    d_sib, d_left, d_len = dev_u64((2, 32, 4), "cuda:0"), torch.zeros((2, 32), dtype=torch.uint8, device="cuda:0"), torch.zeros(2, dtype=torch.int32, device="cuda:0")
+    ctx.call("pmt_mmr_prove_dev", dptr(m.d_elements), 50, dptr(to_device(np.array([49, 50], np.uint64), "cuda:0")), 2, dptr(d_sib), dptr(d_left), dptr(d_len)); ctx.sync()
+    assert d_len.cpu().tolist() == [1, 0]
+
+
+@pytest.mark.parametrize("n0,m", [((1 << 20) + 123, 1), ((1 << 20) + 123, 5), ((1 << 20) - 1, 1), (3 << 18, 70000), ((1 << 21) - 7, 7 + (1 << 20))])
+def test_mmr_host_append_touches_only_peaks_and_new_elements(ctx, api, n0, m):
+    """pmt_mmr_extend on a HOST array: the device holds the old peaks and the new elements only (MmrAppend), so appending one
+    leaf to a 2^20-leaf MMR is a few hundred bytes of device memory -- same elements as the device-resident append"""
+    from plonky2_merkle_trees_b200._lib import ptr
+    leaves = splitmix_felts(n0 + m, n0 + m)
+    ref = api.mmr.MMR.new(ctx)
+    ref.extend(leaves)
+    want = ref.elements
+    s0 = ctx.lib.pmt_mmr_size(n0)
+    el = np.zeros_like(want)
+    el[:s0] = want[:s0]
+    ctx.call("pmt_mmr_extend", ptr(el), n0, ptr(leaves[n0:]), m)
+    assert np.array_equal(el, want)
+
+
+def test_full_size_headline_tree_against_full_oracle_rebuild(api, oracle):
+    """The headline workload, 2^24 leaves x 4 felts, cap 0: EVERY digest (33.5 M) against a full rebuild by the oracle on all
+    host cores (16.7 M permutations, a few seconds) -- and the same for the host-buffer, pipelined entry point"""
+    from plonky2_merkle_trees_b200._lib import ptr
+    import bench
+    lg, w = 24, 4
+    n = 1 << lg
+    rows = bench.splitmix_numpy(0, n * w).reshape(n, w)
+    odg, ocap = oracle.merkle_tree_new(rows, 0, threads=oracle.max_threads(), fast=True)
+    t = api.mt.MerkleTree.new(rows, 0)
+    assert np.array_equal(t.cap, ocap)
+    assert np.array_equal(t.digests, odg)
+    del t
+    dg = np.zeros_like(odg); cap = np.zeros_like(ocap)
+    api.mt._lib.default_context().call("pmt_merkle_tree_build", ptr(rows), n, w, 0, ptr(dg), ptr(cap))
+    assert np.array_equal(cap, ocap) and np.array_equal(dg, odg)
+
+
+def test_full_size_c4_fri_commitment_against_full_oracle_rebuild(api, oracle):
+    """BASELINE C4 at FULL size: 2^20 rows x 135 columns, cap_height 4 (18.9 M permutations): every digest and the cap
+    against the oracle, from row-major leaves and from the prover's column-major LDE values"""
+    from plonky2_merkle_trees_b200.device import to_device
+    import bench
+    lg, w, h = 20, 135, 4
+    n = 1 << lg
+    rows = bench.splitmix_numpy(0, n * w).reshape(n, w)
+    odg, ocap = oracle.merkle_tree_new(rows, h, threads=oracle.max_threads(), fast=True)
+    t = api.mt.MerkleTree.new(rows, h)
+    assert np.array_equal(t.cap, ocap) and np.array_equal(t.digests, odg)
+    del t
+    cols = np.ascontiguousarray(rows.T)
+    t = api.mt.MerkleTree.from_columns_dev(to_device(cols, "cuda:0"), h, bit_reverse=False)
+    assert np.array_equal(t.cap, ocap) and np.array_equal(t.digests, odg)
+
+
+def test_full_size_c5_2p28_sampled_against_oracle(api, oracle):
+    """BASELINE C5 on one GPU: 2^28 leaves x 4 felts (8 GiB of leaves, 16 GiB of digests).  A full CPU rebuild is 40 s, so:
+    (1) the subtree over the first 2^20 leaves (a contiguous slice of upstream's layout) equals the oracle's tree, digest by
+    digest; (2) 20 000 nodes sampled over all 28 levels equal the oracle's two_to_one of their stored children; (3) the root
+    is the oracle's fold of the 16 subtree roots of an independent cap-4 build; (4) leaf digests are the no-op copy"""
+    import bench
+    from plonky2_merkle_trees_b200.device import to_host
+    lg, w = 28, 4
+    n = 1 << lg
+    dev = torch.device("cuda", 0)
+    d_leaves = bench.splitmix_torch(0, n * w, dev).view(n, w)
+    t = api.mt.MerkleTree.new_dev(d_leaves, 0)
+    d = t.d_digests
+    node = lambda l, k: 2 * (((k >> 1) << (l + 1)) + (1 << l) - 1) + (k & 1)
+    # (1)
+    sub = 1 << 20
+    rows = bench.splitmix_numpy(0, sub * w).reshape(sub, w)
+    odg, ocap = oracle.merkle_tree_new(rows, 0, threads=oracle.max_threads(), fast=True)
+    assert np.array_equal(to_host(d[:2 * sub - 2]), odg)
+    assert np.array_equal(to_host(d[node(20, 0)]), ocap[0])
+    # (2)
+    rnd = random.Random(28)
+    ls = [rnd.randrange(1, lg) for _ in range(20000)]
+    ks = [rnd.randrange(n >> l) for l in ls]
+    par = torch.tensor([node(l, k) for l, k in zip(ls, ks)], device=dev)
+    c0 = torch.tensor([node(l - 1, 2 * k) for l, k in zip(ls, ks)], device=dev)
+    assert np.array_equal(oracle.two_to_one_batch(to_host(d[c0]), to_host(d[c0 + 1])), to_host(d[par]))
+    top = to_host(d[torch.tensor([node(lg - 1, 0), node(lg - 1, 1)], device=dev)])
+    root = to_host(t.d_cap)[0]
+    assert np.array_equal(oracle.two_to_one(top[0], top[1]), root)
+    # (4)
+    pick = torch.tensor([rnd.randrange(n // 2) for _ in range(5000)], device=dev)
+    assert torch.equal(d[4 * pick], d_leaves[2 * pick]) and torch.equal(d[4 * pick + 1], d_leaves[2 * pick + 1])
+    del t, d
+    torch.cuda.empty_cache()
+    # (3)
+    t4 = api.mt.MerkleTree.new_dev(d_leaves, 4)
+    lvl = to_host(t4.d_cap)
+    while lvl.shape[0] > 1:
+        lvl = oracle.two_to_one_batch(lvl[0::2], lvl[1::2])
+    assert np.array_equal(lvl[0], root)
+    del t4, d_leaves
+    torch.cuda.empty_cache()
+
+
+def test_multi_gpu_nccl_parity_under_torchrun():
+    """the one-process-per-GPU path (NCCL all_gather of the roots, sharded MMR) against the single-GPU build, bit for bit:
+    tools/multigpu_check.py under torchrun on every visible device -- skipped on a one-GPU box"""
+    import os, subprocess, sys
+    ndev = torch.cuda.device_count()
+    if ndev < 2:
+        pytest.skip("needs at least two GPUs")
+    world = 1 << (ndev.bit_length() - 1)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(root, "tools", "multigpu_check.py")], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert '"ok": false' not in r.stdout

@@ -1,3 +1,4 @@
+// EXPERIMENTAL (tools/ab_level.cu -DPMT_QUAD=1 only): the fp64 tensor-pipe form of round 1, bit-exact, not faster.
 // poseidon_quad.cuh -- width-12 Poseidon over Goldilocks, 32 states per WARP, MDS layers on the fp64 tensor pipe (DMMA).
 //
 // Same function as poseidon.cuh's permute_paired ([UPSTREAM plonky2 hash/poseidon.rs Poseidon::poseidon], the
@@ -24,9 +25,9 @@
 // carries y0 = row0(M) s' + c, so one DMMA pass yields z - col0(M) x and y0; the two S-boxes of lane 0 (held by the
 // j = 0 threads for 4 states each) are spread over the quad with warp shuffles so every thread computes one.
 #pragma once
-#include "poseidon.cuh"
+#include "poseidon_variants.cuh"
 
-namespace poseidon {
+namespace poseidonx {
 
 constexpr int QUAD_SLOTS = 2 * PMT_FULL_HALF + PMT_PARTIAL / 2;   // 8 full rounds + 11 pairs
 
@@ -112,7 +113,7 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 __device__ __forceinline__ uint64_t shfl64(uint64_t v, unsigned src) {
-  return gl::pack(__shfl_sync(0xffffffffu, gl::lo32(v), src), __shfl_sync(0xffffffffu, gl::hi32(v), src));
+  return glx::pack(__shfl_sync(0xffffffffu, glx::lo32(v), src), __shfl_sync(0xffffffffu, glx::hi32(v), src));
 }
 
 template <bool COMBINE_ALU>
@@ -129,7 +130,7 @@ __device__ __forceinline__ void quad_mma(const uint64_t (&x)[3], const double (&
   L0[0] = c0.x; L0[1] = c0.y; H0[0] = c1.x; H0[1] = c1.y; L1[0] = c2.x; L1[1] = c2.y; H1[0] = c3.x; H1[1] = c3.y;
 #pragma unroll
   for (int ks = 0; ks < 3; ks++) {
-    const double lo = (double)gl::lo32(x[ks]), hi = (double)gl::hi32(x[ks]);   // I2F.F64.U32 (conversion pipe)
+    const double lo = (double)glx::lo32(x[ks]), hi = (double)glx::hi32(x[ks]);   // I2F.F64.U32 (conversion pipe)
     dmma884(L0[0], L0[1], lo, B[ks][0]);
     dmma884(H0[0], H0[1], hi, B[ks][0]);
     dmma884(L1[0], L1[1], lo, B[ks][1]);
@@ -145,7 +146,7 @@ __device__ __forceinline__ void permute_quad(uint64_t (&e)[4][3], const QuadTabl
 #pragma unroll
   for (int mb = 0; mb < 4; mb++)
 #pragma unroll
-    for (int t = 0; t < 3; t++) e[mb][t] = gl::add_canonical(e[mb][t], T.rc0[j + 4 * t]);
+    for (int t = 0; t < 3; t++) e[mb][t] = glx::add_canonical(e[mb][t], T.rc0[j + 4 * t]);
 #pragma unroll 1
   for (int half = 0; half < 2; half++) {
 #pragma unroll 1
@@ -204,7 +205,7 @@ __device__ __forceinline__ void permute_quad(uint64_t (&e)[4][3], const QuadTabl
 #pragma unroll
         for (int m = 0; m < 4; m++) {
           const uint64_t x = shfl64(v, quad0 | m);
-          const double xlo = (double)gl::lo32(x), xhi = (double)gl::hi32(x);
+          const double xlo = (double)glx::lo32(x), xhi = (double)glx::hi32(x);
           e[m][0] = quad_combine<COMBINE_ALU>(fma(xlo, rk[0], L0[m][0]), fma(xhi, rk[0], H0[m][0]));
           e[m][1] = quad_combine<COMBINE_ALU>(fma(xlo, rk[1], L0[m][1]), fma(xhi, rk[1], H0[m][1]));
           e[m][2] = quad_combine<COMBINE_ALU>(fma(xlo, rk[2], L1[m]), fma(xhi, rk[2], H1[m]));
@@ -214,4 +215,4 @@ __device__ __forceinline__ void permute_quad(uint64_t (&e)[4][3], const QuadTabl
   }
 }
 
-}  // namespace poseidon
+}  // namespace poseidonx

@@ -6,7 +6,8 @@
 #include <vector>
 #include <cuda_runtime.h>
 
-#include "../plonky2_merkle_trees_b200/csrc/poseidon.cuh"
+#include "experimental/poseidon_variants.cuh"
+#include "../plonky2_merkle_trees_b200/csrc/poseidon_coop.cuh"
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "CUDA %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
 
@@ -183,22 +184,22 @@ __global__ void __launch_bounds__(128, MINB) k_perm(const uint64_t* __restrict__
 #pragma unroll
   for (int i = 0; i < 12; i++) s[i] = in[t * 12 + i];
   for (int c = 0; c < chain; c++) {
-    if (VARIANT == 0) poseidon::permute_naive<false>(s);
-    if (VARIANT == 1) poseidon::permute_fast<false, false>(s);
-    if (VARIANT == 2) poseidon::permute_fast<true, false>(s);
-    if (VARIANT == 3) poseidon::permute_fast<true, true>(s);
-    if (VARIANT == 4) poseidon::permute_naive<true>(s);
-    if (VARIANT == 5) poseidon::permute_fast<true, true, 1>(s);
-    if (VARIANT == 6) poseidon::permute_fast<false, false, 1>(s);
-    if (VARIANT == 7) poseidon::permute_fast<false, false, 2>(s);
-    if (VARIANT == 8) poseidon::permute_fast<true, true, 2>(s);
-    if (VARIANT == 10) poseidon::permute_fast<true, true, 2, false, false, true>(s);
-    if (VARIANT == 11) poseidon::permute_fast<true, true, 3>(s);
-    if (VARIANT == 12) poseidon::permute_fast<false, false, 3>(s);
-    if (VARIANT == 9) { s[8] = s[9] = s[10] = s[11] = 0; poseidon::permute_fast<true, true, 2, true, true>(s); }
+    if (VARIANT == 0) poseidonx::permute_naive<false>(s);
+    if (VARIANT == 1) poseidonx::permute_fast<false, false>(s);
+    if (VARIANT == 2) poseidonx::permute_fast<true, false>(s);
+    if (VARIANT == 3) poseidonx::permute_fast<true, true>(s);
+    if (VARIANT == 4) poseidonx::permute_naive<true>(s);
+    if (VARIANT == 5) poseidonx::permute_fast<true, true, 1>(s);
+    if (VARIANT == 6) poseidonx::permute_fast<false, false, 1>(s);
+    if (VARIANT == 7) poseidonx::permute_fast<false, false, 2>(s);
+    if (VARIANT == 8) poseidonx::permute_fast<true, true, 2>(s);
+    if (VARIANT == 10) poseidonx::permute_fast<true, true, 2, false, false, true>(s);
+    if (VARIANT == 11) poseidonx::permute_fast<true, true, 3>(s);
+    if (VARIANT == 12) poseidonx::permute_fast<false, false, 3>(s);
+    if (VARIANT == 9) { s[8] = s[9] = s[10] = s[11] = 0; poseidonx::permute_fast<true, true, 2, true, true>(s); }
   }
 #pragma unroll
-  for (int i = 0; i < 12; i++) out[t * 12 + i] = gl::canonical(s[i]);
+  for (int i = 0; i < 12; i++) out[t * 12 + i] = glx::canonical(s[i]);
 }
 
 // single-warp latency of the cooperative (16 lanes per state) permutation
@@ -209,8 +210,30 @@ __global__ void __launch_bounds__(256) k_perm_coop(const uint64_t* __restrict__ 
   const unsigned g = threadIdx.x & 15, base_lane = threadIdx.x & 16;
   const size_t grp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
   uint64_t v = g < 12 ? in[grp * 12 + g] : 0;
-  for (int c = 0; c < chain; c++) v = poseidon::permute_coop(v, rc_smem, g, base_lane);
-  if (g < 12) out[grp * 12 + g] = gl::canonical(v);
+  for (int c = 0; c < chain; c++) v = poseidonx::permute_coop(v, rc_smem, g, base_lane);
+  if (g < 12) out[grp * 12 + g] = glx::canonical(v);
+}
+
+// the product's cooperative forms (csrc/poseidon_coop.cuh): Quad = four threads per state, eight states per warp;
+// Wide = 16 lanes per state, two states per warp
+template <class Form>
+__global__ void __launch_bounds__(256) k_perm_form(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, int chain) {
+  __shared__ poseidon::coop::Shared<8> sh;
+  const Form t = Form::make(sh);
+  poseidon::coop::stage(sh);
+  const size_t st = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / Form::LANES;
+  uint64_t e[Form::ELEMS];
+  for (int a = 0; a < Form::ELEMS; a++) e[a] = t.elem(a) < 12 ? in[st * 12 + t.elem(a)] : 0;
+  for (int c = 0; c < chain; c++) t.permute(e, sh);
+  for (int a = 0; a < Form::ELEMS; a++) if (t.elem(a) < 12) out[st * 12 + t.elem(a)] = gl::canonical(e[a]);
+}
+// the product's thread-per-state form
+__global__ void __launch_bounds__(128) k_perm_prod(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, int chain) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t s[12];
+  for (int i = 0; i < 12; i++) s[i] = in[t * 12 + i];
+  for (int c = 0; c < chain; c++) poseidon::permute(s);
+  for (int i = 0; i < 12; i++) out[t * 12 + i] = gl::canonical(s[i]);
 }
 
 static float time_ms(cudaEvent_t a, cudaEvent_t b) { float ms; CK(cudaEventElapsedTime(&ms, a, b)); return ms; }
@@ -265,10 +288,10 @@ static void run_perm(const char* name, int sms, int blocks_per_sm, int chain, bo
 }
 
 static void run_latency(int sms) {
-  uint64_t *din, *dout; CK(cudaMalloc(&din, 1 << 20)); CK(cudaMalloc(&dout, 1 << 20));
-  std::vector<uint64_t> h(1 << 17);
+  uint64_t *din, *dout; CK(cudaMalloc(&din, 1 << 23)); CK(cudaMalloc(&dout, 1 << 23));
+  std::vector<uint64_t> h(1 << 20);
   for (size_t i = 0; i < h.size(); i++) h[i] = i;
-  CK(cudaMemcpy(din, h.data(), 1 << 20, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(din, h.data(), 1 << 23, cudaMemcpyHostToDevice));
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   for (int chain : {1, 17}) {
     for (int rep = 0; rep < 3; rep++) {
@@ -282,6 +305,42 @@ static void run_latency(int sms) {
     }
   }
   uint64_t r[4]; CK(cudaMemcpy(r, dout, 32, cudaMemcpyDeviceToHost));
+  // round 2: the Quad and Wide forms against round 1's 16-lane form and the product's thread-per-state form: chains of
+  // dependent permutations on one warp / half a block / one block / one block per SM / three blocks per SM
+  for (int chain : {1, 17}) {
+    float q[5], w[5], tp = 0, l16 = 0;
+    auto T = [&](auto launch) { CK(cudaEventRecord(e0)); launch(); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); return time_ms(e0, e1); };
+    for (int rep = 0; rep < 3; rep++) {
+      q[0] = T([&] { k_perm_form<poseidon::coop::Quad><<<1, 32>>>(din, dout, chain); });
+      q[1] = T([&] { k_perm_form<poseidon::coop::Quad><<<1, 128>>>(din, dout, chain); });
+      q[2] = T([&] { k_perm_form<poseidon::coop::Quad><<<1, 256>>>(din, dout, chain); });
+      q[3] = T([&] { k_perm_form<poseidon::coop::Quad><<<sms, 256>>>(din, dout, chain); });
+      q[4] = T([&] { k_perm_form<poseidon::coop::Quad><<<3 * sms, 256>>>(din, dout, chain); });
+      w[0] = T([&] { k_perm_form<poseidon::coop::Wide><<<1, 32>>>(din, dout, chain); });
+      w[1] = T([&] { k_perm_form<poseidon::coop::Wide><<<1, 128>>>(din, dout, chain); });
+      w[2] = T([&] { k_perm_form<poseidon::coop::Wide><<<1, 256>>>(din, dout, chain); });
+      w[3] = T([&] { k_perm_form<poseidon::coop::Wide><<<sms, 256>>>(din, dout, chain); });
+      w[4] = T([&] { k_perm_form<poseidon::coop::Wide><<<4 * sms, 256>>>(din, dout, chain); });
+      tp = T([&] { k_perm_prod<<<1, 32>>>(din, dout, chain); });
+      l16 = T([&] { k_perm_coop<<<1, 32>>>(din, dout, chain); });
+    }
+    printf("{\"bench\": \"latency_r2\", \"chain\": %d, \"quad_us\": {\"1x32\": %.2f, \"1x128\": %.2f, \"1x256\": %.2f, \"148x256\": %.2f, \"444x256\": %.2f}, "
+           "\"wide_us\": {\"1x32\": %.2f, \"1x128\": %.2f, \"1x256\": %.2f, \"148x256\": %.2f, \"592x256\": %.2f}, \"thread_prod_1warp_us\": %.2f, \"lane16_r1_1warp_us\": %.2f}\n",
+           chain, q[0] * 1e3, q[1] * 1e3, q[2] * 1e3, q[3] * 1e3, q[4] * 1e3, w[0] * 1e3, w[1] * 1e3, w[2] * 1e3, w[3] * 1e3, w[4] * 1e3, tp * 1e3, l16 * 1e3);
+  }
+  // KAT through both forms: perm(0..11)
+  {
+    std::vector<uint64_t> z(12 * 64);
+    for (size_t i = 0; i < z.size(); i++) z[i] = i % 12;
+    CK(cudaMemcpy(din, z.data(), z.size() * 8, cudaMemcpyHostToDevice));
+    const uint64_t want[4] = {0xd64e1e3efc5b8e9eull, 0x53666633020aaa47ull, 0xd40285597c6a8825ull, 0x613a4f81e81231d2ull};
+    k_perm_form<poseidon::coop::Quad><<<1, 256>>>(din, dout, 1);
+    CK(cudaMemcpy(r, dout + 12 * 37, 32, cudaMemcpyDeviceToHost));
+    printf("{\"bench\": \"kat\", \"name\": \"quad\", \"ok\": %s, \"got0\": \"%016llx\"}\n", memcmp(r, want, 32) == 0 ? "true" : "false", (unsigned long long)r[0]);
+    k_perm_form<poseidon::coop::Wide><<<1, 256>>>(din, dout, 1);
+    CK(cudaMemcpy(r, dout + 12 * 11, 32, cudaMemcpyDeviceToHost));
+    printf("{\"bench\": \"kat\", \"name\": \"wide\", \"ok\": %s, \"got0\": \"%016llx\"}\n", memcmp(r, want, 32) == 0 ? "true" : "false", (unsigned long long)r[0]);
+  }
   CK(cudaFree(din)); CK(cudaFree(dout));
 }
 

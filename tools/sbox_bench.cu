@@ -5,12 +5,12 @@
 #include <cstdlib>
 #include <cstdint>
 #include <cuda_runtime.h>
-#include "../plonky2_merkle_trees_b200/csrc/poseidon.cuh"
+#include "experimental/poseidon_variants.cuh"
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "CUDA %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
 
 // MODE 0: pow7_mix<MASK> on LANES independent lanes   1: combine_magic_alu   2: combine_magic_fma
-// 3: mul only (gl::mul<ALU = !(MASK & 1)>)
+// 3: mul only (glx::mul<ALU = !(MASK & 1)>)
 template <int MODE, int MASK, int LANES>
 __global__ void __launch_bounds__(128) k_sbox(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, int iters) {
   uint64_t s[LANES];
@@ -21,12 +21,12 @@ __global__ void __launch_bounds__(128) k_sbox(const uint64_t* __restrict__ in, u
   for (int it = 0; it < iters; it++) {
 #pragma unroll
     for (int i = 0; i < LANES; i++) {
-      if (MODE == 0) s[i] = poseidon::pow7_mix<MASK>(s[i]);
-      if (MODE == 1) s[i] = poseidon::combine_magic_alu(__longlong_as_double((long long)(0x4330000000000000ull | (s[i] >> 14))),
+      if (MODE == 0) s[i] = poseidonx::pow7_mix<MASK>(s[i]);
+      if (MODE == 1) s[i] = poseidonx::combine_magic_alu(__longlong_as_double((long long)(0x4330000000000000ull | (s[i] >> 14))),
                                                          __longlong_as_double((long long)(0x4330000000000000ull | (s[(i + 1) % LANES] >> 13))));
-      if (MODE == 2) s[i] = poseidon::combine_magic_fma(__longlong_as_double((long long)(0x4330000000000000ull | (s[i] >> 14))),
+      if (MODE == 2) s[i] = poseidonx::combine_magic_fma(__longlong_as_double((long long)(0x4330000000000000ull | (s[i] >> 14))),
                                                          __longlong_as_double((long long)(0x4330000000000000ull | (s[(i + 1) % LANES] >> 13))));
-      if (MODE == 3) s[i] = (MASK & 1) ? gl::mul<false>(s[i], s[(i + 1) % LANES]) : gl::mul<true>(s[i], s[(i + 1) % LANES]);
+      if (MODE == 3) s[i] = (MASK & 1) ? glx::mul<false>(s[i], s[(i + 1) % LANES]) : glx::mul<true>(s[i], s[(i + 1) % LANES]);
     }
   }
   uint64_t r = 0;
