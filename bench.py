@@ -229,7 +229,7 @@ def run_reference(args):
 
 def workload_config(n_gpus):
     return {"workload": "plonky2 MerkleTree::new, 2^%d leaves x %d felts per GPU, cap_height %d, upstream digests layout; "
-                        "N GPUs = one tree of N*2^%d leaves, subtree-sharded, NCCL all_gather of the roots" % (
+                        "N GPUs = one tree of N*2^%d leaves, subtree-sharded, ncclAllGather of the roots inside libpmt (pmt_merkle_tree_build_sharded_dev)" % (
                             LOG2_LEAVES_PER_GPU, WIDTH, CAP_HEIGHT, LOG2_LEAVES_PER_GPU),
             "leaves_per_gpu": 1 << LOG2_LEAVES_PER_GPU, "leaf_width": WIDTH, "cap_height": CAP_HEIGHT,
             "global_leaves": n_gpus << LOG2_LEAVES_PER_GPU, "parallelism": "subtree-shard x%d" % n_gpus,
@@ -367,6 +367,8 @@ def run_ours(args):
     pmt_build.build()
     ctx = _lib.Context(local_rank)
     eng = sharded.CudaEngine(ctx)
+    if world > 1:
+        eng.comm_init()      # libpmt's own NCCL communicator: the roots are exchanged by ncclAllGather inside the library call
 
     n_local = 1 << LOG2_LEAVES_PER_GPU
     n_total = world * n_local

@@ -37,6 +37,7 @@ extern "C" {
 #define PMT_E_NOT_POW2 (-2)    /* log2_strict panic: simple_merkle_tree.rs:30, [UPSTREAM] MerkleTree::new */
 #define PMT_E_OOM (-3)
 #define PMT_E_CUDA (-4)
+#define PMT_E_NCCL (-6)  /* libnccl.so.2 not loadable, or an NCCL call failed */
 #define PMT_E_RANGE (-5) /* index assert: simple_merkle_tree.rs:56,77; cap_height > log2 n; MMR leaf >= 2^30 (:264) */
 
 typedef struct pmt_ctx pmt_ctx;
@@ -145,6 +146,34 @@ int pmt_top_levels_dev(pmt_ctx* ctx, const uint64_t* d_roots, size_t n_roots, ui
  * n_roots - 2^h digests apart in d_top_out): the rounds of a subtree-sharded MMR (one mountain per set bit of n) */
 int pmt_top_levels_batch_dev(pmt_ctx* ctx, const uint64_t* d_roots, size_t batch, size_t n_roots, uint32_t cap_height,
                              uint64_t* d_top_out);
+
+/* ---- subtree-sharded MerkleTree::new, device resident ----------------------------------------------------------
+ * (1) ONE PROCESS, several GPUs: n_ctx = 2^g distinct contexts, one per device.  ctx r builds the subtree over ITS leaves
+ * (d_leaves[r]: n / n_ctx rows on ctx r's device) into d_digests[r] (its contiguous slice of upstream's `digests`:
+ * 2 (n / n_ctx - max(1, 2^(h-g))) digests on its device).  cap_height >= g: ctx r's 2^(h-g) cap entries go straight to
+ * d_cap + 4 r 2^(h-g) on ctxs[0]'s device.  Otherwise every ctx stores its subtree root into d_roots + 4 r on ctxs[0]'s
+ * device -- a 32-byte peer-to-peer copy over NVLink on its own stream (cudaMemcpyPeerAsync; peer access is enabled by
+ * the call when the devices allow it) -- ctxs[0]'s stream waits for the n_ctx copies (events, no host sync) and finishes
+ * the g - h levels above the roots into d_top (level-major, n_ctx - 2^h digests; its last 2^h are the cap, also copied to
+ * d_cap).  d_roots (n_ctx digests), d_top and d_cap (2^h digests) live on ctxs[0]'s device.  Only enqueues: the result is
+ * complete after pmt_sync(ctxs[0]) (which orders after every other ctx's work through the events). */
+int pmt_merkle_tree_build_multi_dev(pmt_ctx* const* ctxs, size_t n_ctx, const uint64_t* const* d_leaves, size_t n, size_t width,
+                                    uint32_t cap_height, uint64_t* const* d_digests, uint64_t* d_roots, uint64_t* d_top,
+                                    uint64_t* d_cap);
+/* (2) ONE PROCESS PER GPU: the roots are exchanged with ncclAllGather on the ctx's own stream, inside the library (libnccl.so.2
+ * is loaded with dlopen at pmt_comm_init: libpmt has no link-time NCCL dependency, and a process that already holds an
+ * NCCL -- PyTorch's -- shares it).  pmt_nccl_unique_id: 128 bytes from ncclGetUniqueId, to be created on one rank and
+ * handed to every rank by the host's own means; pmt_comm_init is collective over the `world` ranks (a power of two). */
+int pmt_nccl_unique_id(pmt_ctx* ctx, void* id_out_128_bytes);
+int pmt_comm_init(pmt_ctx* ctx, const void* unique_id_128_bytes, int rank, int world);
+int pmt_comm_destroy(pmt_ctx* ctx);
+/* collective: this rank's n_total / world rows -> d_local_digests (its slice of `digests`).  cap_height >= log2 world: every
+ * rank ends up with the whole cap in d_cap (2^h digests).  Otherwise d_roots (world digests) receives all subtree roots,
+ * d_top (world - 2^h digests, level-major) the levels above them on EVERY rank, d_cap the cap.  One stream, no host sync:
+ * local build -> ncclAllGather (32 bytes per rank over NVLink / NVSwitch) -> top levels. */
+int pmt_merkle_tree_build_sharded_dev(pmt_ctx* ctx, const uint64_t* d_local_leaves, size_t n_total, size_t width,
+                                      uint32_t cap_height, uint64_t* d_local_digests, uint64_t* d_roots, uint64_t* d_top,
+                                      uint64_t* d_cap);
 
 /* ---- MMR: merkle_mountain_ranges.rs ------------------------------------------------------------------------------------ */
 /* number of elements of an MMR with n leaves = 2n - popcount(n) */

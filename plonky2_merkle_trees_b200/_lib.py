@@ -8,7 +8,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.environ.get("PMT_SO", os.path.join(HERE, "libpmt.so"))  # PMT_SO: A/B testing of kernel builds
 
-PMT_OK, PMT_E_INVALID_ARG, PMT_E_NOT_POW2, PMT_E_OOM, PMT_E_CUDA, PMT_E_RANGE = 0, -1, -2, -3, -4, -5
+PMT_OK, PMT_E_INVALID_ARG, PMT_E_NOT_POW2, PMT_E_OOM, PMT_E_CUDA, PMT_E_RANGE, PMT_E_NCCL = 0, -1, -2, -3, -4, -5, -6
 
 u64p = C.POINTER(C.c_uint64)
 u8p = C.POINTER(C.c_uint8)
@@ -54,6 +54,11 @@ _SIGNATURES = {
     "pmt_merkle_tree_build_from_columns_dev": (_INT, [_VP, _VP, _SZ, _SZ, _INT, _U32, _VP, _VP, _VP]),
     "pmt_merkle_prove_dev": (_INT, [_VP, _VP, _SZ, _U32, _VP, _SZ, _VP]),
     "pmt_merkle_verify_dev": (_INT, [_VP, _VP, _SZ, _VP, _SZ, _VP, _U32, _VP, _SZ, _VP]),
+    "pmt_merkle_tree_build_multi_dev": (_INT, [C.POINTER(_VP), _SZ, C.POINTER(_VP), _SZ, _SZ, _U32, C.POINTER(_VP), _VP, _VP, _VP]),  # ctx array first
+    "pmt_nccl_unique_id": (_INT, [_VP, _VP]),
+    "pmt_comm_init": (_INT, [_VP, _VP, _INT, _INT]),
+    "pmt_comm_destroy": (_INT, [_VP]),
+    "pmt_merkle_tree_build_sharded_dev": (_INT, [_VP, _VP, _SZ, _SZ, _U32, _VP, _VP, _VP, _VP]),
     "pmt_top_levels_dev": (_INT, [_VP, _VP, _SZ, _U32, _VP]),
     "pmt_top_levels_batch_dev": (_INT, [_VP, _VP, _SZ, _SZ, _U32, _VP]),
     "pmt_mmr_size": (_SZ, [_SZ]),

@@ -10,7 +10,7 @@ DEPS = SOURCES + [os.path.join(HERE, "csrc", f) for f in
                    "poseidon_freq_constants.cuh", "merkle_kernels.cuh")] + [
     os.path.join(HERE, "..", "include", "pmt.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
-              "-Xcompiler", "-fPIC", "-cudart", "static"]
+              "-Xcompiler", "-fPIC", "-cudart", "static", "-ldl"]
 
 
 def needs_build():

@@ -26,6 +26,15 @@ __device__ __forceinline__ uint64_t pack(uint32_t lo, uint32_t hi) { return ((ui
 
 __device__ __forceinline__ uint64_t canonical(uint64_t x) { return x >= P ? x - P : x; }
 
+// acc + a * b as ONE chained IMAD.WIDE.U32 Rd, Ra, Rb, Rd.  Written as the mad.lo.cc / madc.hi pair because that is the only
+// spelling ptxas 12.9 keeps as an accumulate (plain C is re-associated into independent IMAD.WIDE + IADD3 add trees).  The
+// 64-bit sum must not overflow (callers keep it < 2^63).
+__device__ __forceinline__ uint64_t mad_wide(uint32_t a, uint32_t b, uint64_t acc) {
+  uint32_t lo = (uint32_t)acc, hi = (uint32_t)(acc >> 32);
+  asm("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
+  return ((uint64_t)hi << 32) | lo;
+}
+
 // Signed two-word form of the reduction, ANY 128-bit input (w3:w2:w1:w0):
 //   V = (w0 - w2 - w3) + 2^32 (w1 + w2)   (mod p),   lo = w0 - w2 - w3 in (-2^33, 2^32),  hi = w1 + w2 + (lo >> 32)
 // hi overflows 32 bits by n in {-1, 0, 1}; n 2^64 = n (2^32 - 1) = (n << 32) - n is added in 64-bit arithmetic, which
@@ -44,6 +53,13 @@ __device__ __forceinline__ uint64_t reduce128(u128 v) {
 }
 
 __device__ __forceinline__ uint64_t mul(uint64_t a, uint64_t b) { return reduce128((u128)a * b); }
+
+// l + 2^32 h (mod p) for any l and h < 2^63 (the column sums of the integer MDS rows of the 16-lane form): three words, one reduction
+__device__ __forceinline__ uint64_t combine_sums(uint64_t l, uint64_t h) {
+  const uint64_t mid = (uint64_t)hi32(l) + lo32(h);                   // < 2^33
+  const uint32_t w2 = hi32(h) + hi32(mid);                            // < 2^32: h < 2^63
+  return reduce128_c(lo32(l), lo32(mid), w2, 0u);
+}
 
 // a^2 with THREE IMAD.WIDE instead of four: a0^2 + 2^33 a0 a1 + 2^64 a1^2.  nvcc's (u128)a * a computes a0 a1 twice (the
 // second time as the accumulate that doubles it) and needs an IMAD.X + IMAD.MOV to carry the 65th bit into a1^2; here the

@@ -4,6 +4,8 @@
 #include "merkle_kernels.cuh"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types only: the library is loaded with dlopen (pmt_comm_init), libpmt does not link against NCCL
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -42,6 +44,11 @@ struct pmt_ctx {
   // launch resets its counter); rotating them keeps launches that overlap on different streams apart
   unsigned* tickets = nullptr;
   unsigned ticket_next = 0;
+  // one process per GPU: the NCCL communicator of pmt_comm_init (pmt_merkle_tree_build_sharded_dev)
+  ncclComm_t comm = nullptr;
+  int comm_rank = 0, comm_world = 0;
+  // one process, several GPUs: the event that publishes this ctx's subtree root to ctxs[0] (pmt_merkle_tree_build_multi_dev)
+  cudaEvent_t root_ready = nullptr;
 };
 constexpr unsigned TICKET_RING = 256;
 
@@ -345,6 +352,8 @@ void pmt_destroy(pmt_ctx* c) {
   for (void* p : c->arena) if (p) cudaFree(p);
   for (void* p : c->user_allocs) cudaFree(p);
   if (c->tickets) cudaFree(c->tickets);
+  if (c->comm) pmt_comm_destroy(c);
+  if (c->root_ready) cudaEventDestroy(c->root_ready);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   if (c->copy_in) cudaStreamDestroy(c->copy_in);
   if (c->copy_out) cudaStreamDestroy(c->copy_out);
@@ -666,6 +675,165 @@ int pmt_top_levels_batch_dev(pmt_ctx* c, const uint64_t* d_roots, size_t batch, 
     TopRoots lay{d_roots + 4 * n_roots * b, d_top_out + 4 * (n_roots - n_cap) * b, n_roots, 0, 0};
     if (int rc = launch_level_span(c, lay, 1, levels, 0, n_roots)) return rc;
   }
+  return PMT_OK;
+}
+
+// ---- subtree-sharded MerkleTree::new, device resident ---------------------------------------------------------------------
+static int check_ctxs(pmt_ctx* const* ctxs, size_t n_ctx, const char* who);
+// the validation + local build shared by the two sharded forms: rank r of G = 2^g builds its n / G rows with the local cap
+// height max(h - g, 0); cap entries / the root go to `d_cap_or_root`
+static int sharded_local_build(pmt_ctx* c, const uint64_t* d_local_leaves, size_t n, size_t w, uint32_t cap_height, int g,
+                               uint64_t* d_local_digests, uint64_t* d_cap_or_root) {
+  const size_t per = n >> g;
+  const uint32_t hl = (int)cap_height >= g ? cap_height - (uint32_t)g : 0;
+  return pmt_merkle_tree_build_dev(c, d_local_leaves, per, w, hl, d_local_digests, d_cap_or_root);
+}
+static int sharded_check(pmt_ctx* c, size_t G, size_t n, size_t w, uint32_t cap_height, int* g_out) {
+  const int g = log2_strict(G), lg = log2_strict(n);
+  if (g < 0) return fail(c, PMT_E_NOT_POW2, "sharded build: %zu ranks / contexts is not a power of two", G);
+  if (lg < 0) return fail(c, PMT_E_NOT_POW2, "MerkleTree::new: %zu leaves is not a power of two (log2_strict)", n);
+  if ((int)cap_height > lg) return fail(c, PMT_E_RANGE, "MerkleTree::new: cap_height=%u should be at most log2(leaves.len())=%d", cap_height, lg);
+  if (w == 0) return fail(c, PMT_E_INVALID_ARG, "MerkleTree::new: zero-width leaves");
+  if (g > lg) return fail(c, PMT_E_RANGE, "sharded build: more ranks (%zu) than leaves (%zu)", G, n);
+  *g_out = g;
+  return PMT_OK;
+}
+
+int pmt_merkle_tree_build_multi_dev(pmt_ctx* const* ctxs, size_t n_ctx, const uint64_t* const* d_leaves, size_t n, size_t w,
+                                    uint32_t cap_height, uint64_t* const* d_digests, uint64_t* d_roots, uint64_t* d_top, uint64_t* d_cap) {
+  if (int rc = check_ctxs(ctxs, n_ctx, "multi build")) return rc;
+  pmt_ctx* c0 = ctxs[0];
+  int g = 0;
+  if (int rc = sharded_check(c0, n_ctx, n, w, cap_height, &g)) return rc;
+  if (!d_leaves || !d_digests || !d_cap) return fail(c0, PMT_E_INVALID_ARG, "multi build: null pointer");
+  const bool gather = (int)cap_height < g;
+  if (gather && (!d_roots || (!d_top && n_ctx > 1))) return fail(c0, PMT_E_INVALID_ARG, "multi build: null d_roots / d_top");
+  const size_t cap_l = gather ? 1 : (size_t)1 << (cap_height - (uint32_t)g);
+  for (size_t r = 0; r < n_ctx; r++) {
+    pmt_ctx* c = ctxs[r];
+    if (int rc = bind(c)) return rc;
+    if (c->device != c0->device) {                   // let device r write device 0's memory (NVLink peer access)
+      int can = 0;
+      CU(c, cudaDeviceCanAccessPeer(&can, c->device, c0->device));
+      if (can) {
+        const cudaError_t e = cudaDeviceEnablePeerAccess(c0->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(c0, PMT_E_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", c->device, c0->device, cudaGetErrorString(e));
+        cudaGetLastError();
+      }
+    }
+    // the subtree of ctx r, in its own device memory; its root / cap entries land in a local staging digest first
+    void* stage = nullptr;
+    if (int rc = arena_get(c, 2, 64 * 32 + 64 + cap_l * 32, &stage)) return fail(c0, rc, "multi build: ctx %zu: %.400s", r, c->err);
+    uint64_t* d_mine = (uint64_t*)stage + 64 * 4 + 8;
+    if (int rc = sharded_local_build(c, d_leaves[r], n, w, cap_height, g, d_digests[r], d_mine)) return fail(c0, rc, "multi build: ctx %zu: %.400s", r, c->err);
+    uint64_t* dst = gather ? d_roots + 4 * r : d_cap + 4 * r * cap_l;
+    CU(c, cudaMemcpyPeerAsync(dst, c0->device, d_mine, c->device, cap_l * 32, c->stream));
+    if (!c->root_ready) CU(c, cudaEventCreateWithFlags(&c->root_ready, cudaEventDisableTiming));
+    CU(c, cudaEventRecord(c->root_ready, c->stream));
+  }
+  if (int rc = bind(c0)) return rc;
+  for (size_t r = 1; r < n_ctx; r++) CU(c0, cudaStreamWaitEvent(c0->stream, ctxs[r]->root_ready, 0));
+  if (!gather) return PMT_OK;
+  if (int rc = pmt_top_levels_dev(c0, d_roots, n_ctx, cap_height, d_top)) return rc;
+  const size_t n_cap = (size_t)1 << cap_height;
+  CU(c0, cudaMemcpyAsync(d_cap, d_top + 4 * (n_ctx - 2 * n_cap), n_cap * 32, cudaMemcpyDeviceToDevice, c0->stream));
+  return PMT_OK;
+}
+
+// NCCL, loaded at run time
+namespace {
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+NcclApi* nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+      api.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+      if (api.handle) break;
+    }
+    if (api.handle) {
+      api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.handle, "ncclGetUniqueId");
+      api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.handle, "ncclCommInitRank");
+      api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
+      api.AllGather = (decltype(api.AllGather))dlsym(api.handle, "ncclAllGather");
+      api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
+      api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.GetErrorString;
+    }
+  }
+  return &api;
+}
+}  // namespace
+#define NC(c, call)                                                                                         \
+  do {                                                                                                      \
+    ncclResult_t r_ = (call);                                                                               \
+    if (r_ != ncclSuccess) return fail((c), PMT_E_NCCL, "%s: %s (%s:%d)", #call, nccl_api()->GetErrorString(r_), __FILE__, __LINE__); \
+  } while (0)
+
+int pmt_nccl_unique_id(pmt_ctx* c, void* id_out) {
+  if (!c || !id_out) return PMT_E_INVALID_ARG;
+  NcclApi* a = nccl_api();
+  if (!a->ok) return fail(c, PMT_E_NCCL, "libnccl.so.2 could not be loaded: %s", dlerror() ? dlerror() : "missing symbols");
+  ncclUniqueId id;
+  NC(c, a->GetUniqueId(&id));
+  memcpy(id_out, &id, sizeof id);
+  return PMT_OK;
+}
+int pmt_comm_init(pmt_ctx* c, const void* unique_id, int rank, int world) {
+  if (int rc = bind(c)) return rc;
+  if (!unique_id || world < 1 || rank < 0 || rank >= world) return fail(c, PMT_E_INVALID_ARG, "pmt_comm_init: bad arguments");
+  if (log2_strict((size_t)world) < 0) return fail(c, PMT_E_NOT_POW2, "pmt_comm_init: world size %d is not a power of two", world);
+  NcclApi* a = nccl_api();
+  if (!a->ok) return fail(c, PMT_E_NCCL, "libnccl.so.2 could not be loaded");
+  if (c->comm) pmt_comm_destroy(c);
+  ncclUniqueId id;
+  memcpy(&id, unique_id, sizeof id);
+  NC(c, a->CommInitRank(&c->comm, world, id, rank));
+  c->comm_rank = rank;
+  c->comm_world = world;
+  return PMT_OK;
+}
+int pmt_comm_destroy(pmt_ctx* c) {
+  if (!c) return PMT_E_INVALID_ARG;
+  if (c->comm) {
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    nccl_api()->CommDestroy(c->comm);
+    c->comm = nullptr;
+    c->comm_world = 0;
+  }
+  return PMT_OK;
+}
+
+int pmt_merkle_tree_build_sharded_dev(pmt_ctx* c, const uint64_t* d_local_leaves, size_t n, size_t w, uint32_t cap_height,
+                                      uint64_t* d_local_digests, uint64_t* d_roots, uint64_t* d_top, uint64_t* d_cap) {
+  if (int rc = bind(c)) return rc;
+  if (!c->comm) return fail(c, PMT_E_INVALID_ARG, "sharded build: pmt_comm_init has not been called on this ctx");
+  const size_t G = (size_t)c->comm_world, r = (size_t)c->comm_rank;
+  int g = 0;
+  if (int rc = sharded_check(c, G, n, w, cap_height, &g)) return rc;
+  if (!d_local_leaves || !d_cap) return fail(c, PMT_E_INVALID_ARG, "sharded build: null pointer");
+  NcclApi* a = nccl_api();
+  if ((int)cap_height >= g) {            // every rank yields 2^(h-g) cap entries: gathered in place into d_cap
+    const size_t cap_l = (size_t)1 << (cap_height - (uint32_t)g);
+    if (int rc = sharded_local_build(c, d_local_leaves, n, w, cap_height, g, d_local_digests, d_cap + 4 * r * cap_l)) return rc;
+    if (G > 1) NC(c, a->AllGather(d_cap + 4 * r * cap_l, d_cap, 4 * cap_l, ncclUint64, c->comm, c->stream));
+    return PMT_OK;
+  }
+  if (!d_roots || !d_top) return fail(c, PMT_E_INVALID_ARG, "sharded build: null d_roots / d_top");
+  if (int rc = sharded_local_build(c, d_local_leaves, n, w, cap_height, g, d_local_digests, d_roots + 4 * r)) return rc;
+  NC(c, a->AllGather(d_roots + 4 * r, d_roots, 4, ncclUint64, c->comm, c->stream));
+  if (int rc = pmt_top_levels_dev(c, d_roots, G, cap_height, d_top)) return rc;
+  const size_t n_cap = (size_t)1 << cap_height;
+  CU(c, cudaMemcpyAsync(d_cap, d_top + 4 * (G - 2 * n_cap), n_cap * 32, cudaMemcpyDeviceToDevice, c->stream));
   return PMT_OK;
 }
 

@@ -5,32 +5,34 @@
 // /root/reference/src/mmr/merkle_mountain_ranges.rs:96,111,125,238-249), other mappings.
 //
 // Why.  A tree level with few nodes, a proof path, a peak bag are chains of DEPENDENT permutations: what counts is the
-// latency of one permutation, and a B200 sub-partition issues a warp's instructions essentially one pipe at a time
-// (DESIGN.md 4.2), so that latency is the length of the warp's own instruction stream.  One state per thread: 15.5 k
-// instructions, 33 us for a lone warp.  Two forms split a state over threads; both run the MDS layer on the fp64 pipe
-// like the thread-per-state form: the owner of an element converts its 32-bit halves to doubles (I2F) and publishes them
-// in a per-warp shared-memory exchange buffer, one __syncwarp, and every thread accumulates ITS output rows over the 12
-// published elements, read in ROTATED order (slot i = element (first + i) mod 12; the first elements are stored twice so
-// the rotation needs no address arithmetic) -- with that order the coefficient of slot i is the same for every thread, a
-// uniform operand.  Accumulators start at 2^52 + round constant, so the mantissa is the integer (combine_magic).  The
-// buffer is double-buffered: one __syncwarp per round.
+// latency of one permutation, not the throughput of many.  One state per thread takes a lone warp 33 us (15.5 k
+// instructions).  Two forms split a state over threads (measured on B200, tools/perm_bench.cu lat, profiles/latency_r2*.jsonl):
 //
-//   Quad (4 threads x 3 elements, 8 states per warp): thread j holds elements j, 4 + j, 8 + j.  Three independent S-boxes
-//     per thread in a full round, 72 DFMAs per thread and layer; 870 warp instructions per state -- the THROUGHPUT form of
-//     the cooperative kernels (levels of 2^5 .. 2^13 nodes, proof batches): 0.53 G permutations/s, 11 us per permutation.
-//   Wide (16 lanes x 1 element, 12 used, 2 states per warp): one S-box and 24 DFMAs per lane and round; 1 900 warp
-//     instructions per state but the shortest instruction stream per warp -- the LATENCY form (levels of <= 16 nodes per
-//     block, the top of a tree, bagging): ~5 us per permutation.
-//   (Round 1's 16-lane form used 22 warp shuffles and 24 chained IMAD.WIDE per round: 6.3 us, 2 120 instructions per state.)
+//   Quad (4 threads x 3 elements, 8 states per warp) -- the THROUGHPUT form of the cooperative kernels (levels of 2^5 .. 2^13
+//     nodes, proof batches): thread j holds elements j, 4 + j, 8 + j.  Three independent S-boxes per thread in a full round.
+//     The MDS layer runs on the fp64 pipe like the thread-per-state form: the owner of an element converts its 32-bit halves
+//     to doubles (I2F) and publishes them in a per-warp shared-memory exchange buffer, one __syncwarp, and every thread
+//     accumulates ITS three output rows over the 12 published elements, read in ROTATED order (slot i = element (j + i) mod
+//     12; elements 0..2 are stored twice so the rotation needs no address arithmetic) -- with that order the coefficient of
+//     slot i in row j + 4a is CIRC[(i - 4a) mod 12] for every thread, a uniform operand: 72 DFMAs per thread and layer.
+//     Accumulators start at 2^52 + round constant, so the mantissa is the integer (combine_magic).  The buffer is double-
+//     buffered: one __syncwarp per round; 15 slots per state (odd) keep writes and rotated reads free of bank conflicts.
+//     870 warp instructions per state (round 1's 16-lane form: 2 120), 0.53 G permutations/s, 11 us per permutation.
+//   Wide (16 lanes x 1 element, 12 used, 2 states per warp) -- the LATENCY form (levels of <= 16 nodes per block, the top
+//     of a tree, bagging, small proof batches): everything stays in integer registers, because in a lone warp the fp64 /
+//     shared-memory layer costs ~300 cycles of dependent latency per round (I2F, STS -> LDS, DFMA chains) against ~150 for
+//     22 warp shuffles feeding four independent IMAD.WIDE accumulation chains (column sums < 2^42: no carries) and one
+//     reduction.  An fp64 Wide form was built and measured: 9.4 us per permutation against 6.2 us for round 1's integer form.
 //
-// Partial rounds, both forms: the linear part of lanes 1..11 does not depend on the S-box of lane 0.  The owner of
-// element 0 publishes ZERO for it, every thread accumulates its rows over the other eleven elements while the S-box chain
-// runs (the S-box is written after the barrier so that both land in one basic block and ptxas interleaves them), then
-// x = sbox(s0) is broadcast with two shuffles and enters with the per-thread coefficients M[row][0].
+// Partial rounds, both forms: the linear part of lanes 1..11 does not depend on the S-box of lane 0.  The rows are
+// accumulated over the other eleven elements (the owner of element 0 contributes zero) while the S-box chain runs -- the
+// S-box is written after the exchange so that both land in one basic block and ptxas interleaves them -- then x = sbox(s0)
+// is broadcast with two shuffles and enters with the per-thread coefficients M[row][0]: the round's critical path is the
+// S-box plus a dozen instructions instead of S-box plus layer.
 //
-// Exactness: products of a 32-bit half with a coefficient < 64 summed over 12 lanes plus the diagonal term and a 32-bit
-// constant half stay below 2^42 -- exact in the 53-bit mantissa (the same bound as the matrix-form fp64 layer of round 1);
-// all values are integers, so the order of the additions does not matter.
+// Exactness (Quad): products of a 32-bit half with a coefficient < 64 summed over 12 lanes plus the diagonal term and a
+// 32-bit constant half stay below 2^42 -- exact in the 53-bit mantissa (the same bound as the matrix-form fp64 layer of
+// round 1); all values are integers, so the order of the additions does not matter.
 #pragma once
 #include "poseidon.cuh"
 
@@ -38,14 +40,13 @@ namespace poseidon {
 namespace coop {
 
 constexpr int QUAD_STRIDE = 15;                 // 16-byte slots per state: elements 0..11, then copies of 0..2 (odd: no bank conflicts)
-constexpr int WIDE_STRIDE = 24;                 // elements 0..11 twice
-constexpr int WARP_SLOTS = 8 * QUAD_STRIDE;     // one exchange buffer of one warp (the Wide form uses 2 * 24 of the 120)
+constexpr int WARP_SLOTS = 8 * QUAD_STRIDE;     // one exchange buffer of one warp
 
 template <int WARPS>
 struct alignas(16) Shared {
   double2 xch[WARPS][2][WARP_SLOTS];       // exchange buffers (lo half, hi half of an element as doubles)
-  double rc_dm[2 * WIDTH * PMT_ROUNDS];    // PMT_RC_DM: 2^52 + halves of the constants the layer of round r adds
-  uint64_t rc0[WIDTH];                     // first constant layer
+  double rc_dm[2 * WIDTH * PMT_ROUNDS];    // PMT_RC_DM: 2^52 + halves of the constants the layer of round r adds (Quad)
+  uint64_t rc[WIDTH * (PMT_ROUNDS + 1)];   // PMT_RC: row 0 = the first constant layer, row r + 1 = what round r's layer adds (Wide)
 };
 
 // all threads of the block; ends with a block barrier.  (Per-lane indices into constant memory serialise, but this runs
@@ -53,7 +54,7 @@ struct alignas(16) Shared {
 template <int WARPS>
 __device__ __forceinline__ void stage(Shared<WARPS>& sh) {
   for (int i = threadIdx.x; i < 2 * WIDTH * PMT_ROUNDS; i += blockDim.x) sh.rc_dm[i] = PMT_RC_DM[i];
-  if (threadIdx.x < WIDTH) sh.rc0[threadIdx.x] = PMT_RC[threadIdx.x];
+  for (int i = threadIdx.x; i < WIDTH * (PMT_ROUNDS + 1); i += blockDim.x) sh.rc[i] = PMT_RC[i];
   __syncthreads();
 }
 
@@ -119,7 +120,7 @@ struct Quad {
   template <int WARPS>
   __device__ __forceinline__ void permute(uint64_t (&e)[3], const Shared<WARPS>& sh) const {
 #pragma unroll
-    for (int a = 0; a < 3; a++) e[a] = gl::add_canonical(e[a], sh.rc0[j + 4 * a]);
+    for (int a = 0; a < 3; a++) e[a] = gl::add_canonical(e[a], sh.rc[j + 4 * a]);
     double2* s = slot;
     const double* k = kdm;
     int toggle = WARP_SLOTS;   // s alternates between the two buffers: +WARP_SLOTS, -WARP_SLOTS, ...
@@ -169,28 +170,31 @@ struct Quad {
 };
 
 // ---------------------------------------------------------------------------------------------------------------
-// Wide: lane g of 16 adjacent lanes holds e[0] = element g (g < 12; lanes 12..15 carry nothing and publish nothing)
+// Wide: lane g of 16 adjacent lanes holds e[0] = element g (g < 12; lanes 12..15 carry nothing).  The LATENCY form: what
+// counts is the dependent chain of one round, so everything stays in integer registers -- no conversions, no shared-memory
+// round trip, no fp64 chain (measured: the fp64 / shared-memory layer costs ~300 cycles of latency per round in a lone
+// warp against ~150 for shuffles + IMAD.WIDE): the MDS row of a lane is 11 pairs of warp shuffles feeding four independent
+// IMAD.WIDE accumulation chains (sums < 2^42: no carries), recombined with one reduction.
 // ---------------------------------------------------------------------------------------------------------------
 struct Wide {
   static constexpr int LANES = 16, ELEMS = 1;
-  unsigned g;            // position in the group; g >= 12: idle
+  unsigned g;            // position in the group; g >= 12: idle (mirrors element 0, stores nothing)
+  unsigned gg;           // g for working lanes, 0 for idle ones
   unsigned lane0;        // warp lane of the group's lane 0
-  double2* slot;         // &xch[warp][0][group * 24 + g] (idle lanes: + 0): writes at +0 and +12, reads at +0 .. +11
-  const double* kdm;     // rc_dm + 2 g
-  double c0;             // coefficient of slot 0 (element g) in output row g: 25 on lane 0, 17 elsewhere
-  double cx;             // M[g][0]
+  uint32_t c0;           // coefficient of the lane's own element in its row: C[0] + DIAG[0] = 25 on lane 0, C[0] = 17 elsewhere
+  uint32_t cx;           // M[g][0]: coefficient of element 0 in this lane's row
+  unsigned zero_step;    // the step i at which this lane's rotated read hits element 0 ((12 - g) mod 12)
 
   template <int WARPS>
-  __device__ __forceinline__ static Wide make(Shared<WARPS>& sh) {
+  __device__ __forceinline__ static Wide make(Shared<WARPS>&) {
     Wide t;
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lane = threadIdx.x & 31;
     t.g = lane & 15;
+    t.gg = t.g < WIDTH ? t.g : 0;
     t.lane0 = lane & 16u;
-    const unsigned gg = t.g < WIDTH ? t.g : 0;
-    t.slot = &sh.xch[warp][0][(lane >> 4) * WIDE_STRIDE + gg];
-    t.kdm = sh.rc_dm + 2 * gg;
-    t.c0 = t.g == 0 ? 25.0 : 17.0;
-    t.cx = PMT_MDS_CIRC_D[gg == 0 ? 12 : 12 - gg];
+    t.c0 = t.gg == 0 ? 25u : 17u;
+    t.cx = PMT_MDS_CIRC32[t.gg == 0 ? 12 : 12 - t.gg];
+    t.zero_step = (WIDTH - t.gg) % WIDTH;
     return t;
   }
   __device__ __forceinline__ unsigned elem(int) const { return g; }
@@ -200,53 +204,49 @@ struct Wide {
     return (b & mask) == mask;
   }
 
-  // this lane's row over the 12 published slots: two independent chains per half (the additions are exact integers)
-  __device__ __forceinline__ void row(const double2* __restrict__ rd, const double* __restrict__ k, double& L, double& H) const {
-    const double2 c = *reinterpret_cast<const double2*>(k);
-    double La = c.x, Ha = c.y, Lb = 0.0, Hb = 0.0;
+  // row g of the MDS layer over the state held one element per lane: out = k + sum_i s[(g + i) % 12] C[i] (+ 8 s[0] on lane 0).
+  // SKIP0: element 0 does not take part (partial rounds: it enters later, after its S-box).
+  template <bool SKIP0>
+  __device__ __forceinline__ void row(uint64_t v, uint64_t k, uint64_t& L, uint64_t& H) const {
+    constexpr uint32_t CIRC[WIDTH] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+    const uint32_t lo = gl::lo32(v), hi = gl::hi32(v);
+    const bool own = !(SKIP0 && gg == 0);
+    uint64_t La = gl::mad_wide(own ? lo : 0u, c0, k), Ha = (uint64_t)(own ? hi : 0u) * c0, Lb = 0, Hb = 0;
 #pragma unroll
-    for (int i = 0; i < WIDTH; i += 2) {
-      const double2 v = rd[i], u = rd[i + 1];
-      const double cv = i == 0 ? c0 : PMT_MDS_CIRC_D[i], cu = PMT_MDS_CIRC_D[i + 1];
-      La = fma(v.x, cv, La); Ha = fma(v.y, cv, Ha);
-      Lb = fma(u.x, cu, Lb); Hb = fma(u.y, cu, Hb);
+    for (int i = 1; i < WIDTH; i++) {
+      const unsigned idx = gg + i;
+      const unsigned src = lane0 + (idx >= WIDTH ? idx - WIDTH : idx);
+      uint32_t slo = __shfl_sync(0xffffffffu, lo, src), shi = __shfl_sync(0xffffffffu, hi, src);
+      if (SKIP0 && (unsigned)i == zero_step) { slo = 0; shi = 0; }
+      if (i & 1) { Lb = gl::mad_wide(slo, CIRC[i], Lb); Hb = gl::mad_wide(shi, CIRC[i], Hb); }
+      else       { La = gl::mad_wide(slo, CIRC[i], La); Ha = gl::mad_wide(shi, CIRC[i], Ha); }
     }
     L = La + Lb; H = Ha + Hb;
   }
 
   template <int WARPS>
   __device__ __forceinline__ void permute(uint64_t (&e)[1], const Shared<WARPS>& sh) const {
-    const bool on = g < WIDTH;
-    uint64_t v = on ? gl::add_canonical(e[0], sh.rc0[g]) : 0ull;
-    double2* s = slot;
-    const double* k = kdm;
-    int toggle = WARP_SLOTS;
+    uint64_t v = g < WIDTH ? gl::add_canonical(e[0], sh.rc[gg]) : 0ull;
+    const uint64_t* k = sh.rc + WIDTH + gg;     // the constants the layer of round r adds: row r + 1 of the table
 #pragma unroll 1
     for (int half = 0; half < 2; half++) {
 #pragma unroll 1
       for (int q = 0; q < PMT_FULL_HALF; q++) {
         v = gl::pow7(v);
-        const double2 d = halves(v);
-        if (on) { s[0] = d; s[WIDTH] = d; }
-        __syncwarp();
-        double L, H;
-        row(s, k, L, H);
-        v = combine_magic(L, H);
-        s += toggle; toggle = -toggle; k += 2 * WIDTH;
+        uint64_t L, H;
+        row<false>(v, *k, L, H);                // constants < 2^64 - 2^48, column sums < 2^42: no overflow
+        v = gl::combine_sums(L, H);
+        k += WIDTH;
       }
       if (half == 0) {
 #pragma unroll 1
         for (int p = 0; p < PMT_PARTIAL; p++) {
-          const double2 d = g == 0 ? make_double2(0.0, 0.0) : halves(v);
-          if (on) { s[0] = d; s[WIDTH] = d; }
-          __syncwarp();
-          double L, H;
-          row(s, k, L, H);                              // independent of x: overlaps the S-box chain below
-          const uint64_t x = gl::pow7(v);               // only lane 0's is used
-          const double xl = (double)__shfl_sync(0xffffffffu, gl::lo32(x), lane0);
-          const double xh = (double)__shfl_sync(0xffffffffu, gl::hi32(x), lane0);
-          v = combine_magic(fma(xl, cx, L), fma(xh, cx, H));
-          s += toggle; toggle = -toggle; k += 2 * WIDTH;
+          uint64_t L, H;
+          row<true>(v, *k, L, H);               // everything but element 0: independent of the S-box below, overlaps it
+          const uint64_t x = gl::pow7(v);       // only lane 0's is used
+          const uint32_t xl = __shfl_sync(0xffffffffu, gl::lo32(x), lane0), xh = __shfl_sync(0xffffffffu, gl::hi32(x), lane0);
+          v = gl::combine_sums(gl::mad_wide(xl, cx, L), gl::mad_wide(xh, cx, H));
+          k += WIDTH;
         }
       }
     }

@@ -88,6 +88,31 @@ class MerkleTree:
         ctxs[0].check(rc)
         return digests, cap
 
+    @staticmethod
+    def new_multi_dev(d_leaves_per_ctx, n, cap_height, ctxs):
+        """MerkleTree::new over several GPUs from ONE process, device resident (pmt_merkle_tree_build_multi_dev):
+        d_leaves_per_ctx[r] = the (n / G, width) leaf rows of context r ON ITS DEVICE.  Returns (digest slices per context,
+        d_roots, d_top, d_cap) -- the last three on ctxs[0]'s device; only enqueued: sync ctxs[0] before reading."""
+        import ctypes as C
+        G = len(ctxs)
+        w = d_leaves_per_ctx[0].shape[1]
+        g = G.bit_length() - 1
+        ncap = 1 << cap_height
+        per = n // G
+        local_cap = max(1, ncap // G) if cap_height >= g else 1
+        d_dig = [dev_u64((2 * (per - local_cap), 4), t.device) for t in d_leaves_per_ctx]
+        dev0 = d_leaves_per_ctx[0].device
+        d_roots, d_top, d_cap = dev_u64((G, 4), dev0), dev_u64((max(G - ncap, 1), 4), dev0), dev_u64((ncap, 4), dev0)
+        handles = (C.c_void_p * G)(*[c.h for c in ctxs])
+        leaves = (C.c_void_p * G)(*[t.data_ptr() for t in d_leaves_per_ctx])
+        digs = (C.c_void_p * G)(*[t.data_ptr() for t in d_dig])
+        from .device import order_after_torch
+        for c in ctxs:
+            order_after_torch(c)
+        rc = ctxs[0].lib.pmt_merkle_tree_build_multi_dev(handles, G, leaves, n, w, cap_height, digs, dptr(d_roots), dptr(d_top), dptr(d_cap))
+        ctxs[0].check(rc)
+        return d_dig, d_roots, d_top, d_cap
+
     @property
     def leaves(self):
         return to_host(self.d_leaves)

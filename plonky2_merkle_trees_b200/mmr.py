@@ -167,14 +167,27 @@ class MMR:
             return
         return self.extend_dev(to_device(leaves, self.dev))
 
-    def extend_dev(self, d_leaves):
+    def extend_dev(self, d_leaves, sync=True):
+        """sync=False only enqueues the append on the ctx stream (the sharded build chains further device work behind it)"""
         m = d_leaves.numel()
         if self.n_leaves + m > 1 << 30:
             raise PmtError(_lib.PMT_E_RANGE, "MMR: more than 2^30 leaves (get_mmr_index is i32, merkle_mountain_ranges.rs:264)")
         self._reserve(self.n_leaves + m)
         self.ctx.call("pmt_mmr_extend_dev", dptr(self.d_elements), self.n_leaves, dptr(d_leaves), m)
-        self.ctx.sync()
+        if sync:
+            self.ctx.sync()
         self.n_leaves += m
+
+    def get_peaks_dev(self, out=None):
+        """get_peaks into a device tensor (popcount(n_leaves), 4), enqueued on the ctx stream, no host sync"""
+        k = bin(self.n_leaves).count("1")
+        if out is None:
+            out = dev_u64((max(k, 1), 4), self.dev)
+        if k:
+            import ctypes as C
+            kk = C.c_uint32(0)
+            self.ctx.call("pmt_mmr_peaks_dev", dptr(self.d_elements), self.n_leaves, dptr(out), C.byref(kk))
+        return out[:k]
 
     def add_leaf(self, leaf):
         self.extend([leaf])

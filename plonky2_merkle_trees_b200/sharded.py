@@ -54,6 +54,7 @@ class CudaEngine:
     def __init__(self, ctx):
         self.ctx = ctx
         self.device = torch.device("cuda:%d" % ctx.device)
+        self.has_comm = False
 
     def build_local(self, d_leaves, cap_height):
         n, w = d_leaves.shape
@@ -78,6 +79,36 @@ class CudaEngine:
 
     def sync(self):
         self.ctx.sync()
+
+    def comm_init(self, group=None):
+        """Give the ctx its own NCCL communicator (pmt_comm_init): rank 0 creates the unique id, torch.distributed carries it
+        to the other ranks (plumbing), every rank joins.  After this build_sharded_tree runs as ONE library call on ONE
+        stream: local build -> ncclAllGather of the roots -> top levels."""
+        import ctypes as C
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        buf = (C.c_char * 128)()
+        if rank == 0:
+            self.ctx.call("pmt_nccl_unique_id", C.cast(buf, C.c_void_p))
+        t = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device=self.device)
+        dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        raw = bytes(t.cpu().tolist())
+        self.ctx.call("pmt_comm_init", C.cast(C.create_string_buffer(raw, 128), C.c_void_p), rank, world)
+        self.has_comm = True
+
+    def build_sharded(self, d_local_leaves, n_total, cap_height, world):
+        """pmt_merkle_tree_build_sharded_dev -> (local digests, roots or None, top or None, cap); enqueued only"""
+        per, w = d_local_leaves.shape
+        g = world.bit_length() - 1
+        ncap = 1 << cap_height
+        local_cap = ncap // world if cap_height >= g else 1
+        d_dig = dev_u64((2 * (per - local_cap), 4), self.device)
+        d_roots, d_top = dev_u64((world, 4), self.device), dev_u64((max(world - ncap, 1), 4), self.device)
+        d_cap = dev_u64((ncap, 4), self.device)
+        self.ctx.call("pmt_merkle_tree_build_sharded_dev", dptr(d_local_leaves), n_total, w, cap_height, dptr(d_dig), dptr(d_roots),
+                      dptr(d_top), dptr(d_cap))
+        if cap_height >= g:
+            return d_dig, None, None, d_cap
+        return d_dig, d_roots, d_top[:world - ncap], d_cap
 
     def publish(self):
         """order torch's current stream (the one NCCL synchronises with) after the ctx stream: no host round trip"""
@@ -141,6 +172,9 @@ def build_sharded_tree(d_local_leaves, n_total, cap_height, engine, group=None):
     if d_local_leaves.shape[0] != count:
         raise ValueError("rank %d: expected %d leaf rows, got %d" % (rank, count, d_local_leaves.shape[0]))
     width = d_local_leaves.shape[1]
+    if world > 1 and getattr(engine, "has_comm", False):      # NCCL inside libpmt: one call, one stream, no host sync
+        d_digests, d_roots, d_top, d_cap = engine.build_sharded(d_local_leaves, n_total, cap_height, world)
+        return ShardedMerkleTree(n_total, width, cap_height, world, rank, d_digests, d_roots, d_top, d_cap)
     local_h = max(cap_height - g, 0)
     d_digests, d_local_cap = engine.build_local(d_local_leaves, local_h)
     if world == 1:
@@ -188,6 +222,13 @@ def _cuda_mmr_engine_methods():
 _cuda_mmr_engine_methods()
 
 
+def _host(x):
+    """numpy uint64 view of a digest array that may still live on a device"""
+    if torch.is_tensor(x):
+        return x.detach().cpu().numpy().view(np.uint64)
+    return np.asarray(x, dtype=np.uint64)
+
+
 class ShardedMMR:
     """One rank's part of an MMR over n leaves, G = world size (a power of two).
 
@@ -203,14 +244,36 @@ class ShardedMMR:
                  global positions mmr_pos(level, S_i / 2^level + k))
       tail       MMR over the last < G leaves (last rank only)
       peaks      global get_peaks(): one per round, then the tail's (replicated)
+
+    The build leaves roots, tops and peaks ON THE DEVICE (no host round trip inside build_sharded_mmr); `rounds` and `peaks`
+    download them on first use.
     """
 
-    def __init__(self, n_total, world, rank, plan, local, rounds, tail, peaks, engine):
+    def __init__(self, n_total, world, rank, plan, local, d_roots, d_tops, tail, d_peaks, engine):
         self.n_total, self.world, self.rank, self.plan = n_total, world, rank, plan
-        self.local, self.rounds, self.tail, self.peaks, self.engine = local, rounds, tail, peaks, engine
+        self.local, self.tail, self.engine = local, tail, engine
+        self.d_roots, self.d_tops, self.d_peaks = d_roots, d_tops, d_peaks      # (rounds, G, 4), (rounds, G - 1, 4), (peaks, 4)
+        self._rounds = self._peaks = None
 
     def __len__(self):
         return mmr_size(self.n_total)
+
+    @property
+    def rounds(self):
+        if self._rounds is None:
+            if hasattr(self.engine, "sync"):
+                self.engine.sync()
+            roots, tops = _host(self.d_roots), _host(self.d_tops)
+            self._rounds = [(m, roots[i], np.ascontiguousarray(tops[i])) for i, m in enumerate(self.plan[0])]
+        return self._rounds
+
+    @property
+    def peaks(self):
+        if self._peaks is None:
+            if hasattr(self.engine, "sync"):
+                self.engine.sync()
+            self._peaks = np.ascontiguousarray(_host(self.d_peaks))
+        return self._peaks
 
     def get_peaks(self):
         return self.peaks
@@ -304,9 +367,31 @@ def mmr_shard_ranges(n_total, world, rank):
     return out
 
 
+def _extend_nosync(m, d_leaves):
+    try:
+        m.extend_dev(d_leaves, sync=False)      # the CUDA MMR: enqueue only
+    except TypeError:
+        m.extend_dev(d_leaves)                  # test doubles
+
+
+def _peaks_into(m, out):
+    """the peaks of MMR m into the device rows `out` (k, 4) without a host round trip where the engine can"""
+    if out.shape[0] == 0:
+        return
+    if hasattr(m, "get_peaks_dev"):
+        m.get_peaks_dev(out)
+    else:
+        out.copy_(torch.from_numpy(np.ascontiguousarray(m.get_peaks()).view(np.int64)))
+
+
 def build_sharded_mmr(d_local_leaves, n_total, engine, group=None):
     """Collective over `group`: rank r passes the leaves of mmr_shard_ranges(n_total, world, r), concatenated, as single
-    felts.  Equivalent to n_total calls of MMR::add_leaf (:89-120) on one machine."""
+    felts.  Equivalent to n_total calls of MMR::add_leaf (:89-120) on one machine.
+
+    Everything stays on the device and nothing waits for the host: one batch append builds all of the rank's sub-mountains,
+    their roots (= the local peaks) and the tail's peaks are gathered by a device kernel into one buffer, ONE all_gather moves
+    them, one batched launch finishes the log2 G levels above every round's roots (pmt_top_levels_batch_dev).  The host
+    sees digests only when it asks (ShardedMMR.peaks / .rounds)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     ms, t = mmr_shard_plan(n_total, world)
@@ -316,46 +401,33 @@ def build_sharded_mmr(d_local_leaves, n_total, engine, group=None):
     if d_local_leaves.numel() != want:
         raise ValueError("rank %d: expected %d leaves, got %d" % (rank, want, d_local_leaves.numel()))
     dev = d_local_leaves.device
+    k, n_tail_peaks = len(ms), bin(t).count("1")
+    slots = max(k + n_tail_peaks, 1)
+    mine = torch.zeros((slots, 4), dtype=torch.int64, device=dev)     # [k sub-mountain roots | the tail's peaks (last rank)]
     local = engine.new_mmr()
     if n_main:
-        local.extend_dev(d_local_leaves[:n_main])
-    k = len(ms)
-    my_roots = torch.zeros((max(k, 1), 4), dtype=torch.int64, device=dev)
-    if k:
-        my_roots.copy_(torch.from_numpy(local.get_peaks().view(np.int64)))
+        _extend_nosync(local, d_local_leaves[:n_main])
+        _peaks_into(local, mine[:k])
     tail = None
-    n_tail_peaks = bin(t).count("1")
-    tail_peaks = torch.zeros((max(n_tail_peaks, 1), 4), dtype=torch.int64, device=dev)
     if t and rank == world - 1:
         tail = engine.new_mmr()
-        tail.extend_dev(d_local_leaves[n_main:])
-        tail_peaks.copy_(torch.from_numpy(tail.get_peaks().view(np.int64)))
-    rounds, big = [], []
+        _extend_nosync(tail, d_local_leaves[n_main:])
+        _peaks_into(tail, mine[k:k + n_tail_peaks])
     if world > 1:
-        gathered = torch.empty((world, max(k, 1), 4), dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(gathered.view(world * max(k, 1), 4), my_roots.contiguous(), group=group)
-        if t:
-            src = dist.get_global_rank(group, world - 1) if group is not None else world - 1
-            dist.broadcast(tail_peaks, src=src, group=group)
-        by_round = gathered.permute(1, 0, 2).contiguous()            # (rounds, world, 4)
-        if k and hasattr(engine, "top_levels_batch"):                  # all rounds' finishes in one launch
-            tops = engine.top_levels_batch(by_round)
-            engine.sync()
-            tops_h = tops.cpu().numpy().view(np.uint64)
+        if hasattr(engine, "publish"):
+            engine.publish()                    # NCCL (torch's stream) after the ctx stream: an event, not a host sync
+        gathered = torch.empty((world, slots, 4), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(gathered.view(world * slots, 4), mine, group=group)
+        d_roots = gathered[:, :k].permute(1, 0, 2).contiguous()        # (rounds, world, 4)
+        if k and hasattr(engine, "top_levels_batch"):                    # all rounds' finishes in one launch
+            d_tops = engine.top_levels_batch(d_roots)
+        elif k:
+            d_tops = torch.stack([engine.top_levels(d_roots[i], 0) for i in range(k)])
         else:
-            tops_h = []
-            for i in range(k):
-                t_i = engine.top_levels(by_round[i], 0)
-                engine.sync()
-                tops_h.append(t_i.cpu().numpy().view(np.uint64))
-        roots_h = by_round.cpu().numpy().view(np.uint64)
-        for i, m in enumerate(ms):
-            rounds.append((m, roots_h[i], np.ascontiguousarray(tops_h[i])))
-            big.append(np.ascontiguousarray(tops_h[i])[-1:])
+            d_tops = torch.zeros((0, world - 1, 4), dtype=torch.int64, device=dev)
+        d_peaks = torch.cat([d_tops[:, -1], gathered[world - 1, k:k + n_tail_peaks]], dim=0) if k else gathered[world - 1, k:k + n_tail_peaks]
     else:
-        roots_h = my_roots.cpu().numpy().view(np.uint64)
-        for i, m in enumerate(ms):
-            rounds.append((m, roots_h[i:i + 1], np.zeros((0, 4), np.uint64)))
-            big.append(roots_h[i:i + 1])
-    peaks = np.concatenate(big + [tail_peaks.cpu().numpy().view(np.uint64)[:n_tail_peaks]], axis=0)
-    return ShardedMMR(n_total, world, rank, (ms, t), local, rounds, tail, peaks, engine)
+        d_roots = mine[:k].view(k, 1, 4)
+        d_tops = torch.zeros((k, 0, 4), dtype=torch.int64, device=dev)
+        d_peaks = mine[:k + n_tail_peaks]
+    return ShardedMMR(n_total, world, rank, (ms, t), local, d_roots, d_tops, tail, d_peaks, engine)

@@ -1090,3 +1090,62 @@ def test_multi_gpu_nccl_parity_under_torchrun():
                         "--master-port", "29533", os.path.join(root, "tools", "multigpu_check.py")], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert '"ok": false' not in r.stdout
+
+
+@pytest.mark.parametrize("lg,w,h,G", [(10, 4, 0, 8), (10, 4, 1, 4), (10, 4, 3, 8), (9, 135, 4, 8), (8, 4, 5, 8), (6, 1, 0, 2), (5, 4, 0, 1),
+                                      (15, 7, 0, 4), (16, 4, 2, 2)])
+def test_multi_context_device_resident_build_with_peer_copies(ctx_pool, api, oracle, lg, w, h, G):
+    """pmt_merkle_tree_build_multi_dev: every context builds its subtree from leaves on ITS device, the roots (or cap
+    entries) travel with cudaMemcpyPeerAsync to ctxs[0]'s device, ctxs[0]'s stream waits on the other streams' events and
+    finishes the top.  Slices, roots, top levels and cap against the oracle (on a one-GPU box the contexts share cuda:0)."""
+    from plonky2_merkle_trees_b200 import sharded
+    from plonky2_merkle_trees_b200.device import to_device, to_host
+    n = 1 << lg
+    rows = splitmix_felts(900 + lg + w + h + G, n * w).reshape(n, w)
+    ctxs = ctx_pool[:G]
+    per = n // G
+    d_leaves = [to_device(rows[r * per:(r + 1) * per], "cuda:%d" % c.device) for r, c in enumerate(ctxs)]
+    for rep in range(2):      # the second call reuses the events and staging
+        d_dig, d_roots, d_top, d_cap = api.mt.MerkleTree.new_multi_dev(d_leaves, n, h, ctxs)
+        ctxs[0].sync()
+    for c in ctxs:
+        c.sync()
+    odg, ocap = oracle.merkle_tree_new(rows, h, threads=4, fast=True)
+    assert np.array_equal(to_host(d_cap), ocap)
+    g = G.bit_length() - 1
+    chunks = [to_host(t) for t in d_dig]
+    if h >= g:
+        t = sharded.ShardedMerkleTree(n, w, h, G, 0, None, None, None, to_host(d_cap))
+    else:
+        t = sharded.ShardedMerkleTree(n, w, h, G, 0, None, to_host(d_roots), to_host(d_top)[:G - (1 << h)], to_host(d_cap))
+    assert np.array_equal(t.assemble_global(chunks), odg)
+
+
+def test_sharded_build_with_nccl_inside_the_library_world_of_one(ctx, api, oracle):
+    """pmt_nccl_unique_id / pmt_comm_init / pmt_merkle_tree_build_sharded_dev with a communicator of ONE rank (the box the
+    driver tests on has one GPU; tools/multigpu_check.py and bench.py --gpus N run the same call over 2 .. 8 ranks): libnccl
+    is loaded with dlopen, the communicator hangs off the ctx, the build equals the plain one."""
+    import ctypes as C
+    from plonky2_merkle_trees_b200 import _lib
+    from plonky2_merkle_trees_b200.device import dev_u64, dptr, to_device, to_host
+    c = _lib.Context(0)
+    try:
+        uid = C.create_string_buffer(128)
+        c.call("pmt_nccl_unique_id", C.cast(uid, C.c_void_p))
+        assert any(uid.raw)
+        c.call("pmt_comm_init", C.cast(uid, C.c_void_p), 0, 1)
+        for lg, w, h in [(10, 4, 0), (9, 9, 3), (14, 4, 0)]:
+            n = 1 << lg
+            rows = splitmix_felts(lg + w + h, n * w).reshape(n, w)
+            d_dig, d_roots, d_top, d_cap = dev_u64((2 * (n - (1 << h)), 4), "cuda:0"), dev_u64((1, 4), "cuda:0"), dev_u64((1, 4), "cuda:0"), dev_u64((1 << h, 4), "cuda:0")
+            c.call("pmt_merkle_tree_build_sharded_dev", dptr(to_device(rows, "cuda:0")), n, w, h, dptr(d_dig), dptr(d_roots), dptr(d_top), dptr(d_cap))
+            c.sync()
+            odg, ocap = oracle.merkle_tree_new(rows, h, threads=4, fast=True)
+            assert np.array_equal(to_host(d_dig), odg) and np.array_equal(to_host(d_cap), ocap)
+        with pytest.raises(_lib.PmtError):
+            c.call("pmt_comm_init", C.cast(uid, C.c_void_p), 0, 3)       # not a power of two
+        c.call("pmt_comm_destroy")
+        with pytest.raises(_lib.PmtError):                               # no communicator any more
+            c.call("pmt_merkle_tree_build_sharded_dev", dptr(d_dig), 1 << 10, 4, 0, dptr(d_dig), dptr(d_roots), dptr(d_top), dptr(d_cap))
+    finally:
+        c.close()

@@ -34,11 +34,19 @@ def main():
     eng = sharded.CudaEngine(ctx)
     ok_all = True
     cases = [(14, 4, 0), (14, 1, 0), (12, 135, 4), (13, 9, 1), (16, 4, 5), (10, 4, 3)]
-    for lg, w, h in cases:
+    # every case twice: the roots exchanged by torch.distributed's all_gather (plumbing in Python), then by ncclAllGather inside
+    # libpmt on the ctx's own stream (pmt_comm_init + pmt_merkle_tree_build_sharded_dev: one call, no host sync)
+    for lg, w, h, in_lib in [c + (False,) for c in cases] + [c + (True,) for c in cases]:
+        if in_lib and not eng.has_comm:
+            eng.comm_init()
+        eng_used = eng
+        if not in_lib:
+            eng_used = sharded.CudaEngine(ctx)          # same ctx, no communicator: the torch path
         n = 1 << lg
         per = n // world
         d_local = bench.splitmix_torch(rank * per * w, per * w, dev).view(per, w)
-        tree = sharded.build_sharded_tree(d_local, n, h, eng)
+        tree = sharded.build_sharded_tree(d_local, n, h, eng_used)
+        eng.sync()
         chunk = tree.local_digests.contiguous()
         chunks = [torch.empty_like(chunk) for _ in range(world)] if rank == 0 else None
         dist.gather(chunk, chunks, dst=0)
@@ -50,6 +58,7 @@ def main():
             ok = bool(np.array_equal(got, ref.digests) and np.array_equal(cap, ref.cap))
             ok_all &= ok
             print(json.dumps({"check": "sharded_vs_single", "world": world, "log2_n": lg, "width": w, "cap_height": h,
+                              "roots_exchange": "ncclAllGather inside libpmt" if in_lib else "torch.distributed all_gather",
                               "digests": int(got.shape[0]), "ok": ok}), flush=True)
     # ---- sharded MMR (balanced rounds + tail) against one MMR built on rank 0's GPU ------------------------------------
     from plonky2_merkle_trees_b200 import mmr
