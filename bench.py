@@ -462,6 +462,45 @@ def run_ours(args):
     if prev_affinity is not None:
         os.sched_setaffinity(0, prev_affinity)
 
+    # ---- the same call from the host memory a real caller has (N = 1 only: one more PCIe user per rank changes nothing) -------
+    # pinned (above) is the best case.  A Rust Vec / malloc is PAGEABLE: libpmt then stages the chunks through its own
+    # page-locked slots with a few copy threads.  The same pageable buffers page-locked once with pmt_host_register behave
+    # like pinned ones.  And the C++ host mirror (include/pmt.hpp: Vec<Vec<F>> in, Vec<HashOut> out -- the conversions the
+    # Rust shim of INTEGRATION.md makes) is timed as a whole call by tools/mirror_bench.cpp.
+    e2e_kinds = None
+    if world == 1:
+        def time_host_call(p_leaves, p_dig, p_cap, reps=3):
+            ts = []
+            for _ in range(reps + 1):
+                ctx.sync(); t0 = time.perf_counter()
+                ctx.call("pmt_merkle_tree_build", C.cast(p_leaves, u64p), n_local, WIDTH, CAP_HEIGHT, C.cast(p_dig, u64p), C.cast(p_cap, u64p))
+                ts.append(time.perf_counter() - t0)
+            return 1e3 * sorted(ts[1:])[len(ts[1:]) // 2]
+        pg_l = h_leaves.numpy().copy()
+        pg_d = np.empty((n_dig, 4), np.int64); pg_c = np.empty((1, 4), np.int64)
+        pageable_ms = time_host_call(pg_l.ctypes.data, pg_d.ctypes.data, pg_c.ctypes.data)
+        pageable_ok = bool(np.array_equal(pg_d[::4099], h_digests.numpy()[::4099]) and np.array_equal(pg_c, h_cap.numpy()))
+        t0 = time.perf_counter()
+        ctx.call("pmt_host_register", C.c_void_p(pg_l.ctypes.data), pg_l.nbytes)
+        ctx.call("pmt_host_register", C.c_void_p(pg_d.ctypes.data), pg_d.nbytes)
+        register_ms = 1e3 * (time.perf_counter() - t0)
+        registered_ms = time_host_call(pg_l.ctypes.data, pg_d.ctypes.data, pg_c.ctypes.data)
+        ctx.call("pmt_host_unregister", C.c_void_p(pg_l.ctypes.data)); ctx.call("pmt_host_unregister", C.c_void_p(pg_d.ctypes.data))
+        del pg_l, pg_d
+        e2e_kinds = {"pinned_ms": e2e_ms, "pageable_ms": pageable_ms, "pageable_equals_pinned": pageable_ok,
+                     "registered_ms": registered_ms, "register_once_ms": register_ms,
+                     "pageable_how": "pageable caller buffers are staged through libpmt's own page-locked slots by copy threads "
+                                     "(host memcpy of 1.5 GiB is the bound); pmt_host_register / pmt_host_alloc remove the staging"}
+        mirror = os.path.join(ROOT, "tools", "_ab", "mirror_bench")
+        if os.path.exists(mirror):
+            try:
+                r = subprocess.run([mirror, str(LOG2_LEAVES_PER_GPU), "2"], capture_output=True, text=True, timeout=300)
+                m = json.loads(r.stdout.strip().splitlines()[-1])
+                e2e_kinds["cpp_mirror"] = {"api": m["mirror"], "ms": m["ms_median"], "c_abi_on_its_pageable_vectors_ms": m["c_abi_on_pageable_vectors_ms_median"],
+                                           "root": m["root"], "leaves_per_s": n_local / (m["ms_median"] * 1e-3)}
+            except Exception as e:      # the mirror is an extra figure, not the product path
+                e2e_kinds["cpp_mirror"] = {"error": str(e)[:200]}
+
     # ---- parity of what was just measured, against the oracle, in this run ------------------------------------------------
     # rank 0 rebuilds ITS WHOLE 2^24-leaf tree on the host cores (this is also the cpu_baseline measurement) and compares all
     # 2^25 - 2 digests the e2e call left in host memory; the other ranks compare the subtree over their first 2^16 leaves;
@@ -484,6 +523,11 @@ def run_ours(args):
         ok &= bool(np.array_equal(dev_slice, odg[:dev_slice.shape[0]]))
         ok &= bool(np.array_equal(dev_root if world == 1 else dev_roots[0:1], ocap))
         checked += odg.shape[0] + 1 + dev_slice.shape[0] + 1
+        if e2e_kinds is not None:
+            ok &= e2e_kinds["pageable_equals_pinned"]
+            if "root" in e2e_kinds.get("cpp_mirror", {}):
+                e2e_kinds["cpp_mirror"]["root_equals_oracle"] = [int(x) for x in ocap[0]] == e2e_kinds["cpp_mirror"].pop("root")
+                ok &= e2e_kinds["cpp_mirror"]["root_equals_oracle"]
         del odg
     else:
         _, _, _, odg, ocap = cpu_tree(PAR_LOG2, rank * n_local, threads=2)
@@ -562,7 +606,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "leaves/s", "h2d_bytes_per_step": n_local * WIDTH * 8,
                 "d2h_bytes_per_step": (n_dig + 1) * 32, "ms_per_step": e2e_ms,
                 "api": "pmt_merkle_tree_build (host buffers, pinned; every digest downloaded)",
-                "host_numa_node": numa_node},
+                "host_numa_node": numa_node, "host_memory_kinds": e2e_kinds},
         "gpu_launches": launches,
         "kernels": prof,
         "roofline": roofline,

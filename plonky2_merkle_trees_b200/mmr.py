@@ -136,6 +136,7 @@ class MMR:
         self.n_leaves = 0
         self._cap_leaves = 0
         self.d_elements = None
+        self._pending = False     # an append was only enqueued (extend_dev(sync=False)): sync before torch reads d_elements
 
     @classmethod
     def new(cls, ctx=None):
@@ -144,16 +145,23 @@ class MMR:
     def __len__(self):
         return 2 * self.n_leaves - bin(self.n_leaves).count("1")
 
+    def _settle(self):
+        if self._pending:
+            self.ctx.sync()
+            self._pending = False
+
     @property
     def elements(self):
         """Vec<HashOut>: (len, 4) u64, post-order."""
         if self.n_leaves == 0:
             return np.zeros((0, 4), np.uint64)
+        self._settle()
         return to_host(self.d_elements[:len(self)])
 
     def _reserve(self, n_total):
         if n_total <= self._cap_leaves:
             return
+        self._settle()
         cap = max(self.GROW, 1 << (n_total - 1).bit_length())
         new = dev_u64((2 * cap, 4), self.dev)
         if self.n_leaves:
@@ -176,6 +184,7 @@ class MMR:
         self.ctx.call("pmt_mmr_extend_dev", dptr(self.d_elements), self.n_leaves, dptr(d_leaves), m)
         if sync:
             self.ctx.sync()
+        self._pending = not sync
         self.n_leaves += m
 
     def get_peaks_dev(self, out=None):

@@ -425,6 +425,8 @@ def build_sharded_mmr(d_local_leaves, n_total, engine, group=None):
             d_tops = torch.stack([engine.top_levels(d_roots[i], 0) for i in range(k)])
         else:
             d_tops = torch.zeros((0, world - 1, 4), dtype=torch.int64, device=dev)
+        if hasattr(engine, "publish"):
+            engine.publish()                    # the tops were written on the ctx stream; torch's stream reads them next
         d_peaks = torch.cat([d_tops[:, -1], gathered[world - 1, k:k + n_tail_peaks]], dim=0) if k else gathered[world - 1, k:k + n_tail_peaks]
     else:
         d_roots = mine[:k].view(k, 1, 4)

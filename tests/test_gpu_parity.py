@@ -1087,7 +1087,7 @@ def test_multi_gpu_nccl_parity_under_torchrun():
     world = 1 << (ndev.bit_length() - 1)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
-                        "--master-port", "29533", os.path.join(root, "tools", "multigpu_check.py")], capture_output=True, text=True, timeout=900)
+                        "--master-port", "29533", os.path.join(root, "tools", "multigpu_check.py")], capture_output=True, text=True, timeout=400)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert '"ok": false' not in r.stdout
 

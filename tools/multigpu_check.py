@@ -29,7 +29,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    dist.init_process_group("nccl", device_id=dev)
+    import datetime
+    import faulthandler
+    faulthandler.dump_traceback_later(150, exit=True)       # a hung collective shows where, and costs 150 s, not the NCCL timeout
+    dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     ctx = _lib.Context(local_rank)
     eng = sharded.CudaEngine(ctx)
     ok_all = True
@@ -97,6 +100,7 @@ def main():
     flag = torch.tensor([1 if ok_all else 0], device=dev)
     dist.broadcast(flag, 0)
     dist.destroy_process_group()
+    faulthandler.cancel_dump_traceback_later()
     return 0 if int(flag.item()) else 1
 
 
