@@ -572,12 +572,23 @@ def run_ours(args):
     mac32 = perms_per_s * MAC32_PER_PERM
     hbm_gbs = perms_per_s * ALG_BYTES_PER_PERM / 1e9
     total_prof_ms = sum(v["ms"] for v in prof.values()) or 1.0
+    # traffic / hardware view: one `ncu --set full` capture of this kernel (profiles/ncu_k_level_r2.json, written by
+    # tools/ncu_summarize.py), scaled to the average launch of this run -- but only while the kernel sources are still the
+    # ones that were profiled (tools/kernel_hash.py): a changed kernel prints null, not a stale figure
     traffic, hardware = None, None
-    try:   # one `ncu --set full` capture of this kernel (profiles/), scaled to the average launch of this run
-        with open(os.path.join(ROOT, "profiles", "ncu_traffic_r1c.json")) as f:
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        from kernel_hash import kernel_sources_hash
+        with open(os.path.join(ROOT, "profiles", "ncu_k_level_r2.json")) as f:
             cap = json.load(f)
-        traffic = cap.get("k_level_dram_bytes_per_permutation") * lvl["units"] / max(lvl["launches"], 1)
-        hardware = dict(cap.get("hardware_view", {}), source="profiles/k_level_r1c_summary.txt (ncu --set full, not this run)")
+        if cap.get("kernel_sources_sha16") == kernel_sources_hash():
+            per_perm = (cap["dram_bytes_read"] + cap["dram_bytes_write"]) / cap["permutations_in_launch"]
+            traffic = per_perm * lvl["units"] / max(lvl["launches"], 1)
+            hardware = dict(cap.get("hardware_view", {}), dram_bytes_per_permutation=per_perm,
+                            source="profiles/%s (ncu --set full, kernel sources %s = this tree)" % (cap.get("summary", "k_level_r2_summary.txt"), cap["kernel_sources_sha16"]))
+        else:
+            hardware = {"stale": "profiles/ncu_k_level_r2.json was captured for kernel sources %s, this tree is %s" % (
+                cap.get("kernel_sources_sha16"), kernel_sources_hash())}
     except Exception:
         pass
     roofline = {

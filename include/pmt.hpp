@@ -19,10 +19,15 @@
 // reference (log2_strict, index asserts, the assert! in MMR_proof::verify) is a pmt::Error here.  Header-only; link
 // with -lpmt.  There is no CPU fallback: Engine's constructor throws when libpmt finds no CUDA device.
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cstdint>
+#include <exception>
 #include <stdexcept>
+#include <memory>
 #include <string>
+#include <thread>
+#include <type_traits>
 #include <utility>
 #include <vector>
 
@@ -32,12 +37,29 @@ namespace pmt {
 
 using F = uint64_t;  // GoldilocksField(u64): any u64 on input, canonical on output
 
-struct HashOut {  // plonky2 HashOut<GoldilocksField>
-  std::array<F, 4> elements{};
+struct HashOut {  // plonky2 HashOut<GoldilocksField>.  Trivial: `HashOut h{}` is zero, `HashOut h;` is filled by the next call
+  std::array<F, 4> elements;
   bool operator==(const HashOut& o) const { return elements == o.elements; }
   bool operator!=(const HashOut& o) const { return !(*this == o); }
 };
 static_assert(sizeof(HashOut) == 32, "a digest is 4 consecutive u64 in every libpmt buffer");
+
+// Vec<HashOut> for the big outputs (1 GiB of digests for 2^24 leaves).  std::vector::resize would write zeros into every
+// element libpmt is about to overwrite -- a serial pass over fresh pages that costs more than the GPU build.  This allocator
+// default-initialises instead (the C++ stand-in for Rust's Vec::with_capacity + set_len after the FFI call has filled it).
+template <class T>
+struct NoInitAlloc : std::allocator<T> {
+  template <class U> struct rebind { using other = NoInitAlloc<U>; };
+  NoInitAlloc() = default;
+  template <class U> NoInitAlloc(const NoInitAlloc<U>&) {}
+  template <class U> void construct(U* p) noexcept { ::new (static_cast<void*>(p)) U; }
+  template <class U, class... A> void construct(U* p, A&&... a) { ::new (static_cast<void*>(p)) U(std::forward<A>(a)...); }
+};
+using Digests = std::vector<HashOut, NoInitAlloc<HashOut>>;
+template <class A, class B>
+typename std::enable_if<!std::is_same<A, B>::value, bool>::type operator==(const std::vector<HashOut, A>& x, const std::vector<HashOut, B>& y) {
+  return x.size() == y.size() && std::equal(x.begin(), x.end(), y.begin());
+}
 
 struct Error : std::runtime_error {
   int code;
@@ -83,8 +105,28 @@ class Engine {
 };
 
 namespace detail {
-inline const uint64_t* words(const std::vector<HashOut>& v) { return reinterpret_cast<const uint64_t*>(v.data()); }
-inline uint64_t* words(std::vector<HashOut>& v) { return reinterpret_cast<uint64_t*>(v.data()); }
+template <class A> inline const uint64_t* words(const std::vector<HashOut, A>& v) { return reinterpret_cast<const uint64_t*>(v.data()); }
+template <class A> inline uint64_t* words(std::vector<HashOut, A>& v) { return reinterpret_cast<uint64_t*>(v.data()); }
+// Vec<Vec<F>> -> one row-major array, by a few threads (16 M four-felt rows scattered over the heap: 170 ms on one thread)
+inline std::vector<F, NoInitAlloc<F>> flatten(const std::vector<std::vector<F>>& rows, size_t w) {
+  const size_t n = rows.size();
+  std::vector<F, NoInitAlloc<F>> flat(n * w);
+  auto part = [&](size_t a, size_t b) {
+    for (size_t i = a; i < b; i++) {
+      if (rows[i].size() != w) throw Error(PMT_E_INVALID_ARG, "MerkleTree::new: ragged leaves");
+      std::copy(rows[i].begin(), rows[i].end(), flat.begin() + i * w);
+    }
+  };
+  unsigned t = n * w >= (size_t(1) << 20) ? std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2)) : 1;
+  if (t <= 1) { part(0, n); return flat; }
+  std::vector<std::thread> pool;
+  std::vector<std::exception_ptr> err(t);
+  for (unsigned k = 0; k < t; k++)
+    pool.emplace_back([&, k] { try { part(n * k / t, n * (k + 1) / t); } catch (...) { err[k] = std::current_exception(); } });
+  for (auto& th : pool) th.join();
+  for (auto& e : err) if (e) std::rethrow_exception(e);
+  return flat;
+}
 inline unsigned popcount(uint64_t x) { return (unsigned)__builtin_popcountll(x); }
 inline bool is_pow2(size_t n) { return n && !(n & (n - 1)); }
 inline unsigned log2_strict(size_t n) {
@@ -289,7 +331,7 @@ struct MerkleProof { std::vector<HashOut> siblings; };
 
 struct MerkleTree {
   std::vector<std::vector<F>> leaves;
-  std::vector<HashOut> digests;  // upstream's layout: per cap subtree, left subtree || left digest || right digest || right subtree
+  Digests digests;  // upstream's layout: per cap subtree, left subtree || left digest || right digest || right subtree
   MerkleCap cap;
 
   // [UPSTREAM] MerkleTree::new(leaves, cap_height)
@@ -298,12 +340,7 @@ struct MerkleTree {
     const unsigned log2n = detail::log2_strict(n);
     if (cap_height > log2n) throw Error(PMT_E_RANGE, "cap_height " + std::to_string(cap_height) + " > log2(leaves.len())");
     const size_t w = leaves[0].size();
-    std::vector<F> flat;
-    flat.reserve(n * w);
-    for (const auto& row : leaves) {
-      if (row.size() != w) throw Error(PMT_E_INVALID_ARG, "MerkleTree::new: ragged leaves");
-      flat.insert(flat.end(), row.begin(), row.end());
-    }
+    const auto flat = detail::flatten(leaves, w);
     MerkleTree t;
     t.digests.resize(2 * (n - (size_t(1) << cap_height)));
     t.cap.hashes.resize(size_t(1) << cap_height);
@@ -322,12 +359,7 @@ struct MerkleTree {
     const unsigned log2n = detail::log2_strict(n);
     if (cap_height > log2n) throw Error(PMT_E_RANGE, "cap_height " + std::to_string(cap_height) + " > log2(leaves.len())");
     const size_t w = leaves[0].size();
-    std::vector<F> flat;
-    flat.reserve(n * w);
-    for (const auto& row : leaves) {
-      if (row.size() != w) throw Error(PMT_E_INVALID_ARG, "MerkleTree::new: ragged leaves");
-      flat.insert(flat.end(), row.begin(), row.end());
-    }
+    const auto flat = detail::flatten(leaves, w);
     std::vector<pmt_ctx*> ctxs;
     for (const Engine* e : engines) ctxs.push_back(e ? e->ctx() : nullptr);
     MerkleTree t;

@@ -1334,20 +1334,47 @@ static int mmr_extend_host(pmt_ctx* c, uint64_t* elements, size_t n0, const uint
   // first piece: up to the next multiple of `chunk` so that every later piece is an aligned perfect sub-mountain
   const size_t chunks = (m + chunk - 1) / chunk + 1;
   if (int rc = pipeline_streams(c, chunks)) return rc;
-  size_t done = 0, i = 0;
+  // pageable caller buffers go through the ctx's page-locked slots and copy threads, as in pmt_merkle_tree_build
+  const size_t out_slot_bytes = (2 * chunk + 64) * 32;       // a piece of <= chunk leaves creates < 2 chunk + 64 elements
+  const bool in_staged = is_pageable(new_leaves), out_staged = is_pageable(elements);
+  void *si[2] = {nullptr, nullptr}, *so[2] = {nullptr, nullptr};
+  if (in_staged) for (int k = 0; k < 2; k++) if (int rc = stage_get(c, k, chunk * 8, &si[k])) return rc;
+  if (out_staged) for (int k = 0; k < 2; k++) if (int rc = stage_get(c, 2 + k, out_slot_bytes, &so[k])) return rc;
+  cudaEvent_t* ev_out = c->ev.data() + 2 * chunks + 2;
+  size_t done = 0, i = 0, prev_p0 = 0, prev_bytes = 0;
   while (done < m) {
     size_t len = chunk - ((n0 + done) & (chunk - 1));     // to the next chunk boundary
     if (len > m - done) len = m - done;
-    CU(c, cudaMemcpyAsync(d_leaves + done, new_leaves + done, len * 8, cudaMemcpyHostToDevice, c->copy_in));
+    const uint64_t* src = new_leaves + done;
+    if (in_staged) {
+      if (i >= 2) CU(c, cudaEventSynchronize(c->ev[2 * (i - 2)]));
+      c->pool->copy(si[i & 1], src, len * 8);
+      src = (const uint64_t*)si[i & 1];
+    }
+    CU(c, cudaMemcpyAsync(d_leaves + done, src, len * 8, cudaMemcpyHostToDevice, c->copy_in));
     CU(c, cudaEventRecord(c->ev[2 * i], c->copy_in));
     CU(c, cudaStreamWaitEvent(c->stream, c->ev[2 * i], 0));
     if (int rc = mmr_extend_plan(c, lay, n0 + done, d_leaves + done, len)) return rc;
     CU(c, cudaEventRecord(c->ev[2 * i + 1], c->stream));
     CU(c, cudaStreamWaitEvent(c->copy_out, c->ev[2 * i + 1], 0));
     const size_t p0 = pmt_mmr_size(n0 + done), p1 = pmt_mmr_size(n0 + done + len);
-    CU(c, cudaMemcpyAsync(elements + 4 * p0, d_new + 4 * (p0 - s0), (p1 - p0) * 32, cudaMemcpyDeviceToHost, c->copy_out));
+    if (out_staged) {
+      CU(c, cudaMemcpyAsync(so[i & 1], d_new + 4 * (p0 - s0), (p1 - p0) * 32, cudaMemcpyDeviceToHost, c->copy_out));
+      CU(c, cudaEventRecord(ev_out[i], c->copy_out));
+      if (i >= 1) {      // drain the previous piece while this one is hashed
+        CU(c, cudaEventSynchronize(ev_out[i - 1]));
+        c->pool->copy(elements + 4 * prev_p0, so[(i - 1) & 1], prev_bytes);
+      }
+      prev_p0 = p0; prev_bytes = (p1 - p0) * 32;
+    } else {
+      CU(c, cudaMemcpyAsync(elements + 4 * p0, d_new + 4 * (p0 - s0), (p1 - p0) * 32, cudaMemcpyDeviceToHost, c->copy_out));
+    }
     done += len;
     i++;
+  }
+  if (out_staged && i >= 1) {
+    CU(c, cudaEventSynchronize(ev_out[i - 1]));
+    c->pool->copy(elements + 4 * prev_p0, so[(i - 1) & 1], prev_bytes);
   }
   CU(c, cudaStreamSynchronize(c->copy_out));
   FINISH(c);

@@ -19,7 +19,7 @@ def build(force=False):
     if not force and os.path.exists(BIN) and all(os.path.getmtime(d) <= os.path.getmtime(BIN) for d in DEPS + libs):
         return BIN
     os.makedirs(os.path.dirname(BIN), exist_ok=True)
-    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-o", BIN, SRC,
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-pthread", "-o", BIN, SRC,
                            "-L" + os.path.dirname(libs[0]), "-lpmt", "-L" + os.path.dirname(libs[1]), "-lpmt_oracle",
                            "-Wl,-rpath,$ORIGIN/../../../plonky2_merkle_trees_b200:$ORIGIN/../../../oracle"])
     return BIN
