@@ -15,8 +15,16 @@ _SO = os.path.join(_HERE, "libpmt_oracle.so")
 
 def build(force=False):
     src = [os.path.join(_HERE, f) for f in ("pmt_oracle.c", "pmt_oracle.h", "poseidon_constants.h", "Makefile")]
-    if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src):
-        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    stale = lambda: not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src)
+    if force or stale():
+        import fcntl
+        with open(_SO + ".lock", "w") as lock:      # several ranks may get here at once: one runs make, the others wait
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            try:
+                if force or stale():
+                    subprocess.check_call(["make", "-C", _HERE, "-s"])
+            finally:
+                fcntl.flock(lock, fcntl.LOCK_UN)
     return _SO
 
 

@@ -18,11 +18,26 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
+    """Safe under concurrency (torchrun starts one process per GPU, each of which calls this): one process holds the lock
+    and compiles into a temporary file that is renamed over libpmt.so atomically; the others wait and find it up to date."""
     if not force and not needs_build():
         return SO
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + SOURCES
-    subprocess.check_call(cmd)
+    import fcntl
+    with open(SO + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if force or needs_build():
+                nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+                tmp = "%s.tmp.%d" % (SO, os.getpid())
+                cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + SOURCES
+                try:
+                    subprocess.check_call(cmd)
+                    os.replace(tmp, SO)
+                finally:
+                    if os.path.exists(tmp):
+                        os.remove(tmp)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return SO
 
 

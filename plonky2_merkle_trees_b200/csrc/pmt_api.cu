@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <condition_variable>
 #include <mutex>
 #include <new>
@@ -99,6 +100,7 @@ struct pmt_ctx {
   int comm_rank = 0, comm_world = 0;
   // one process, several GPUs: the event that publishes this ctx's subtree root to ctxs[0] (pmt_merkle_tree_build_multi_dev)
   cudaEvent_t root_ready = nullptr;
+  std::vector<int> peers;      // devices this ctx's device has been given peer access to
   // pageable caller buffers: library-owned page-locked staging slots (2 in, 2 out) and the copy threads
   void* stage[4] = {nullptr, nullptr, nullptr, nullptr};
   size_t stage_bytes[4] = {0, 0, 0, 0};
@@ -394,6 +396,12 @@ int pmt_init(pmt_ctx** out, int device_id) {
       cudaMemset(c->tickets, 0, TICKET_RING * sizeof(unsigned)) != cudaSuccess) {
     pmt_destroy(c);
     return PMT_E_OOM;
+  }
+  // the cooperative kernels stage their round constants from global memory (poseidon_coop.cuh): fill the tables of this device
+  poseidon::coop::k_coop_tables_init<<<1, 256, 0, c->stream>>>();
+  if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) {
+    pmt_destroy(c);
+    return PMT_E_CUDA;
   }
   *out = c;
   return PMT_OK;
@@ -765,28 +773,43 @@ int pmt_merkle_tree_build_multi_dev(pmt_ctx* const* ctxs, size_t n_ctx, const ui
   const bool gather = (int)cap_height < g;
   if (gather && (!d_roots || (!d_top && n_ctx > 1))) return fail(c0, PMT_E_INVALID_ARG, "multi build: null d_roots / d_top");
   const size_t cap_l = gather ? 1 : (size_t)1 << (cap_height - (uint32_t)g);
-  for (size_t r = 0; r < n_ctx; r++) {
+  // what context r enqueues on its own device: its subtree, the peer copy of its root / cap entries to device 0, an event
+  auto enqueue = [&](size_t r) -> int {
     pmt_ctx* c = ctxs[r];
     if (int rc = bind(c)) return rc;
-    if (c->device != c0->device) {                   // let device r write device 0's memory (NVLink peer access)
-      int can = 0;
+    if (c->device != c0->device && std::find(c->peers.begin(), c->peers.end(), c0->device) == c->peers.end()) {
+      int can = 0;                                   // let device r write device 0's memory (NVLink peer access), once
       CU(c, cudaDeviceCanAccessPeer(&can, c->device, c0->device));
       if (can) {
         const cudaError_t e = cudaDeviceEnablePeerAccess(c0->device, 0);
-        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(c0, PMT_E_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", c->device, c0->device, cudaGetErrorString(e));
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(c, PMT_E_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", c->device, c0->device, cudaGetErrorString(e));
         cudaGetLastError();
       }
+      c->peers.push_back(c0->device);
     }
     // the subtree of ctx r, in its own device memory; its root / cap entries land in a local staging digest first
     void* stage = nullptr;
-    if (int rc = arena_get(c, 2, 64 * 32 + 64 + cap_l * 32, &stage)) return fail(c0, rc, "multi build: ctx %zu: %.400s", r, c->err);
+    if (int rc = arena_get(c, 2, 64 * 32 + 64 + cap_l * 32, &stage)) return rc;
     uint64_t* d_mine = (uint64_t*)stage + 64 * 4 + 8;
-    if (int rc = sharded_local_build(c, d_leaves[r], n, w, cap_height, g, d_digests[r], d_mine)) return fail(c0, rc, "multi build: ctx %zu: %.400s", r, c->err);
+    if (int rc = sharded_local_build(c, d_leaves[r], n, w, cap_height, g, d_digests[r], d_mine)) return rc;
     uint64_t* dst = gather ? d_roots + 4 * r : d_cap + 4 * r * cap_l;
     CU(c, cudaMemcpyPeerAsync(dst, c0->device, d_mine, c->device, cap_l * 32, c->stream));
     if (!c->root_ready) CU(c, cudaEventCreateWithFlags(&c->root_ready, cudaEventDisableTiming));
     CU(c, cudaEventRecord(c->root_ready, c->stream));
-  }
+    return PMT_OK;
+  };
+  // a dozen launches per device: from one host thread the last device would start ~0.4 ms after the first on an 8-GPU box
+  // (measured: 2^24 leaves on 8 devices 2.08 ms enqueued serially), so from 4 contexts on every context is fed by its own thread
+  std::vector<int> rcs(n_ctx, PMT_OK);
+  if (n_ctx >= 4) run_per_ctx(ctxs, rcs, [&](size_t r) { rcs[r] = enqueue(r); });
+  else for (size_t r = 0; r < n_ctx; r++) rcs[r] = enqueue(r);
+  for (size_t r = 0; r < n_ctx; r++)
+    if (rcs[r] != PMT_OK) {
+      char msg[sizeof ctxs[r]->err];
+      memcpy(msg, ctxs[r]->err, sizeof msg);
+      msg[sizeof msg - 1] = 0;
+      return fail(c0, rcs[r], "multi build: ctx %zu (device %d): %.400s", r, ctxs[r]->device, msg);
+    }
   if (int rc = bind(c0)) return rc;
   for (size_t r = 1; r < n_ctx; r++) CU(c0, cudaStreamWaitEvent(c0->stream, ctxs[r]->root_ready, 0));
   if (!gather) return PMT_OK;

@@ -39,8 +39,16 @@
 namespace poseidon {
 namespace coop {
 
-constexpr int QUAD_STRIDE = 15;                 // 16-byte slots per state: elements 0..11, then copies of 0..2 (odd: no bank conflicts)
-constexpr int WARP_SLOTS = 8 * QUAD_STRIDE;     // one exchange buffer of one warp
+// Exchange buffer of one warp: 15 sixteen-byte slots per state (elements 0..11, then copies of 0..2).  A 128-bit shared
+// access is served a QUARTER-warp (8 threads = two quads) at a time, each 16-byte slot covering a group of 4 banks, so
+// the two quads of a quarter must touch disjoint slots mod 8: the odd quad of a pair sits 20 slots (= 4 mod 8) after the
+// even one, pairs are 35 slots apart.  (The first version used a flat stride of 15: two-way conflicts on every access,
+// 1 900 excess wavefronts per permutation in profiles/k_perm_form_r2_summary.txt.)
+constexpr int QUAD_PAIR_STRIDE = 35, QUAD_ODD_OFFSET = 20;
+constexpr int WARP_SLOTS = 4 * QUAD_PAIR_STRIDE;     // one exchange buffer of one warp
+__device__ __forceinline__ int quad_slot_base(unsigned quad_in_warp) {
+  return (int)(quad_in_warp >> 1) * QUAD_PAIR_STRIDE + (int)(quad_in_warp & 1) * QUAD_ODD_OFFSET;
+}
 
 template <int WARPS>
 struct alignas(16) Shared {
@@ -49,16 +57,33 @@ struct alignas(16) Shared {
   uint64_t rc[WIDTH * (PMT_ROUNDS + 1)];   // PMT_RC: row 0 = the first constant layer, row r + 1 = what round r's layer adds (Wide)
 };
 
-// all threads of the block; ends with a block barrier.  (Per-lane indices into constant memory serialise, but this runs
-// once per block: ~1 us.)
+// The round constants in GLOBAL memory, for staging: per-lane indices into constant memory serialise (32 replays per warp
+// load, and the 8.7 KB of tables miss the constant cache): staging them from the constant bank cost ~8 us at the head of
+// every cooperative launch.  From global memory (L2-resident after the first launch) it is one coalesced pass.  Filled
+// once per device by pmt_init (k_coop_tables_init).
+static __device__ double RC_DM_G[2 * WIDTH * PMT_ROUNDS];
+static __device__ uint64_t RC_G[WIDTH * (PMT_ROUNDS + 1)];
+static __global__ void k_coop_tables_init() {
+  for (int i = threadIdx.x; i < 2 * WIDTH * PMT_ROUNDS; i += blockDim.x) RC_DM_G[i] = PMT_RC_DM[i];
+  for (int i = threadIdx.x; i < WIDTH * (PMT_ROUNDS + 1); i += blockDim.x) RC_G[i] = PMT_RC[i];
+}
+
+// all threads of the block; ends with a block barrier
 template <int WARPS>
 __device__ __forceinline__ void stage(Shared<WARPS>& sh) {
-  for (int i = threadIdx.x; i < 2 * WIDTH * PMT_ROUNDS; i += blockDim.x) sh.rc_dm[i] = PMT_RC_DM[i];
-  for (int i = threadIdx.x; i < WIDTH * (PMT_ROUNDS + 1); i += blockDim.x) sh.rc[i] = PMT_RC[i];
+  for (int i = threadIdx.x; i < 2 * WIDTH * PMT_ROUNDS; i += blockDim.x) sh.rc_dm[i] = RC_DM_G[i];
+  for (int i = threadIdx.x; i < WIDTH * (PMT_ROUNDS + 1); i += blockDim.x) sh.rc[i] = RC_G[i];
   __syncthreads();
 }
 
-__device__ __forceinline__ double2 halves(uint64_t x) { return make_double2((double)gl::lo32(x), (double)gl::hi32(x)); }
+// the 32-bit halves of x as doubles.  2^52 magic-number conversion (pair the word with 0x43300000, subtract 2^52): one
+// DADD per half on the fp64 pipe.  The thread-per-state kernel uses I2F on the otherwise idle conversion pipe (better
+// THROUGHPUT), but I2F + its scoreboard wait is 35 cycles of dependent latency against 9 for the DADD, and here latency is
+// what counts (tools/lat_bench.cu).
+__device__ __forceinline__ double2 halves(uint64_t x) {
+  const double MAGIC = 4503599627370496.0;
+  return make_double2(__hiloint2double(0x43300000, (int)gl::lo32(x)) - MAGIC, __hiloint2double(0x43300000, (int)gl::hi32(x)) - MAGIC);
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // Quad: thread j of 4 adjacent lanes holds e[a] = element j + 4a
@@ -67,7 +92,7 @@ struct Quad {
   static constexpr int LANES = 4, ELEMS = 3;
   unsigned j;            // position in the quad
   unsigned lane0;        // warp lane of the quad's thread 0
-  double2* slot;         // &xch[warp][0][quad * 15 + j]: writes at +0 (+12 for j < 3), +4, +8; reads at +0 .. +11
+  double2* slot;         // &xch[warp][0][quad_slot_base(quad) + j]: writes at +0 (+12 for j < 3), +4, +8; reads at +0 .. +11
   const double* kdm;     // rc_dm + 2 j: the constants of element j + 4a in round r are kdm[24 r + 8 a + {0, 1}]
   double c00;            // coefficient of slot 0 in output row j: C[0] + DIAG[0] = 25 on thread 0, C[0] = 17 elsewhere
   double cx[3];          // M[j + 4a][0]: coefficient of element 0 in this thread's three output rows
@@ -78,7 +103,7 @@ struct Quad {
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     t.j = lane & 3;
     t.lane0 = lane & ~3u;
-    t.slot = &sh.xch[warp][0][(lane >> 2) * QUAD_STRIDE + t.j];
+    t.slot = &sh.xch[warp][0][quad_slot_base(lane >> 2) + t.j];
     t.kdm = sh.rc_dm + 2 * t.j;
     t.c00 = t.j == 0 ? 25.0 : 17.0;
 #pragma unroll
@@ -154,8 +179,8 @@ struct Quad {
           double L[3], H[3];
           rows(s, k, L, H);                             // independent of x: overlaps the S-box chain below
           const uint64_t x = gl::pow7(e[0]);            // only thread 0's is used; the others' element j skips the S-box
-          const double xl = (double)__shfl_sync(0xffffffffu, gl::lo32(x), lane0);
-          const double xh = (double)__shfl_sync(0xffffffffu, gl::hi32(x), lane0);
+          const double2 dx = halves(gl::pack(__shfl_sync(0xffffffffu, gl::lo32(x), lane0), __shfl_sync(0xffffffffu, gl::hi32(x), lane0)));
+          const double xl = dx.x, xh = dx.y;
 #pragma unroll
           for (int a = 0; a < 3; a++) {
             L[a] = fma(xl, cx[a], L[a]);

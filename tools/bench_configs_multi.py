@@ -55,6 +55,7 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     ctx = _lib.Context(local_rank)
     eng = sharded.CudaEngine(ctx)
+    eng.comm_init()      # the roots are exchanged by ncclAllGather inside libpmt (pmt_merkle_tree_build_sharded_dev)
     only = sys.argv[1:] or ["C4", "C5", "C3"]
 
     def emit(**kw):

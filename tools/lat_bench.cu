@@ -51,6 +51,8 @@ static double run(uint64_t* d_out, long long* d_cyc, double per_iter_ops) {
 int main() {
   uint64_t* d_out; long long* d_cyc;
   CK(cudaMalloc(&d_out, 4096)); CK(cudaMalloc(&d_cyc, 64));
+  poseidon::coop::k_coop_tables_init<<<1, 256>>>();
+  CK(cudaDeviceSynchronize());
   printf("{\"bench\": \"chain_latency_cycles\", \"pow7\": %.1f, \"mul\": %.1f, \"sqr\": %.1f, \"shuffle_row_plus_combine\": %.1f, \"dfma\": %.1f, "
          "\"imad_wide_acc\": %.1f, \"int_alu_imad_mix_per_op\": %.1f, \"i2f_plus_dadd\": %.1f, \"sts_syncwarp_lds_dadd\": %.1f, \"combine_magic\": %.1f, "
          "\"shfl_plus_add\": %.1f, \"reduce128_c\": %.1f}\n",

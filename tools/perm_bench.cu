@@ -305,6 +305,8 @@ static void run_latency(int sms) {
     }
   }
   uint64_t r[4]; CK(cudaMemcpy(r, dout, 32, cudaMemcpyDeviceToHost));
+  poseidon::coop::k_coop_tables_init<<<1, 256>>>();      // the cooperative forms stage their constants from global memory
+  CK(cudaDeviceSynchronize());
   // round 2: the Quad and Wide forms against round 1's 16-lane form and the product's thread-per-state form: chains of
   // dependent permutations on one warp / half a block / one block / one block per SM / three blocks per SM
   for (int chain : {1, 17}) {
