@@ -285,14 +285,16 @@ __device__ __forceinline__ void coop_node(const Layout& lay, int l, size_t k, bo
   }
 }
 
-// the nodes k_first + [0, nb) of level l by one block: in passes of 64 by quads, or -- when there are at most 16, where
+// the nodes k_first + [0, nb) of level l by one block: in passes of 64 by quads, or -- when there are at most 8, where
 // only latency counts -- in one pass by 16-lane groups.  Warps all of whose groups have no node skip the permutation
 // (its exchanges never cross a warp).  nb is the same for all threads of the block.
 template <class Layout>
 __device__ __forceinline__ void coop_level(const Layout& lay, int l, size_t k_first, size_t nb, const Quad& q, const Wide& w,
                                            const CoopShared& sh) {
   const unsigned warp = threadIdx.x >> 5;
-  if (nb > (size_t)WIDE_NODES) {
+  // measured per level (tools/perm_bench.cu lat, profiles/latency_r2b.jsonl): Quad 12.9 / 9.3 / 8.8 us for 64 / 32 / <= 16 nodes
+  // of a block (8 / 4 / <= 2 warps), Wide 9.5 us for 16 nodes (8 warps) and 6.4 us for <= 8 (one warp per sub-partition)
+  if (nb > (size_t)WIDE_NODES / 2) {
     for (size_t base = 0; base < nb; base += COOP_NODES)
       if (base + warp * 8 < nb) coop_node(lay, l, k_first + base + q.state(), base + q.state() < nb, q, sh);
   } else if (warp * 2 < nb) {

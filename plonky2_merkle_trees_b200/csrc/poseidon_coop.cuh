@@ -208,7 +208,6 @@ struct Wide {
   unsigned lane0;        // warp lane of the group's lane 0
   uint32_t c0;           // coefficient of the lane's own element in its row: C[0] + DIAG[0] = 25 on lane 0, C[0] = 17 elsewhere
   uint32_t cx;           // M[g][0]: coefficient of element 0 in this lane's row
-  unsigned zero_step;    // the step i at which this lane's rotated read hits element 0 ((12 - g) mod 12)
 
   template <int WARPS>
   __device__ __forceinline__ static Wide make(Shared<WARPS>&) {
@@ -219,7 +218,6 @@ struct Wide {
     t.lane0 = lane & 16u;
     t.c0 = t.gg == 0 ? 25u : 17u;
     t.cx = PMT_MDS_CIRC32[t.gg == 0 ? 12 : 12 - t.gg];
-    t.zero_step = (WIDTH - t.gg) % WIDTH;
     return t;
   }
   __device__ __forceinline__ unsigned elem(int) const { return g; }
@@ -230,19 +228,19 @@ struct Wide {
   }
 
   // row g of the MDS layer over the state held one element per lane: out = k + sum_i s[(g + i) % 12] C[i] (+ 8 s[0] on lane 0).
-  // SKIP0: element 0 does not take part (partial rounds: it enters later, after its S-box).
+  // SKIP0: element 0 does not take part (partial rounds: it enters later, after its S-box) -- lane 0 simply contributes zero
+  // to its own term and to every shuffle that reads it.
   template <bool SKIP0>
   __device__ __forceinline__ void row(uint64_t v, uint64_t k, uint64_t& L, uint64_t& H) const {
     constexpr uint32_t CIRC[WIDTH] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
-    const uint32_t lo = gl::lo32(v), hi = gl::hi32(v);
-    const bool own = !(SKIP0 && gg == 0);
-    uint64_t La = gl::mad_wide(own ? lo : 0u, c0, k), Ha = (uint64_t)(own ? hi : 0u) * c0, Lb = 0, Hb = 0;
+    const bool mute = SKIP0 && gg == 0;
+    const uint32_t lo = mute ? 0u : gl::lo32(v), hi = mute ? 0u : gl::hi32(v);
+    uint64_t La = gl::mad_wide(lo, c0, k), Ha = (uint64_t)hi * c0, Lb = 0, Hb = 0;
 #pragma unroll
     for (int i = 1; i < WIDTH; i++) {
       const unsigned idx = gg + i;
       const unsigned src = lane0 + (idx >= WIDTH ? idx - WIDTH : idx);
-      uint32_t slo = __shfl_sync(0xffffffffu, lo, src), shi = __shfl_sync(0xffffffffu, hi, src);
-      if (SKIP0 && (unsigned)i == zero_step) { slo = 0; shi = 0; }
+      const uint32_t slo = __shfl_sync(0xffffffffu, lo, src), shi = __shfl_sync(0xffffffffu, hi, src);
       if (i & 1) { Lb = gl::mad_wide(slo, CIRC[i], Lb); Hb = gl::mad_wide(shi, CIRC[i], Hb); }
       else       { La = gl::mad_wide(slo, CIRC[i], La); Ha = gl::mad_wide(shi, CIRC[i], Ha); }
     }
