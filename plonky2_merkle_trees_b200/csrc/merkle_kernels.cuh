@@ -266,53 +266,78 @@ using poseidon::coop::Quad;
 using poseidon::coop::Wide;
 
 // one two_to_one by one group of threads; groups without a node (`active` false) still run the permutation's warp-wide
-// operations.  Children are read with ld.global.cg: they may have been written by another SM earlier in the same launch.
+// operations.  Children come from shared memory when this block produced them at the previous level (`ch`: the two
+// digests, 8 consecutive words), else from global memory with ld.global.cg (another SM may have written them earlier in the
+// same launch).  The digest goes to its place in the layout -- every level is stored once, proofs need it -- and, if `keep`
+// is given, to shared memory for the next level: the parent does not wait for an L2 round trip.
 template <class Form, class Layout>
-__device__ __forceinline__ void coop_node(const Layout& lay, int l, size_t k, bool active, const Form& t, const CoopShared& sh) {
+__device__ __forceinline__ void coop_node(const Layout& lay, int l, size_t k, bool active, const uint64_t* ch, uint64_t* keep,
+                                          const Form& t, const CoopShared& sh) {
   uint64_t e[Form::ELEMS];
   const uint64_t *a = nullptr, *b = nullptr;
-  if (active) lay.children(l, k, a, b);
+  if (active && !ch) lay.children(l, k, a, b);
 #pragma unroll
   for (int i = 0; i < Form::ELEMS; i++) {
     const unsigned idx = t.elem(i);
-    e[i] = (active && idx < 8) ? __ldcg(idx < 4 ? a + idx : b + (idx - 4)) : 0ull;
+    e[i] = 0ull;
+    if (active && idx < 8) e[i] = ch ? ch[idx] : __ldcg(idx < 4 ? a + idx : b + (idx - 4));
   }
   t.permute(e, sh);
 #pragma unroll
   for (int i = 0; i < Form::ELEMS; i++) {
     const unsigned idx = t.elem(i);
-    if (active && idx < 4) lay.at(l, k)[idx] = gl::canonical(e[i]);
+    if (active && idx < 4) {
+      const uint64_t d = gl::canonical(e[i]);
+      lay.at(l, k)[idx] = d;
+      if (keep) keep[idx] = d;
+    }
   }
 }
 
-// the nodes k_first + [0, nb) of level l by one block: in passes of 64 by quads, or -- when there are at most 8, where
+// Digests a block hands from one level to the next without leaving the SM: the nodes of a level alternate between two
+// regions (64 and 32 digests), node i of the level below at words 4 i of the other region.
+constexpr int KEEP_A = 64, KEEP_B = 32;
+struct KeepBuf {
+  uint64_t w[(KEEP_A + KEEP_B) * 4];
+  __device__ __forceinline__ uint64_t* region(int parity) { return parity ? w + 4 * KEEP_A : w; }
+  __device__ __forceinline__ static size_t room(int parity) { return parity ? KEEP_B : KEEP_A; }
+};
+
+// the nodes k_first + [0, nb) of level l by one block: in passes of 64 by quads, or -- when there are at most 16, where
 // only latency counts -- in one pass by 16-lane groups.  Warps all of whose groups have no node skip the permutation
-// (its exchanges never cross a warp).  nb is the same for all threads of the block.
+// (its exchanges never cross a warp).  nb is the same for all threads of the block.  from: the level below as this block
+// kept it (node i's children at digests 2 i, 2 i + 1), or nullptr; to: where to keep this level (room for nb), or nullptr.
 template <class Layout>
-__device__ __forceinline__ void coop_level(const Layout& lay, int l, size_t k_first, size_t nb, const Quad& q, const Wide& w,
-                                           const CoopShared& sh) {
+__device__ __forceinline__ void coop_level(const Layout& lay, int l, size_t k_first, size_t nb, const uint64_t* from, uint64_t* to,
+                                           const Quad& q, const Wide& w, const CoopShared& sh) {
   const unsigned warp = threadIdx.x >> 5;
-  // measured per level (tools/perm_bench.cu lat, profiles/latency_r2b.jsonl): Quad 12.9 / 9.3 / 8.8 us for 64 / 32 / <= 16 nodes
-  // of a block (8 / 4 / <= 2 warps), Wide 9.5 us for 16 nodes (8 warps) and 6.4 us for <= 8 (one warp per sub-partition)
-  if (nb > (size_t)WIDE_NODES / 2) {
+  // measured per level (tools/perm_bench.cu lat, profiles/latency_r2.jsonl): Quad 12.9 / 9.3 / 8.8 us for 64 / 32 / <= 16 nodes
+  // of a block (8 / 4 / <= 2 warps), Wide 8.4 us for 16 nodes (8 warps) and 6.3 us for <= 8 (one warp per sub-partition);
+  // switching at 8 instead of 16 nodes made the tail of a tree 9 us slower (profiles/tail_r2.jsonl)
+  if (nb > (size_t)WIDE_NODES) {
     for (size_t base = 0; base < nb; base += COOP_NODES)
-      if (base + warp * 8 < nb) coop_node(lay, l, k_first + base + q.state(), base + q.state() < nb, q, sh);
+      if (base + warp * 8 < nb) {
+        const size_t i = base + q.state();
+        coop_node(lay, l, k_first + i, i < nb, from ? from + 8 * i : nullptr, to ? to + 4 * i : nullptr, q, sh);
+      }
   } else if (warp * 2 < nb) {
-    coop_node(lay, l, k_first + w.state(), w.state() < nb, w, sh);
+    const size_t i = w.state();
+    coop_node(lay, l, k_first + i, i < nb, from ? from + 8 * i : nullptr, to ? to + 4 * i : nullptr, w, sh);
   }
 }
 
 // The latency-bound part of a tree in ONE launch.  Level l0 has the nodes k0 + [0, count0); block b owns the 64 nodes
 // k0 + [64 b, 64 b + 64) of it and every ancestor of theirs for `local_levels` levels (64, 32, ..., 1 nodes; needs k0 and
 // count0 to be multiples of 2^(local_levels - 1)), a block barrier between levels: a block only reads children it wrote
-// itself, every level is still stored once (proofs need it).  Then, for a perfect subtree (count0 a power of two, k0 a
-// multiple of it), the LAST block to finish -- a ticket taken after a device-wide fence -- continues with the
-// `top_levels` levels above the block roots (count0 >> local_levels nodes, halving), so the whole tail of the tree is one
-// launch instead of three and there is no grid-wide barrier.  local_levels = 1, top_levels = 0: a plain level.
+// itself -- it keeps them in shared memory -- and every level is still stored once (proofs need it).  Then, for a perfect
+// subtree (count0 a power of two, k0 a multiple of it), the LAST block to finish -- a ticket taken after a device-wide fence
+// -- continues with the `top_levels` levels above the block roots (count0 >> local_levels nodes, halving), so the whole tail
+// of the tree is one launch instead of three and there is no grid-wide barrier.  local_levels = 1, top_levels = 0: a plain level.
 template <class Layout>
 __global__ void __launch_bounds__(COOP_BLOCK) k_tree_coop(Layout lay_in, int l0, size_t k0, size_t count0, int local_levels,
                                                            int top_levels, unsigned* __restrict__ ticket) {
   __shared__ CoopShared sh;
+  __shared__ KeepBuf kept;
   __shared__ bool is_last;
   const Layout lay = lay_in.for_set(blockIdx.y);
   const Quad q = Quad::make(sh);
@@ -322,8 +347,9 @@ __global__ void __launch_bounds__(COOP_BLOCK) k_tree_coop(Layout lay_in, int l0,
     const size_t per = (size_t)COOP_NODES >> j, cnt = count0 >> j;
     const size_t base = ((size_t)blockIdx.x * COOP_NODES) >> j;
     const size_t nb = base >= cnt ? 0 : (cnt - base < per ? cnt - base : per);
-    coop_level(lay, l0 + j, (k0 >> j) + base, nb, q, w, sh);
-    if (j + 1 < local_levels) { __threadfence_block(); __syncthreads(); }
+    coop_level(lay, l0 + j, (k0 >> j) + base, nb, j ? kept.region((j - 1) & 1) : nullptr,
+               j + 1 < local_levels ? kept.region(j & 1) : nullptr, q, w, sh);
+    if (j + 1 < local_levels) __syncthreads();
   }
   if (top_levels <= 0) return;
   // ticket: the block roots must be visible device-wide before the ticket is taken
@@ -338,9 +364,13 @@ __global__ void __launch_bounds__(COOP_BLOCK) k_tree_coop(Layout lay_in, int l0,
   if (!is_last) return;
   __threadfence();
   size_t cnt = count0 >> local_levels;
+  bool have = false;                          // the level below is in kept.region(parity ^ 1)
+  int parity = 0;
   for (int j = local_levels; j < local_levels + top_levels; j++, cnt >>= 1) {
-    coop_level(lay, l0 + j, k0 >> j, cnt, q, w, sh);
-    __threadfence_block();
+    const bool fits = cnt <= KeepBuf::room(parity);
+    coop_level(lay, l0 + j, k0 >> j, cnt, have ? kept.region(parity ^ 1) : nullptr, fits ? kept.region(parity) : nullptr, q, w, sh);
+    have = fits;
+    parity ^= 1;
     __syncthreads();
   }
 }
