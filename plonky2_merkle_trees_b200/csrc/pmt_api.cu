@@ -106,7 +106,7 @@ struct pmt_ctx {
   size_t stage_bytes[4] = {0, 0, 0, 0};
   HostCopyPool* pool = nullptr;
 };
-constexpr unsigned TICKET_RING = 256;
+constexpr unsigned TICKET_RING = 4096;
 
 static inline void prof_begin(pmt_ctx* c, const char* name, double units) {
   if (!c->profiling) return;
@@ -223,10 +223,11 @@ CoopPlan coop_plan(const pmt_ctx* c, size_t n) {
 int log2_floor(size_t x) { int l = 0; while (((size_t)2 << l) <= x) l++; return l; }
 int ctz_cap(size_t x, int cap) { int z = 0; while (z < cap && !((x >> z) & 1)) z++; return z; }
 
-unsigned* next_ticket(pmt_ctx* c, unsigned sets) {
-  if (c->ticket_next + sets > TICKET_RING) c->ticket_next = 0;
+// `n` consecutive zeroed counters for one k_tree_coop launch (1 for the final round + 1 per group of 8 blocks)
+unsigned* next_ticket(pmt_ctx* c, unsigned n) {
+  if (c->ticket_next + n > TICKET_RING) c->ticket_next = 0;
   unsigned* t = c->tickets + c->ticket_next;
-  c->ticket_next += sets;
+  c->ticket_next += n;
   return t;
 }
 
@@ -241,7 +242,8 @@ int launch_coop(pmt_ctx* c, const Layout& lay, int l, int room, size_t k0, size_
     local = align + 1 < room ? align + 1 : room;
     if (local > COOP_LOCAL_LEVELS) local = COOP_LOCAL_LEVELS;
     const bool perfect = (count & (count - 1)) == 0 && k0 % count == 0;
-    if (perfect && local == COOP_LOCAL_LEVELS && count > (size_t)COOP_NODES) {
+    if (perfect && local == COOP_LOCAL_LEVELS && count > (size_t)COOP_NODES && sets == 1 &&
+        count / COOP_NODES / TICKET_GROUP + 1 <= TICKET_RING / 4) {
       const int height = log2_floor(count) + 1;           // levels of the subtree, its root included
       top = (height < room ? height : room) - local;
     }
@@ -250,8 +252,8 @@ int launch_coop(pmt_ctx* c, const Layout& lay, int l, int room, size_t k0, size_
   size_t units = 0;
   for (int j = 0; j < local + top; j++) units += count >> j;
   TAG(c, top ? "k_tree_coop" : (local > 1 ? "k_subtree_coop" : "k_level_coop"), units * sets);
-  k_tree_coop<Layout><<<dim3((unsigned)blocks, sets), COOP_BLOCK, 0, c->stream>>>(lay, l, k0, count, local, top,
-                                                                                   top ? next_ticket(c, sets) : nullptr);
+  k_tree_coop<Layout><<<dim3((unsigned)blocks, sets), COOP_BLOCK, 0, c->stream>>>(
+      lay, l, k0, count, local, top, top ? next_ticket(c, 1 + (unsigned)(blocks / TICKET_GROUP)) : nullptr);
   CHECK_LAUNCH(c);
   return local + top;
 }
