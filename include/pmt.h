@@ -175,6 +175,20 @@ int pmt_merkle_tree_build_sharded_dev(pmt_ctx* ctx, const uint64_t* d_local_leav
                                       uint32_t cap_height, uint64_t* d_local_digests, uint64_t* d_roots, uint64_t* d_top,
                                       uint64_t* d_cap);
 
+/* The subtree-sharded MMR with one process per GPU (pmt_comm_init first).  pmt_mmr_shard_plan is its pure index
+ * math: every set bit 2^b >= world of n_total is one mountain, cut into `world` equal perfect sub-mountains of m[i] leaves
+ * (round i, decreasing powers of two; at most 31 rounds); the bits below `world` are the tail of the last rank.  Rank r owns the
+ * leaves [S_i + r m[i], S_i + (r + 1) m[i]) of every round (S_i = world (m[0] + .. + m[i-1])) and the last rank also the tail.
+ * pmt_mmr_build_sharded_dev (collective, enqueues only): d_local_leaves = the rank's leaves in that order; outputs:
+ * d_local_elements (pmt_mmr_size(sum m[i]) digests: sub-mountain i is the slice of the global `elements` starting at
+ * pmt_mmr_size(S_i + r m[i])), d_tail_elements (last rank, pmt_mmr_size(tail) digests), d_gathered (world x slots digests,
+ * slots = rounds + popcount(tail): every rank's sub-mountain roots and the tail's peaks), d_tops (rounds x (world - 1) digests:
+ * the levels above each round's roots, level-major; global positions as for pmt_top_levels_dev) and d_peaks (slots digests:
+ * get_peaks() of the whole MMR, replicated).  One batch append, one ncclAllGather, one batched finish, one stream. */
+int pmt_mmr_shard_plan(size_t n_total, size_t world, uint32_t* n_rounds, size_t* m_out_64, size_t* tail);
+int pmt_mmr_build_sharded_dev(pmt_ctx* ctx, const uint64_t* d_local_leaves, size_t n_total, uint64_t* d_local_elements,
+                              uint64_t* d_tail_elements, uint64_t* d_gathered, uint64_t* d_tops, uint64_t* d_peaks);
+
 /* ---- MMR: merkle_mountain_ranges.rs ------------------------------------------------------------------------------------ */
 /* number of elements of an MMR with n leaves = 2n - popcount(n) */
 size_t pmt_mmr_size(size_t n_leaves);

@@ -140,21 +140,25 @@ struct MmrAppend {
 };
 
 // The levels above a gathered array of subtree roots (the finish of a subtree-sharded tree): level 0 = the
-// n_roots roots (read only), levels 1 .. log2(n_roots) level-major in `out` (n_roots/2, n_roots/4, ... digests).
+// n_roots roots (read only, root_step digests apart: 1 for a dense array, the row length when they are one column of an
+// all-gathered matrix), levels 1 .. log2(n_roots) level-major in `out` (n_roots/2, n_roots/4, ... digests).
 // A batch of independent sets (blockIdx.y; the rounds of a sharded MMR) lies roots_stride / out_stride digests apart.
 struct TopRoots {
   const uint64_t* roots;
   uint64_t* out;
-  size_t n_roots, roots_stride, out_stride;
+  size_t n_roots, roots_stride, out_stride, root_step;
   __device__ __forceinline__ uint64_t* at(int l, size_t k) const {
-    if (l == 0) return const_cast<uint64_t*>(roots) + 4 * k;
+    if (l == 0) return const_cast<uint64_t*>(roots) + 4 * k * root_step;
     return out + 4 * (n_roots - (n_roots >> (l - 1)) + k);
   }
   __device__ __forceinline__ void children(int l, size_t k, const uint64_t*& a, const uint64_t*& b) const {
-    a = at(l - 1, 2 * k); b = a + 4;
+    a = at(l - 1, 2 * k); b = at(l - 1, 2 * k + 1);
   }
   __device__ __forceinline__ TopRoots for_set(unsigned set) const {
-    return TopRoots{roots + 4 * roots_stride * set, out + 4 * out_stride * set, n_roots, roots_stride, out_stride};
+    return TopRoots{roots + 4 * roots_stride * set, out + 4 * out_stride * set, n_roots, roots_stride, out_stride, root_step};
+  }
+  TopRoots for_set_host(unsigned set) const {
+    return TopRoots{roots + 4 * roots_stride * set, out + 4 * out_stride * set, n_roots, 0, 0, root_step};
   }
 };
 

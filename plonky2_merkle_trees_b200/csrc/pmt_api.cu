@@ -733,12 +733,12 @@ int pmt_top_levels_batch_dev(pmt_ctx* c, const uint64_t* d_roots, size_t batch, 
   const size_t n_cap = (size_t)1 << cap_height;
   const int levels = g - (int)cap_height;                  // levels 1 .. levels of TopRoots
   if (n_roots / 2 <= (size_t)COOP_NODES) {
-    TopRoots lay{d_roots, d_top_out, n_roots, n_roots, n_roots - n_cap};
+    TopRoots lay{d_roots, d_top_out, n_roots, n_roots, n_roots - n_cap, 1};
     const int done = launch_coop(c, lay, 1, levels, 0, n_roots / 2, (unsigned)batch);
     return done < 0 ? done : PMT_OK;
   }
   for (size_t b = 0; b < batch; b++) {
-    TopRoots lay{d_roots + 4 * n_roots * b, d_top_out + 4 * (n_roots - n_cap) * b, n_roots, 0, 0};
+    TopRoots lay{d_roots + 4 * n_roots * b, d_top_out + 4 * (n_roots - n_cap) * b, n_roots, 0, 0, 1};
     if (int rc = launch_level_span(c, lay, 1, levels, 0, n_roots)) return rc;
   }
   return PMT_OK;
@@ -1519,6 +1519,81 @@ int pmt_mmr_extend_multi(pmt_ctx* const* ctxs, size_t n_ctx, uint64_t* elements,
   } catch (const std::bad_alloc&) {
     return fail(c0, PMT_E_OOM, "mmr extend multi: out of host memory");
   }
+}
+
+// ---- subtree-sharded MMR, one process per GPU, NCCL inside the library ------------------------------------------------------
+// The plan: every set bit 2^b >= G of n is one mountain cut into G equal perfect sub-mountains of m_i = 2^b / G
+// leaves, one per rank ("round" i); the bits below G (t < G leaves) are the tail, kept by the last rank.  Pure index math.
+int pmt_mmr_shard_plan(size_t n_total, size_t world, uint32_t* n_rounds, size_t* m_out, size_t* tail) {
+  if (world == 0 || (world & (world - 1))) return PMT_E_NOT_POW2;
+  uint32_t k = 0;
+  size_t rest = n_total;
+  while (rest >= world) {
+    const size_t m = (size_t)1 << log2_floor(rest / world);
+    if (m_out) m_out[k] = m;
+    k++;
+    rest -= world * m;
+  }
+  if (n_rounds) *n_rounds = k;
+  if (tail) *tail = rest;
+  return PMT_OK;
+}
+
+// Collective.  This rank's leaves: its m_i leaves of every round i, in round order, then -- last rank only -- the t tail
+// leaves.  ONE batch append builds all of the rank's sub-mountains (they are exactly the mountains of its local MMR),
+// k_mmr_peaks writes their roots and the tail's peaks into this rank's row of d_gathered, ONE ncclAllGather exchanges the rows
+// (<= 62 digests per rank), one batched launch finishes the log2 G levels above every round's G roots, and the global peaks
+// (one per round, then the tail's) are collected.  One stream, no host synchronisation.
+//   d_local_elements  pmt_mmr_size(sum m_i) digests: the rank's local MMR; sub-mountain i is the slice of the global
+//                     `elements` that starts at pmt_mmr_size(S_i + rank m_i), S_i = world (m_0 + .. + m_(i-1))
+//   d_tail_elements   pmt_mmr_size(t) digests (last rank; ignored elsewhere)
+//   d_gathered        world x slots digests, slots = rounds + popcount(t): row r = [rank r's sub-mountain roots | tail peaks]
+//   d_tops            rounds x (world - 1) digests: the levels above each round's roots, level-major; last one = the round's peak
+//   d_peaks           slots digests: get_peaks() of the whole MMR, on every rank
+int pmt_mmr_build_sharded_dev(pmt_ctx* c, const uint64_t* d_local_leaves, size_t n_total, uint64_t* d_local_elements,
+                              uint64_t* d_tail_elements, uint64_t* d_gathered, uint64_t* d_tops, uint64_t* d_peaks) {
+  if (int rc = bind(c)) return rc;
+  if (!c->comm) return fail(c, PMT_E_INVALID_ARG, "sharded mmr: pmt_comm_init has not been called on this ctx");
+  const size_t G = (size_t)c->comm_world, r = (size_t)c->comm_rank;
+  if (n_total == 0 || n_total > ((size_t)1 << 30)) return fail(c, PMT_E_RANGE, "sharded mmr: bad leaf count (get_mmr_index is i32, merkle_mountain_ranges.rs:264)");
+  uint32_t k = 0;
+  size_t ms[64], t = 0;
+  pmt_mmr_shard_plan(n_total, G, &k, ms, &t);
+  size_t n_main = 0;
+  for (uint32_t i = 0; i < k; i++) n_main += ms[i];
+  const uint32_t tp = (uint32_t)__builtin_popcountll((unsigned long long)t);
+  const size_t slots = (size_t)k + tp;
+  const bool last = r + 1 == G;
+  if (!d_gathered || !d_peaks || (n_main && (!d_local_leaves || !d_local_elements)) || (k && G > 1 && !d_tops) || (t && last && !d_tail_elements))
+    return fail(c, PMT_E_INVALID_ARG, "sharded mmr: null pointer");
+  uint64_t* mine = d_gathered + 4 * slots * r;
+  CU(c, cudaMemsetAsync(mine, 0, slots * 32, c->stream));
+  if (n_main) {
+    if (int rc = mmr_extend_plan(c, Mmr{d_local_elements}, 0, d_local_leaves, n_main)) return rc;
+    k_mmr_peaks<<<1, 64, 0, c->stream>>>(Mmr{d_local_elements}, n_main, mine);      // popcount(n_main) = k peaks: the sub-mountain roots
+    CHECK_LAUNCH(c);
+  }
+  if (t && last) {
+    if (int rc = mmr_extend_plan(c, Mmr{d_tail_elements}, 0, d_local_leaves + n_main, t)) return rc;
+    k_mmr_peaks<<<1, 64, 0, c->stream>>>(Mmr{d_tail_elements}, t, mine + 4 * k);
+    CHECK_LAUNCH(c);
+  }
+  if (G > 1) NC(c, nccl_api()->AllGather(mine, d_gathered, 4 * slots, ncclUint64, c->comm, c->stream));
+  if (k && G > 1) {      // round i: roots = column i of the gathered matrix (slots digests apart), finished in set i
+    TopRoots lay{d_gathered, d_tops, G, 1, G - 1, slots};
+    if (G / 2 <= (size_t)COOP_NODES) {
+      const int done = launch_coop(c, lay, 1, log2_strict(G), 0, G / 2, k);
+      if (done < 0) return done;
+    } else {
+      for (uint32_t i = 0; i < k; i++)
+        if (int rc = launch_level_span(c, lay.for_set_host(i), 1, log2_strict(G), 0, G)) return rc;
+    }
+    CU(c, cudaMemcpy2DAsync(d_peaks, 32, d_tops + 4 * (G - 2), (G - 1) * 32, 32, k, cudaMemcpyDeviceToDevice, c->stream));
+  } else if (k) {
+    CU(c, cudaMemcpyAsync(d_peaks, d_gathered, (size_t)k * 32, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  if (tp) CU(c, cudaMemcpyAsync(d_peaks + 4 * k, d_gathered + 4 * (slots * (G - 1) + k), (size_t)tp * 32, cudaMemcpyDeviceToDevice, c->stream));
+  return PMT_OK;
 }
 
 // positions of the peaks in the post-order array, largest mountain first (get_peaks, :179-200)
