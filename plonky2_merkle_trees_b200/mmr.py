@@ -142,6 +142,14 @@ class MMR:
     def new(cls, ctx=None):
         return cls(ctx)
 
+    @classmethod
+    def adopt(cls, ctx, d_elements, n_leaves, pending=True):
+        """an MMR over device elements some other call produced (the sharded build): (>= mmr_size(n_leaves), 4) rows"""
+        m = cls(ctx)
+        m.d_elements, m.n_leaves, m._pending = d_elements, n_leaves, pending
+        m._cap_leaves = d_elements.shape[0] // 2
+        return m
+
     def __len__(self):
         return 2 * self.n_leaves - bin(self.n_leaves).count("1")
 

@@ -110,6 +110,30 @@ class CudaEngine:
             return d_dig, None, None, d_cap
         return d_dig, d_roots, d_top[:world - ncap], d_cap
 
+    def build_sharded_mmr(self, d_local_leaves, n_total, world, rank):
+        """pmt_mmr_build_sharded_dev -> (local MMR, tail MMR or None, roots (rounds, G, 4), tops (rounds, G - 1, 4), peaks);
+        enqueued only.  The plan comes from the library too (pmt_mmr_shard_plan)."""
+        import ctypes as C
+        from .mmr import MMR
+        k, ms, t = C.c_uint32(0), (C.c_size_t * 64)(), C.c_size_t(0)
+        self.ctx.check(self.ctx.lib.pmt_mmr_shard_plan(n_total, world, C.byref(k), ms, C.byref(t)))
+        k, t = k.value, t.value
+        n_main, tp = sum(ms[:k]), bin(t).count("1")
+        slots = k + tp
+        last = rank == world - 1
+        d_local = dev_u64((max(mmr_size(n_main), 1), 4), self.device)
+        d_tail = dev_u64((max(mmr_size(t), 1), 4), self.device) if (t and last) else None
+        d_gathered = dev_u64((world, max(slots, 1), 4), self.device)
+        d_tops = dev_u64((max(k, 1), max(world - 1, 1), 4), self.device)
+        d_peaks = dev_u64((max(slots, 1), 4), self.device)
+        self.ctx.call("pmt_mmr_build_sharded_dev", dptr(d_local_leaves), n_total, dptr(d_local), dptr(d_tail) if d_tail is not None else None,
+                      dptr(d_gathered), dptr(d_tops), dptr(d_peaks))
+        local = MMR.adopt(self.ctx, d_local, n_main)
+        tail = MMR.adopt(self.ctx, d_tail, t) if d_tail is not None else None
+        # (rounds, G, 4) view of the gathered matrix: round i = column i; no copy, the host reads it only on demand
+        d_roots = d_gathered[:, :k].permute(1, 0, 2)
+        return local, tail, d_roots, d_tops[:k, :world - 1], d_peaks[:slots]
+
     def publish(self):
         """order torch's current stream (the one NCCL synchronises with) after the ctx stream: no host round trip"""
         cur = torch.cuda.current_stream(self.device)
@@ -400,6 +424,9 @@ def build_sharded_mmr(d_local_leaves, n_total, engine, group=None):
     d_local_leaves = d_local_leaves.reshape(-1)
     if d_local_leaves.numel() != want:
         raise ValueError("rank %d: expected %d leaves, got %d" % (rank, want, d_local_leaves.numel()))
+    if world > 1 and getattr(engine, "has_comm", False):      # NCCL inside libpmt: one call, one stream, no host sync
+        local, tail, d_roots, d_tops, d_peaks = engine.build_sharded_mmr(d_local_leaves, n_total, world, rank)
+        return ShardedMMR(n_total, world, rank, (ms, t), local, d_roots, d_tops, tail, d_peaks, engine)
     dev = d_local_leaves.device
     k, n_tail_peaks = len(ms), bin(t).count("1")
     slots = max(k + n_tail_peaks, 1)

@@ -226,6 +226,26 @@ def test_mmr_multi_plan_and_block_construction(oracle, n0, m, g):
     assert np.array_equal(out, want)
 
 
+def test_mmr_shard_plan_in_the_library_equals_the_host_plan():
+    """pmt_mmr_shard_plan (what pmt_mmr_build_sharded_dev cuts the leaves by) against sharded.mmr_shard_plan (what the gloo
+    world-of-2 tests below replay with the oracle), 5 000 random (n, world); the rounds tile n exactly; bad worlds are refused."""
+    import ctypes as C
+    import random
+    from plonky2_merkle_trees_b200 import _lib, sharded
+    L = _lib.load()
+    rnd = random.Random(11)
+    k, ms, t = C.c_uint32(0), (C.c_size_t * 64)(), C.c_size_t(0)
+    for _ in range(5000):
+        w = 1 << rnd.randrange(0, 5)
+        n = rnd.choice([rnd.randrange(0, 1 << 30), rnd.randrange(0, 4 * w), (1 << rnd.randrange(0, 31)) - rnd.randrange(0, 2)])
+        assert L.pmt_mmr_shard_plan(n, w, C.byref(k), ms, C.byref(t)) == 0
+        got = list(ms[:k.value])
+        assert (got, t.value) == sharded.mmr_shard_plan(n, w)
+        assert w * sum(got) + t.value == n and t.value < w and all(a > b for a, b in zip(got, got[1:]))
+    for w in (0, 3, 12):
+        assert L.pmt_mmr_shard_plan(100, w, C.byref(k), ms, C.byref(t)) == _lib.PMT_E_NOT_POW2
+
+
 def test_mmr_multi_plan_invariants_random():
     """pmt_mmr_multi_plan over 20 000 random (n_before, m, contexts): block size, alignment, head / tail bounds, block count, and
     that every node the plan assigns (head, blocks, coarse nodes, tail) is a distinct new position of the post-order array."""

@@ -805,6 +805,40 @@ def test_sharded_mmr_virtual_world_of_one(ctx, api, oracle):
             assert sm.get_proof_normal_index(i).verify(int(leaves[i]), sm.bagging_the_peaks(), ctx)
 
 
+def test_sharded_mmr_with_nccl_inside_the_library_world_of_one(api, oracle):
+    """pmt_mmr_build_sharded_dev on a communicator of ONE rank (several ranks: tools/multigpu_check.py under torchrun): one
+    library call builds the sub-mountains, gathers their roots and finishes the peaks; elements, peaks, bag and proofs against
+    the sequential add_leaf oracle.  Also the call's argument checks."""
+    import ctypes as C
+    from plonky2_merkle_trees_b200 import _lib, sharded
+    from plonky2_merkle_trees_b200.device import to_device
+    c = _lib.Context(0)
+    try:
+        eng = sharded.CudaEngine(c)
+        with pytest.raises(_lib.PmtError):                               # no communicator yet
+            eng.build_sharded_mmr(to_device(splitmix_felts(1, 8), eng.device), 8, 1, 0)
+        uid = C.create_string_buffer(128)
+        c.call("pmt_nccl_unique_id", C.cast(uid, C.c_void_p))
+        c.call("pmt_comm_init", C.cast(uid, C.c_void_p), 0, 1)
+        eng.has_comm = True
+        for n in (1, 2, 77, 1000, 4097, (1 << 15) + 5):
+            leaves = splitmix_felts(n + 3, n)
+            local, tail, d_roots, d_tops, d_peaks = eng.build_sharded_mmr(to_device(leaves, eng.device), n, 1, 0)
+            assert tail is None and d_tops.shape[1] == 0
+            sm = sharded.ShardedMMR(n, 1, 0, sharded.mmr_shard_plan(n, 1), local, d_roots, d_tops, tail, d_peaks, eng)
+            want = oracle.mmr_extend(None, leaves)
+            assert np.array_equal(sm.assemble_global([sm.local.elements], None), want)
+            assert np.array_equal(sm.get_peaks(), oracle.mmr_peaks(want))
+            assert np.array_equal(sm.bagging_the_peaks(), oracle.mmr_bag(want))
+            assert len(sm.rounds) == bin(n).count("1")
+            for i in {0, n // 2, n - 1}:
+                assert sm.get_proof_normal_index(i).verify(int(leaves[i]), sm.bagging_the_peaks(), c)
+        with pytest.raises(_lib.PmtError):                               # more than 2^30 leaves
+            c.call("pmt_mmr_build_sharded_dev", None, (1 << 30) + 1, None, None, None, None, None)
+    finally:
+        c.close()
+
+
 # ---- tree fed by the prover's column-major LDE values (SURVEY 8(f) N1) -----------------------------------------------------
 def _reverse_index_bits(rows):
     """[UPSTREAM] plonky2_util::reverse_index_bits: out[i] = in[bit_reverse(i, log2 n)]"""

@@ -65,12 +65,14 @@ def main():
                               "digests": int(got.shape[0]), "ok": ok}), flush=True)
     # ---- sharded MMR (balanced rounds + tail) against one MMR built on rank 0's GPU ------------------------------------
     from plonky2_merkle_trees_b200 import mmr
-    for n in [1 << 14, (1 << 14) - 1, 100100, 77, world]:
+    # both forms: torch.distributed's all_gather between library calls, then pmt_mmr_build_sharded_dev (one call, ncclAllGather inside)
+    for n, in_lib in [(n, f) for f in (False, True) for n in [1 << 14, (1 << 14) - 1, 100100, 77, world]]:
+        eng_used = eng if in_lib else sharded.CudaEngine(ctx)
         leaves = bench.splitmix_numpy(7, n)
         rngs = sharded.mmr_shard_ranges(n, world, rank)
         mine = np.concatenate([leaves[a:a + c] for a, c in rngs]) if rngs else np.zeros(0, np.uint64)
         d_mine = torch.from_numpy(mine.view(np.int64)).to(dev)
-        sm = sharded.build_sharded_mmr(d_mine, n, eng)
+        sm = sharded.build_sharded_mmr(d_mine, n, eng_used)
         loc = torch.from_numpy(np.ascontiguousarray(sm.local.elements).view(np.int64)).to(dev)
         chunks = [torch.empty_like(loc) for _ in range(world)]
         if loc.numel():
@@ -96,7 +98,8 @@ def main():
                       and np.array_equal(bag, ref.bagging_the_peaks()) and int(okt.item()) == 1)
             ok_all &= ok
             print(json.dumps({"check": "sharded_mmr_vs_single", "world": world, "n_leaves": n, "rounds": len(sm.rounds),
-                              "tail": sm.plan[1], "elements": int(got.shape[0]), "ok": ok}), flush=True)
+                              "tail": sm.plan[1],
+                              "roots_exchange": "ncclAllGather inside libpmt" if in_lib else "torch.distributed all_gather", "elements": int(got.shape[0]), "ok": ok}), flush=True)
     flag = torch.tensor([1 if ok_all else 0], device=dev)
     dist.broadcast(flag, 0)
     dist.destroy_process_group()
