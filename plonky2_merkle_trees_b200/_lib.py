@@ -115,6 +115,11 @@ def exported_symbols():
     return sorted(_SIGNATURES)
 
 
+def signatures():
+    """name -> (restype, argtypes) as bound on the library (tests compare them with include/pmt.h)"""
+    return dict(_SIGNATURES)
+
+
 def as_u64(x, shape=None):
     a = np.ascontiguousarray(np.asarray(x, dtype=np.uint64))
     return a if shape is None else a.reshape(shape)

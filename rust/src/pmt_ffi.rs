@@ -58,6 +58,9 @@ extern "C" {
     pub fn pmt_comm_destroy(ctx: *mut pmt_ctx) -> c_int;
     pub fn pmt_merkle_tree_build_sharded_dev(ctx: *mut pmt_ctx, d_local_leaves: *const u64, n_total: usize, width: usize, cap_height: u32,
                                              d_local_digests: *mut u64, d_roots: *mut u64, d_top: *mut u64, d_cap: *mut u64) -> c_int;
+    pub fn pmt_mmr_shard_plan(n_total: usize, world: usize, n_rounds: *mut u32, m_out_64: *mut usize, tail: *mut usize) -> c_int;
+    pub fn pmt_mmr_build_sharded_dev(ctx: *mut pmt_ctx, d_local_leaves: *const u64, n_total: usize, d_local_elements: *mut u64,
+                                     d_tail_elements: *mut u64, d_gathered: *mut u64, d_tops: *mut u64, d_peaks: *mut u64) -> c_int;
     // MMR (merkle_mountain_ranges.rs)
     pub fn pmt_mmr_size(n_leaves: usize) -> usize;
     pub fn pmt_mmr_index(leaf_normal_index: usize) -> usize;

@@ -26,6 +26,49 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert [lib.pmt_mmr_size(n) for n in (0, 1, 2, 3, 4, 7, 8)] == [0, 1, 3, 4, 7, 11, 15]
 
 
+def _c_prototypes(header):
+    """name -> list of 'p' (pointer) / 's' (scalar) per parameter, from the prototypes of include/pmt.h"""
+    text = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    text = re.sub(r"//[^\n]*", " ", text)
+    out = {}
+    for name, args in re.findall(r"\b(pmt_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text):
+        args = " ".join(args.split())
+        kinds = [] if args in ("", "void") else ["p" if "*" in a else "s" for a in args.split(",")]
+        out[name] = kinds
+    return out
+
+
+def test_header_ctypes_table_and_rust_extern_block_agree():
+    """The ABI is declared three times -- include/pmt.h (the contract), _lib.py's ctypes signatures (what the tests and the
+    bench call through) and rust/src/pmt_ffi.rs (the crate a maintainer links; it cannot be compiled in this image) --:
+    every function they share must have the same number of parameters and the same pointer / scalar kind in each position."""
+    import ctypes as C
+    from plonky2_merkle_trees_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "pmt.h")).read()
+    protos = _c_prototypes(header)
+    assert len(protos) >= 60
+    # ctypes table: every declared function, exactly
+    sigs = _lib.signatures()
+    assert set(sigs) == set(protos)
+    for name, (_, argtypes) in sigs.items():
+        kinds = []
+        for t in argtypes:
+            is_ptr = t in (C.c_void_p, C.c_char_p) or hasattr(t, "contents") or (isinstance(t, type) and issubclass(t, C._Pointer))
+            kinds.append("p" if is_ptr else "s")
+        # the table lists the ctx handle first for the functions that take one, like the header
+        assert kinds == protos[name], (name, kinds, protos[name])
+    # Rust extern block: a subset of the header (what the wrappers use), same shapes
+    rs = open(os.path.join(ROOT, "rust", "src", "pmt_ffi.rs")).read()
+    rs = re.sub(r"//[^\n]*", " ", rs)
+    fns = re.findall(r"pub fn (pmt_[a-z0-9_]+)\s*\(([^;]*?)\)\s*(?:->\s*[^;]+)?;", rs, flags=re.S)
+    assert len(fns) >= 35
+    for name, args in fns:
+        assert name in protos, "rust/src/pmt_ffi.rs declares %s, include/pmt.h does not" % name
+        args = " ".join(args.split())
+        kinds = ["p" if "*" in a else "s" for a in args.split(",") if a.strip()]
+        assert kinds == protos[name], (name, kinds, protos[name])
+
+
 def test_no_cpu_fallback_without_device():
     import torch
     from plonky2_merkle_trees_b200 import PmtError, _lib
