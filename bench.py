@@ -228,9 +228,11 @@ def run_reference(args):
 
 
 def workload_config(n_gpus):
+    # the same in both arms (the driver pairs the lines by it); how the subtree roots travel is a property of the run and
+    # is reported beside it ("roots_exchange")
     return {"workload": "plonky2 MerkleTree::new, 2^%d leaves x %d felts per GPU, cap_height %d, upstream digests layout; "
-                        "N GPUs = one tree of N*2^%d leaves, subtree-sharded, ncclAllGather of the roots inside libpmt (pmt_merkle_tree_build_sharded_dev)" % (
-                            LOG2_LEAVES_PER_GPU, WIDTH, CAP_HEIGHT, LOG2_LEAVES_PER_GPU),
+                       "N GPUs = one tree of N*2^%d leaves, subtree-sharded, the roots exchanged inside libpmt (pmt_merkle_tree_build_sharded_dev)" % (
+                           LOG2_LEAVES_PER_GPU, WIDTH, CAP_HEIGHT, LOG2_LEAVES_PER_GPU),
             "leaves_per_gpu": 1 << LOG2_LEAVES_PER_GPU, "leaf_width": WIDTH, "cap_height": CAP_HEIGHT,
             "global_leaves": n_gpus << LOG2_LEAVES_PER_GPU, "parallelism": "subtree-shard x%d" % n_gpus,
             "l2_policy": "inputs (512 MiB leaves + 1 GiB digests per GPU) are larger than the 126 MB L2"}
@@ -368,7 +370,7 @@ def run_ours(args):
     ctx = _lib.Context(local_rank)
     eng = sharded.CudaEngine(ctx)
     if world > 1:
-        eng.comm_init()      # libpmt's own NCCL communicator: the roots are exchanged by ncclAllGather inside the library call
+        eng.comm_init()      # libpmt's own communicator: the roots are exchanged inside the library call (peer-memory mailboxes or ncclAllGather)
 
     n_local = 1 << LOG2_LEAVES_PER_GPU
     n_total = world * n_local
@@ -613,6 +615,9 @@ def run_ours(args):
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u64 (Goldilocks field, 32-bit IMAD limbs)", "data": "synthetic",
         "config": workload_config(world),
+        "roots_exchange": ("n/a (one GPU)" if world == 1 else
+                           "peer-memory mailboxes: P2P stores + flags fused with the top levels in one kernel (k_exchange_top)" if eng.peer_memory
+                           else "ncclAllGather inside libpmt, then a finish launch"),
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": "leaves/s", "h2d_bytes_per_step": n_local * WIDTH * 8,
                 "d2h_bytes_per_step": (n_dig + 1) * 32, "ms_per_step": e2e_ms,

@@ -148,6 +148,14 @@ int pmt_top_levels_batch_dev(pmt_ctx* ctx, const uint64_t* d_roots, size_t batch
                              uint64_t* d_top_out);
 
 /* ---- subtree-sharded MerkleTree::new, device resident ----------------------------------------------------------
+ * THE EXCHANGE.  Where every device can write its peers' memory (NVLink peer access inside one process, CUDA IPC mappings
+ * between the processes of a communicator) the subtree roots travel through per-context MAILBOXES and the exchange is fused
+ * with the levels above the roots in ONE kernel per context: it stores the context's root into every peer's mailbox with
+ * plain NVLink stores + a flag, spins (bounded) on the flags in its own mailbox, and finishes the top levels.  No NCCL call, no
+ * event, no copy on that path.  Otherwise -- PMT_EXCHANGE=nccl, no peer access, contexts that share a device, more than 64
+ * ranks or 64 digests per rank -- the forms below fall back to what their comments describe (peer copies + events, or
+ * ncclAllGather, then a separate finish launch); results are identical.  A peer that does not arrive within
+ * PMT_EXCHANGE_TIMEOUT_MS (default 20 000) is reported by the next pmt_sync as PMT_E_NCCL instead of hanging the device.
  * (1) ONE PROCESS, several GPUs: n_ctx = 2^g distinct contexts, one per device.  ctx r builds the subtree over ITS leaves
  * (d_leaves[r]: n / n_ctx rows on ctx r's device) into d_digests[r] (its contiguous slice of upstream's `digests`:
  * 2 (n / n_ctx - max(1, 2^(h-g))) digests on its device).  cap_height >= g: ctx r's 2^(h-g) cap entries go straight to
@@ -167,6 +175,9 @@ int pmt_merkle_tree_build_multi_dev(pmt_ctx* const* ctxs, size_t n_ctx, const ui
 int pmt_nccl_unique_id(pmt_ctx* ctx, void* id_out_128_bytes);
 int pmt_comm_init(pmt_ctx* ctx, const void* unique_id_128_bytes, int rank, int world);
 int pmt_comm_destroy(pmt_ctx* ctx);
+/* 1 if the ranks of this ctx's communicator exchange through peer-memory mailboxes (decided unanimously in pmt_comm_init), 0 if
+ * they use ncclAllGather */
+int pmt_comm_uses_peer_memory(const pmt_ctx* ctx);
 /* collective: this rank's n_total / world rows -> d_local_digests (its slice of `digests`).  cap_height >= log2 world: every
  * rank ends up with the whole cap in d_cap (2^h digests).  Otherwise d_roots (world digests) receives all subtree roots,
  * d_top (world - 2^h digests, level-major) the levels above them on EVERY rank, d_cap the cap.  One stream, no host sync:

@@ -59,6 +59,7 @@ _SIGNATURES = {
     "pmt_comm_init": (_INT, [_VP, _VP, _INT, _INT]),
     "pmt_comm_destroy": (_INT, [_VP]),
     "pmt_merkle_tree_build_sharded_dev": (_INT, [_VP, _VP, _SZ, _SZ, _U32, _VP, _VP, _VP, _VP]),
+    "pmt_comm_uses_peer_memory": (_INT, [_VP]),
     "pmt_mmr_shard_plan": (_INT, [_SZ, _SZ, u32p, C.POINTER(_SZ), C.POINTER(_SZ)]),  # no ctx: pure index math
     "pmt_mmr_build_sharded_dev": (_INT, [_VP, _VP, _SZ, _VP, _VP, _VP, _VP, _VP]),
     "pmt_top_levels_dev": (_INT, [_VP, _VP, _SZ, _U32, _VP]),

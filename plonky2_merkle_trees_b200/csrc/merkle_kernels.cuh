@@ -413,6 +413,91 @@ __global__ void __launch_bounds__(COOP_BLOCK) k_tree_coop(Layout lay_in, int l0,
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The exchange of a subtree-sharded build FUSED with the levels above it, over peer memory ("direct P2P stores
+// + flag").  Every rank owns a mailbox in its own HBM that its peers can write (one process: peer access; one process per
+// GPU: CUDA IPC mappings made by pmt_comm_init): MAIL_RING slots x MAIL_MAX_WORLD ranks x MAIL_DIGESTS digests + one flag
+// per (slot, rank).  Exchange number `seq` uses slot seq % MAIL_RING and the flag value seq + 1.
+//   push   thread p of block (0, 0) stores this rank's digests into peer p's mailbox (NVLink stores), fences system-wide, then
+//          stores the flag: a peer that sees the flag sees the digests
+//   wait   thread p of every block spins on the flag of rank p in its OWN mailbox (local memory, volatile loads)
+//   top    block y finishes set y: the G gathered roots of column y -> log2 G levels (Wide / Quad, digests handed on in shared
+//          memory) -> `tops`, and the last level's nodes -> `finals`
+// so the step that used to be ncclAllGather + a finish launch + a copy is ONE launch, and the transfer is 32 bytes per peer
+// written straight from the kernel.  A rank cannot get more than one exchange ahead of the slowest peer (it waits for all
+// peers' flags of exchange s before it leaves s), so a ring of 4 slots is never overwritten while in use.  The spin is bounded
+// (timeout_cycles): on expiry the block raises *fault (host-mapped) and pmt_sync reports it instead of hanging the device.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr unsigned MAIL_RING = 4, MAIL_MAX_WORLD = 64, MAIL_DIGESTS = 64;
+constexpr size_t MAIL_DATA_WORDS = (size_t)MAIL_RING * MAIL_MAX_WORLD * MAIL_DIGESTS * 4;
+constexpr size_t MAIL_BYTES = MAIL_DATA_WORDS * 8 + (size_t)MAIL_RING * MAIL_MAX_WORLD * 4;
+struct Exchange {
+  uint64_t* const* peers;        // device array [world]: base of every rank's mailbox as THIS device addresses it; peers[rank] = own
+  unsigned world, rank, seq;
+  long long timeout_cycles;
+  unsigned* fault;               // host-mapped word, set when a wait times out
+  __device__ __forceinline__ static uint64_t* data(uint64_t* base, unsigned slot, unsigned from) {
+    return base + ((size_t)slot * MAIL_MAX_WORLD + from) * MAIL_DIGESTS * 4;
+  }
+  __device__ __forceinline__ static unsigned* flag(uint64_t* base, unsigned slot, unsigned from) {
+    return reinterpret_cast<unsigned*>(base + MAIL_DATA_WORDS) + (size_t)slot * MAIL_MAX_WORLD + from;
+  }
+};
+
+// mine: this rank's n_mine digests (<= MAIL_DIGESTS).  gathered: world x n_mine digests, row p = rank p's (an output the callers
+// keep: d_roots / d_cap / the MMR's gathered matrix).  sets = gridDim.y sets of `world` roots = columns 0 .. sets - 1 of
+// `gathered` (sets = 0: gather only, gridDim.y = 1); set y's levels go to tops + 4 (world - 1) y (level-major, as TopRoots), the
+// n_final = world >> top_levels nodes of its last level to finals + 4 n_final y.  Block 0 also moves the columns that belong
+// to no set: into `gathered`, and the last rank's into finals + 4 n_final sets (the peaks of a sharded MMR's tail).
+__global__ void __launch_bounds__(COOP_BLOCK) k_exchange_top(Exchange x, const uint64_t* mine, unsigned n_mine, uint64_t* gathered,
+                                                              unsigned sets, uint64_t* tops, int top_levels, uint64_t* finals) {
+  // no __restrict__: `mine` is the rank's own row of `gathered` in the one-process-per-GPU forms
+  __shared__ CoopShared sh;
+  __shared__ KeepBuf kept;
+  const unsigned t = threadIdx.x, y = blockIdx.y, G = x.world, slot = x.seq % MAIL_RING, epoch = x.seq + 1u;
+  uint64_t* const own = x.peers[x.rank];
+  if (y == 0 && t < G && t != x.rank) {                       // push: one thread per peer
+    uint64_t* dst = Exchange::data(x.peers[t], slot, x.rank);
+    for (unsigned i = 0; i < 4 * n_mine; i++) dst[i] = mine[i];
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned*>(Exchange::flag(x.peers[t], slot, x.rank)) = epoch;
+  }
+  if (top_levels > 0) poseidon::coop::stage(sh);              // the tables load while the peers' stores are in flight
+  if (t < G && t != x.rank) {                                 // wait: one thread per peer
+    const volatile unsigned* f = Exchange::flag(own, slot, t);
+    const long long t0 = clock64();
+    while (*f != epoch) {
+      if (clock64() - t0 > x.timeout_cycles) { *reinterpret_cast<volatile unsigned*>(x.fault) = 1u + t; break; }
+      __nanosleep(64);
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  // this block's columns of the gathered matrix: column y (its set), and for block 0 every column outside the sets
+  const unsigned n_final = top_levels >= 0 ? G >> top_levels : 0;
+  for (unsigned i = t; i < G * 4 * n_mine; i += COOP_BLOCK) {
+    const unsigned p = i / (4 * n_mine), col = (i / 4) % n_mine, wd = i % 4;
+    const bool in_set = col < sets, my_col = in_set ? col == y : y == 0;
+    if (!my_col) continue;
+    const uint64_t v = p == x.rank ? mine[4 * col + wd] : __ldcv(Exchange::data(own, slot, p) + 4 * col + wd);
+    gathered[((size_t)p * n_mine + col) * 4 + wd] = v;
+    if (in_set) kept.region(0)[4 * p + wd] = v;
+    else if (finals && p == G - 1) finals[4 * ((size_t)n_final * sets + (col - sets)) + wd] = v;
+  }
+  if (sets == 0 || top_levels <= 0) return;
+  __syncthreads();
+  const Quad q = Quad::make(sh);
+  const Wide w = Wide::make(sh);
+  const TopRoots lay{gathered + 4 * y, tops + 4 * (size_t)(G - 1) * y, G, 0, 0, n_mine};
+  int parity = 1;
+  for (int j = 1; j <= top_levels; j++, parity ^= 1) {
+    coop_level(lay, j, 0, (size_t)(G >> j), kept.region(parity ^ 1), kept.region(parity), q, w, sh);
+    __syncthreads();
+  }
+  if (finals)
+    for (unsigned i = t; i < 4 * n_final; i += COOP_BLOCK) finals[4 * (size_t)n_final * y + i] = kept.region(parity ^ 1)[i];
+}
+
 // level 0 by groups of threads: digest(0, k0 + i) = hash_or_noop(row i) (NOOP_RULE) or hash_no_pad(row i).  The sponge's
 // permutations are sequential, so for few rows (a small FRI commitment, one bag of peaks) the cooperative forms cut the
 // latency 3 - 6x; the owner of element idx < 8 reads felt off + idx of every 8-felt block.  blockDim.x / Form::LANES rows

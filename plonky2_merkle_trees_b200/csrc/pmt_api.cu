@@ -101,12 +101,26 @@ struct pmt_ctx {
   // one process, several GPUs: the event that publishes this ctx's subtree root to ctxs[0] (pmt_merkle_tree_build_multi_dev)
   cudaEvent_t root_ready = nullptr;
   std::vector<int> peers;      // devices this ctx's device has been given peer access to
+  // the peer-memory exchange of the sharded builds (k_exchange_top): this ctx's mailbox, the table of every rank's mailbox as
+  // this device addresses it, and who the table belongs to (MAIL_COMM: the ranks of pmt_comm_init, mapped with CUDA IPC;
+  // MAIL_LOCAL: the contexts of one process, mail_group = their mailboxes in rank order)
+  uint64_t* mail = nullptr;
+  bool mail_exported = false;
+  uint64_t** d_peers = nullptr;
+  std::vector<void*> ipc_open;
+  int mail_mode = 0, mail_rank = 0, mail_world = 0;
+  std::vector<uint64_t*> mail_group;
+  unsigned xchg_seq = 0;
+  unsigned* fault_h = nullptr;
+  unsigned* fault_d = nullptr;
+  long long xchg_timeout_cycles = 0;
   // pageable caller buffers: library-owned page-locked staging slots (2 in, 2 out) and the copy threads
   void* stage[4] = {nullptr, nullptr, nullptr, nullptr};
   size_t stage_bytes[4] = {0, 0, 0, 0};
   HostCopyPool* pool = nullptr;
 };
 constexpr unsigned TICKET_RING = 4096;
+enum { MAIL_NONE = 0, MAIL_COMM = 1, MAIL_LOCAL = 2 };
 
 static inline void prof_begin(pmt_ctx* c, const char* name, double units) {
   if (!c->profiling) return;
@@ -418,6 +432,11 @@ void pmt_destroy(pmt_ctx* c) {
   if (c->tickets) cudaFree(c->tickets);
   if (c->comm) pmt_comm_destroy(c);
   if (c->root_ready) cudaEventDestroy(c->root_ready);
+  for (void* p : c->ipc_open) cudaIpcCloseMemHandle(p);
+  // a mailbox that was exported to other processes may still be mapped there: it is left to process teardown
+  if (c->mail && !c->mail_exported) cudaFree(c->mail);
+  if (c->d_peers) cudaFree(c->d_peers);
+  if (c->fault_h) cudaFreeHost(c->fault_h);
   for (void* p : c->stage) if (p) cudaFreeHost(p);
   delete c->pool;
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -439,6 +458,11 @@ void* pmt_get_stream(const pmt_ctx* c) { return c ? (void*)c->stream : nullptr; 
 int pmt_sync(pmt_ctx* c) {
   if (int rc = bind(c)) return rc;
   CU(c, cudaStreamSynchronize(c->stream));
+  if (c->fault_h && *c->fault_h) {            // a k_exchange_top gave up waiting for a peer: its outputs are garbage
+    const unsigned who = *c->fault_h - 1;
+    *c->fault_h = 0;
+    return fail(c, PMT_E_NCCL, "sharded build: rank %u did not deliver its subtree root within the exchange timeout (PMT_EXCHANGE_TIMEOUT_MS)", who);
+  }
   return PMT_OK;
 }
 uint64_t pmt_kernel_launches(const pmt_ctx* c) { return c ? c->launches : 0; }
@@ -744,6 +768,103 @@ int pmt_top_levels_batch_dev(pmt_ctx* c, const uint64_t* d_roots, size_t batch, 
   return PMT_OK;
 }
 
+// ---- the peer-memory exchange (k_exchange_top): mailboxes, peer tables -------------------------------------------------------
+// PMT_EXCHANGE=nccl keeps the sharded builds on ncclAllGather / peer copies + a separate finish launch (the A/B knob and the
+// fallback when peers cannot map each other's memory); anything else: mailboxes where they can be set up.
+static bool exchange_wanted() {
+  const char* e = getenv("PMT_EXCHANGE");
+  return !(e && (!strcmp(e, "nccl") || !strcmp(e, "copy") || !strcmp(e, "0")));
+}
+static int mail_alloc(pmt_ctx* c) {
+  if (!c->mail) {
+    CU(c, cudaMalloc((void**)&c->mail, MAIL_BYTES));
+    CU(c, cudaMalloc((void**)&c->d_peers, MAIL_MAX_WORLD * sizeof(uint64_t*)));
+    CU(c, cudaHostAlloc((void**)&c->fault_h, sizeof(unsigned), cudaHostAllocMapped));
+    *c->fault_h = 0;
+    CU(c, cudaHostGetDevicePointer((void**)&c->fault_d, c->fault_h, 0));
+    int khz = 0;
+    CU(c, cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c->device));
+    long long ms = 20000;                          // a peer that has not arrived after 20 s is reported, not waited for
+    if (const char* e = getenv("PMT_EXCHANGE_TIMEOUT_MS")) { const long long v = atoll(e); if (v > 0) ms = v; }
+    c->xchg_timeout_cycles = ms * (long long)(khz > 0 ? khz : 1965000);
+  }
+  // stream first: a kernel of an earlier group may still be reading the mailbox
+  CU(c, cudaStreamSynchronize(c->stream));
+  CU(c, cudaMemset(c->mail, 0, MAIL_BYTES));
+  c->xchg_seq = 0;
+  return PMT_OK;
+}
+static void mail_close_peers(pmt_ctx* c) {
+  for (void* p : c->ipc_open) cudaIpcCloseMemHandle(p);
+  c->ipc_open.clear();
+  c->mail_mode = MAIL_NONE;
+  c->mail_group.clear();
+}
+// one launch: push `mine`, wait for every peer, gather, finish `sets` sets of `world` roots (see k_exchange_top)
+static int launch_exchange(pmt_ctx* c, const uint64_t* d_mine, size_t n_mine, uint64_t* d_gathered, size_t sets, uint64_t* d_tops,
+                           int top_levels, uint64_t* d_finals) {
+  const Exchange x{c->d_peers, (unsigned)c->mail_world, (unsigned)c->mail_rank, c->xchg_seq++, c->xchg_timeout_cycles, c->fault_d};
+  TAG(c, "k_exchange_top", sets * ((size_t)c->mail_world - ((size_t)c->mail_world >> top_levels)));
+  k_exchange_top<<<dim3(1, (unsigned)(sets ? sets : 1)), COOP_BLOCK, 0, c->stream>>>(x, d_mine, (unsigned)n_mine, d_gathered, (unsigned)sets,
+                                                                                    d_tops, top_levels, d_finals);
+  CHECK_LAUNCH(c);
+  return PMT_OK;
+}
+// the contexts of ONE process as an exchange group (rank = position in ctxs): every device must be able to write every other
+// device's memory.  Returns false (and leaves the contexts usable for the copy path) when that cannot be arranged.
+static bool mail_local_group(pmt_ctx* const* ctxs, size_t n) {
+  if (!exchange_wanted() || n < 2 || n > MAIL_MAX_WORLD) return false;
+  bool cached = true;
+  for (size_t i = 0; i < n && cached; i++) {
+    pmt_ctx* c = ctxs[i];
+    cached = c->mail_mode == MAIL_LOCAL && c->mail_rank == (int)i && c->mail_group.size() == n;
+    for (size_t j = 0; j < n && cached; j++) cached = c->mail_group[j] == ctxs[j]->mail && ctxs[j]->mail;
+  }
+  if (cached) return true;
+  for (size_t i = 0; i < n; i++) if (ctxs[i]->mail_mode == MAIL_COMM) return false;   // owned by a communicator
+  for (size_t i = 0; i < n; i++)                  // a kernel of an earlier group may still be writing a mailbox that is re-zeroed below
+    if (cudaSetDevice(ctxs[i]->device) != cudaSuccess || cudaStreamSynchronize(ctxs[i]->stream) != cudaSuccess) return false;
+  // Contexts that share a device keep the copy path: their streams may share a hardware queue, and a kernel that spins on a
+  // flag would then block the very kernel that sets it (PMT_EXCHANGE_SAME_DEVICE=1: the test hook for one-GPU boxes).
+  const char* same = getenv("PMT_EXCHANGE_SAME_DEVICE");
+  const bool same_ok = same && !strcmp(same, "1");
+  for (size_t a = 0; a < n; a++)
+    for (size_t b = 0; b < n; b++) {
+      if (ctxs[a]->device == ctxs[b]->device) {
+        if (a != b && !same_ok) return false;
+        continue;
+      }
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, ctxs[a]->device, ctxs[b]->device) != cudaSuccess || !can) { cudaGetLastError(); return false; }
+    }
+  for (size_t i = 0; i < n; i++) {
+    pmt_ctx* c = ctxs[i];
+    if (cudaSetDevice(c->device) != cudaSuccess) return false;
+    mail_close_peers(c);
+    if (mail_alloc(c) != PMT_OK) return false;
+    for (size_t b = 0; b < n; b++) {
+      const int dev = ctxs[b]->device;
+      if (dev == c->device || std::find(c->peers.begin(), c->peers.end(), dev) != c->peers.end()) continue;
+      const cudaError_t e = cudaDeviceEnablePeerAccess(dev, 0);
+      cudaGetLastError();
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return false;
+      c->peers.push_back(dev);
+    }
+  }
+  std::vector<uint64_t*> table(MAIL_MAX_WORLD, nullptr);
+  for (size_t i = 0; i < n; i++) table[i] = ctxs[i]->mail;
+  for (size_t i = 0; i < n; i++) {
+    pmt_ctx* c = ctxs[i];
+    if (cudaSetDevice(c->device) != cudaSuccess) return false;
+    if (cudaMemcpy(c->d_peers, table.data(), MAIL_MAX_WORLD * sizeof(uint64_t*), cudaMemcpyHostToDevice) != cudaSuccess) return false;
+    c->mail_mode = MAIL_LOCAL;
+    c->mail_rank = (int)i;
+    c->mail_world = (int)n;
+    c->mail_group.assign(table.begin(), table.begin() + n);
+  }
+  return true;
+}
+
 // ---- subtree-sharded MerkleTree::new, device resident ---------------------------------------------------------------------
 static int check_ctxs(pmt_ctx* const* ctxs, size_t n_ctx, const char* who);
 // the validation + local build shared by the two sharded forms: rank r of G = 2^g builds its n / G rows with the local cap
@@ -775,10 +896,38 @@ int pmt_merkle_tree_build_multi_dev(pmt_ctx* const* ctxs, size_t n_ctx, const ui
   const bool gather = (int)cap_height < g;
   if (gather && (!d_roots || (!d_top && n_ctx > 1))) return fail(c0, PMT_E_INVALID_ARG, "multi build: null d_roots / d_top");
   const size_t cap_l = gather ? 1 : (size_t)1 << (cap_height - (uint32_t)g);
-  // what context r enqueues on its own device: its subtree, the peer copy of its root / cap entries to device 0, an event
+  // Mailbox form: every context pushes its root / cap entries into every other context's mailbox and finishes the top itself
+  // (k_exchange_top: one launch per context, no events, no copies); ctxs[0] writes the caller's d_roots / d_top / d_cap, the
+  // others write scratch.  pmt_sync(ctxs[0]) still orders after every context's subtree: ctxs[0]'s kernel has seen their flags.
+  const bool mailbox = n_ctx > 1 && cap_l <= MAIL_DIGESTS && mail_local_group(ctxs, n_ctx);
+  const size_t n_cap = (size_t)1 << cap_height;
+  // arena 2 of a context in the mailbox form: [64 digests + 64 B: other calls' scratch][mine: cap_l][gathered: G cap_l][tops: G][finals: n_cap].
+  // Allocated for ALL contexts before anything is launched: cudaFree / cudaMalloc may wait for the device, and a context's
+  // exchange kernel waits for its peers -- whose launches would then never be enqueued.
+  const size_t mail_words = 64 * 4 + 8 + 4 * (cap_l + n_ctx * cap_l + n_ctx + n_cap);
+  if (mailbox)
+    for (size_t r = 0; r < n_ctx; r++) {
+      void* stage = nullptr;
+      if (int rc = bind(ctxs[r])) return rc;
+      if (int rc = arena_get(ctxs[r], 2, mail_words * 8, &stage)) {
+        char msg[sizeof ctxs[r]->err];
+        memcpy(msg, ctxs[r]->err, sizeof msg);
+        msg[sizeof msg - 1] = 0;
+        return fail(c0, rc, "multi build: ctx %zu (device %d): %.400s", r, ctxs[r]->device, msg);
+      }
+    }
+  // what context r enqueues on its own device: its subtree, then the exchange (mailbox) or the peer copy of its root / cap
+  // entries to device 0 and an event
   auto enqueue = [&](size_t r) -> int {
     pmt_ctx* c = ctxs[r];
     if (int rc = bind(c)) return rc;
+    if (mailbox) {
+      uint64_t* d_mine = (uint64_t*)c->arena[2] + 64 * 4 + 8;
+      uint64_t* sc_gathered = d_mine + 4 * cap_l, *sc_tops = sc_gathered + 4 * n_ctx * cap_l, *sc_finals = sc_tops + 4 * n_ctx;
+      if (int rc = sharded_local_build(c, d_leaves[r], n, w, cap_height, g, d_digests[r], d_mine)) return rc;
+      if (gather) return launch_exchange(c, d_mine, 1, r ? sc_gathered : d_roots, 1, r ? sc_tops : d_top, g - (int)cap_height, r ? sc_finals : d_cap);
+      return launch_exchange(c, d_mine, cap_l, r ? sc_gathered : d_cap, 0, nullptr, 0, nullptr);
+    }
     if (c->device != c0->device && std::find(c->peers.begin(), c->peers.end(), c0->device) == c->peers.end()) {
       int can = 0;                                   // let device r write device 0's memory (NVLink peer access), once
       CU(c, cudaDeviceCanAccessPeer(&can, c->device, c0->device));
@@ -813,10 +962,10 @@ int pmt_merkle_tree_build_multi_dev(pmt_ctx* const* ctxs, size_t n_ctx, const ui
       return fail(c0, rcs[r], "multi build: ctx %zu (device %d): %.400s", r, ctxs[r]->device, msg);
     }
   if (int rc = bind(c0)) return rc;
+  if (mailbox) return PMT_OK;
   for (size_t r = 1; r < n_ctx; r++) CU(c0, cudaStreamWaitEvent(c0->stream, ctxs[r]->root_ready, 0));
   if (!gather) return PMT_OK;
   if (int rc = pmt_top_levels_dev(c0, d_roots, n_ctx, cap_height, d_top)) return rc;
-  const size_t n_cap = (size_t)1 << cap_height;
   CU(c0, cudaMemcpyAsync(d_cap, d_top + 4 * (n_ctx - 2 * n_cap), n_cap * 32, cudaMemcpyDeviceToDevice, c0->stream));
   return PMT_OK;
 }
@@ -859,6 +1008,53 @@ NcclApi* nccl_api() {
     if (r_ != ncclSuccess) return fail((c), PMT_E_NCCL, "%s: %s (%s:%d)", #call, nccl_api()->GetErrorString(r_), __FILE__, __LINE__); \
   } while (0)
 
+// The ranks of a communicator as an exchange group: every rank exports its mailbox (CUDA IPC), the handles travel by
+// ncclAllGather, every rank maps its peers' mailboxes, and a second all-gather makes the decision unanimous -- either all
+// ranks use k_exchange_top or all stay on ncclAllGather (ranks inside one process, or devices without peer access).
+static int comm_setup_mail(pmt_ctx* c) {
+  const int G = c->comm_world, r = c->comm_rank;
+  if (G < 2 || G > (int)MAIL_MAX_WORLD || !exchange_wanted()) return PMT_OK;
+  NcclApi* a = nccl_api();
+  struct Info { cudaIpcMemHandle_t h; int ok; int pad; };
+  static_assert(sizeof(Info) == 72, "Info is gathered as bytes");
+  if (int rc = mail_alloc(c)) return rc;
+  Info mine{};
+  mine.ok = cudaIpcGetMemHandle(&mine.h, c->mail) == cudaSuccess;
+  cudaGetLastError();
+  c->mail_exported = c->mail_exported || mine.ok;
+  void* buf = nullptr;
+  if (int rc = arena_get(c, 2, (size_t)G * sizeof(Info), &buf)) return rc;
+  std::vector<Info> all((size_t)G);
+  auto gather = [&](const Info& v) -> int {
+    CU(c, cudaMemcpyAsync((char*)buf + (size_t)r * sizeof(Info), &v, sizeof(Info), cudaMemcpyHostToDevice, c->stream));
+    NC(c, a->AllGather((char*)buf + (size_t)r * sizeof(Info), buf, sizeof(Info), ncclChar, c->comm, c->stream));
+    CU(c, cudaMemcpyAsync(all.data(), buf, (size_t)G * sizeof(Info), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return PMT_OK;
+  };
+  if (int rc = gather(mine)) return rc;
+  std::vector<uint64_t*> table(MAIL_MAX_WORLD, nullptr);
+  bool ok = true;
+  for (int p = 0; p < G; p++) ok = ok && all[(size_t)p].ok;
+  for (int p = 0; p < G && ok; p++) {
+    if (p == r) { table[(size_t)p] = c->mail; continue; }
+    void* ptr = nullptr;
+    if (cudaIpcOpenMemHandle(&ptr, all[(size_t)p].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+    c->ipc_open.push_back(ptr);
+    table[(size_t)p] = (uint64_t*)ptr;
+  }
+  Info vote{};
+  vote.ok = ok;
+  if (int rc = gather(vote)) return rc;
+  for (int p = 0; p < G; p++) ok = ok && all[(size_t)p].ok;
+  if (!ok) { mail_close_peers(c); return PMT_OK; }
+  CU(c, cudaMemcpy(c->d_peers, table.data(), MAIL_MAX_WORLD * sizeof(uint64_t*), cudaMemcpyHostToDevice));
+  c->mail_mode = MAIL_COMM;
+  c->mail_rank = r;
+  c->mail_world = G;
+  return PMT_OK;
+}
+
 int pmt_nccl_unique_id(pmt_ctx* c, void* id_out) {
   if (!c || !id_out) return PMT_E_INVALID_ARG;
   NcclApi* a = nccl_api();
@@ -880,13 +1076,16 @@ int pmt_comm_init(pmt_ctx* c, const void* unique_id, int rank, int world) {
   NC(c, a->CommInitRank(&c->comm, world, id, rank));
   c->comm_rank = rank;
   c->comm_world = world;
-  return PMT_OK;
+  if (c->mail_mode != MAIL_NONE) mail_close_peers(c);
+  return comm_setup_mail(c);
 }
+int pmt_comm_uses_peer_memory(const pmt_ctx* c) { return c && c->comm && c->mail_mode == MAIL_COMM ? 1 : 0; }
 int pmt_comm_destroy(pmt_ctx* c) {
   if (!c) return PMT_E_INVALID_ARG;
   if (c->comm) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->mail_mode == MAIL_COMM) mail_close_peers(c);
     nccl_api()->CommDestroy(c->comm);
     c->comm = nullptr;
     c->comm_world = 0;
@@ -903,14 +1102,18 @@ int pmt_merkle_tree_build_sharded_dev(pmt_ctx* c, const uint64_t* d_local_leaves
   if (int rc = sharded_check(c, G, n, w, cap_height, &g)) return rc;
   if (!d_local_leaves || !d_cap) return fail(c, PMT_E_INVALID_ARG, "sharded build: null pointer");
   NcclApi* a = nccl_api();
+  const bool mailbox = G > 1 && c->mail_mode == MAIL_COMM;     // unanimous among the ranks (comm_setup_mail)
   if ((int)cap_height >= g) {            // every rank yields 2^(h-g) cap entries: gathered in place into d_cap
     const size_t cap_l = (size_t)1 << (cap_height - (uint32_t)g);
     if (int rc = sharded_local_build(c, d_local_leaves, n, w, cap_height, g, d_local_digests, d_cap + 4 * r * cap_l)) return rc;
+    if (mailbox && cap_l <= MAIL_DIGESTS) return launch_exchange(c, d_cap + 4 * r * cap_l, cap_l, d_cap, 0, nullptr, 0, nullptr);
     if (G > 1) NC(c, a->AllGather(d_cap + 4 * r * cap_l, d_cap, 4 * cap_l, ncclUint64, c->comm, c->stream));
     return PMT_OK;
   }
   if (!d_roots || !d_top) return fail(c, PMT_E_INVALID_ARG, "sharded build: null d_roots / d_top");
   if (int rc = sharded_local_build(c, d_local_leaves, n, w, cap_height, g, d_local_digests, d_roots + 4 * r)) return rc;
+  // exchange + the g - h levels above the roots + the cap: ONE launch over peer memory
+  if (mailbox) return launch_exchange(c, d_roots + 4 * r, 1, d_roots, 1, d_top, g - (int)cap_height, d_cap);
   NC(c, a->AllGather(d_roots + 4 * r, d_roots, 4, ncclUint64, c->comm, c->stream));
   if (int rc = pmt_top_levels_dev(c, d_roots, G, cap_height, d_top)) return rc;
   const size_t n_cap = (size_t)1 << cap_height;
@@ -1578,6 +1781,8 @@ int pmt_mmr_build_sharded_dev(pmt_ctx* c, const uint64_t* d_local_leaves, size_t
     k_mmr_peaks<<<1, 64, 0, c->stream>>>(Mmr{d_tail_elements}, t, mine + 4 * k);
     CHECK_LAUNCH(c);
   }
+  if (G > 1 && c->mail_mode == MAIL_COMM && slots <= MAIL_DIGESTS)      // exchange + every round's finish + the peaks: ONE launch
+    return launch_exchange(c, mine, slots, d_gathered, k, d_tops, log2_strict(G), d_peaks);
   if (G > 1) NC(c, nccl_api()->AllGather(mine, d_gathered, 4 * slots, ncclUint64, c->comm, c->stream));
   if (k && G > 1) {      // round i: roots = column i of the gathered matrix (slots digests apart), finished in set i
     TopRoots lay{d_gathered, d_tops, G, 1, G - 1, slots};

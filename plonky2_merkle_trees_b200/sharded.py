@@ -55,6 +55,7 @@ class CudaEngine:
         self.ctx = ctx
         self.device = torch.device("cuda:%d" % ctx.device)
         self.has_comm = False
+        self.peer_memory = False      # set by comm_init: the ranks exchange through peer-memory mailboxes (k_exchange_top)
 
     def build_local(self, d_leaves, cap_height):
         n, w = d_leaves.shape
@@ -81,9 +82,10 @@ class CudaEngine:
         self.ctx.sync()
 
     def comm_init(self, group=None):
-        """Give the ctx its own NCCL communicator (pmt_comm_init): rank 0 creates the unique id, torch.distributed carries it
-        to the other ranks (plumbing), every rank joins.  After this build_sharded_tree runs as ONE library call on ONE
-        stream: local build -> ncclAllGather of the roots -> top levels."""
+        """Give the ctx its own communicator (pmt_comm_init): rank 0 creates the unique id, torch.distributed carries it to the
+        other ranks (plumbing), every rank joins and maps its peers' mailboxes (CUDA IPC).  After this build_sharded_tree runs
+        as ONE library call on ONE stream: local build -> k_exchange_top (the roots stored straight into the peers' memory,
+        the top levels in the same launch); where peers cannot map each other: ncclAllGather -> top levels."""
         import ctypes as C
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         buf = (C.c_char * 128)()
@@ -94,6 +96,7 @@ class CudaEngine:
         raw = bytes(t.cpu().tolist())
         self.ctx.call("pmt_comm_init", C.cast(C.create_string_buffer(raw, 128), C.c_void_p), rank, world)
         self.has_comm = True
+        self.peer_memory = bool(self.ctx.lib.pmt_comm_uses_peer_memory(self.ctx.h))
 
     def build_sharded(self, d_local_leaves, n_total, cap_height, world):
         """pmt_merkle_tree_build_sharded_dev -> (local digests, roots or None, top or None, cap); enqueued only"""

@@ -1126,6 +1126,18 @@ def test_multi_gpu_nccl_parity_under_torchrun():
     assert '"ok": false' not in r.stdout
 
 
+def test_peer_memory_exchange_on_one_device():
+    """k_exchange_top -- the subtree roots pushed into the peers' mailboxes with plain stores + flags, the bounded wait, the top
+    levels, all in one launch per context -- exercised on a one-GPU box by 2 .. 8 contexts that share cuda:0 (a hook: such
+    contexts normally keep the copy path), 11 exchanges in a row (the ring has 4 slots), against the oracle and the copy path.
+    With >= 2 GPUs the same kernel runs over NVLink in test_multi_context_device_resident_build... and under torchrun."""
+    import os, subprocess, sys
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "run_mailbox_same_device.py")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert '"ok": false' not in r.stdout and r.stdout.count('"exchange": "mailbox"') >= 9
+
+
 @pytest.mark.parametrize("lg,w,h,G", [(10, 4, 0, 8), (10, 4, 1, 4), (10, 4, 3, 8), (9, 135, 4, 8), (8, 4, 5, 8), (6, 1, 0, 2), (5, 4, 0, 1),
                                       (15, 7, 0, 4), (16, 4, 2, 2)])
 def test_multi_context_device_resident_build_with_peer_copies(ctx_pool, api, oracle, lg, w, h, G):

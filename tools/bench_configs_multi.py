@@ -55,11 +55,12 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     ctx = _lib.Context(local_rank)
     eng = sharded.CudaEngine(ctx)
-    eng.comm_init()      # the roots are exchanged by ncclAllGather inside libpmt (pmt_merkle_tree_build_sharded_dev)
+    eng.comm_init()      # the roots are exchanged inside libpmt (peer-memory mailboxes, or ncclAllGather with PMT_EXCHANGE=nccl)
     only = sys.argv[1:] or ["C4", "C5", "C3"]
 
     def emit(**kw):
         if rank == 0:
+            kw["roots_exchange"] = "peer-memory mailboxes (k_exchange_top)" if eng.peer_memory else "ncclAllGather"
             print(json.dumps(kw), flush=True)
 
     for name, lg, w, h in [("C4", 20, 135, 4), ("C5", 28, 4, 0)]:

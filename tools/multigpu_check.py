@@ -37,19 +37,25 @@ def main():
     eng = sharded.CudaEngine(ctx)
     ok_all = True
     cases = [(14, 4, 0), (14, 1, 0), (12, 135, 4), (13, 9, 1), (16, 4, 5), (10, 4, 3)]
-    # every case twice: the roots exchanged by torch.distributed's all_gather (plumbing in Python), then by ncclAllGather inside
-    # libpmt on the ctx's own stream (pmt_comm_init + pmt_merkle_tree_build_sharded_dev: one call, no host sync)
-    for lg, w, h, in_lib in [c + (False,) for c in cases] + [c + (True,) for c in cases]:
-        if in_lib and not eng.has_comm:
-            eng.comm_init()
-        eng_used = eng
-        if not in_lib:
-            eng_used = sharded.CudaEngine(ctx)          # same ctx, no communicator: the torch path
+    # every case three times: the roots exchanged by torch.distributed's all_gather (plumbing in Python), then inside libpmt on
+    # the ctx's own stream (pmt_comm_init + pmt_merkle_tree_build_sharded_dev: one call, no host sync) -- through peer-memory
+    # mailboxes (k_exchange_top) where the ranks can map each other, and with PMT_EXCHANGE=nccl through ncclAllGather
+    eng_nccl = sharded.CudaEngine(_lib.Context(local_rank))
+    os.environ["PMT_EXCHANGE"] = "nccl"
+    eng_nccl.comm_init()
+    os.environ.pop("PMT_EXCHANGE")
+    eng.comm_init()
+    assert not eng_nccl.peer_memory
+    engines = {"torch": sharded.CudaEngine(ctx), "lib": eng, "lib-nccl": eng_nccl}     # "torch": same ctx, no communicator
+    label = {"torch": "torch.distributed all_gather", "lib-nccl": "ncclAllGather inside libpmt",
+             "lib": "peer-memory mailboxes inside libpmt" if eng.peer_memory else "ncclAllGather inside libpmt (no peer mapping)"}
+    for lg, w, h, how in [c + (m,) for m in engines for c in cases]:
+        eng_used = engines[how]
         n = 1 << lg
         per = n // world
         d_local = bench.splitmix_torch(rank * per * w, per * w, dev).view(per, w)
         tree = sharded.build_sharded_tree(d_local, n, h, eng_used)
-        eng.sync()
+        eng_used.sync()
         chunk = tree.local_digests.contiguous()
         chunks = [torch.empty_like(chunk) for _ in range(world)] if rank == 0 else None
         dist.gather(chunk, chunks, dst=0)
@@ -61,13 +67,13 @@ def main():
             ok = bool(np.array_equal(got, ref.digests) and np.array_equal(cap, ref.cap))
             ok_all &= ok
             print(json.dumps({"check": "sharded_vs_single", "world": world, "log2_n": lg, "width": w, "cap_height": h,
-                              "roots_exchange": "ncclAllGather inside libpmt" if in_lib else "torch.distributed all_gather",
+                              "roots_exchange": label[how],
                               "digests": int(got.shape[0]), "ok": ok}), flush=True)
     # ---- sharded MMR (balanced rounds + tail) against one MMR built on rank 0's GPU ------------------------------------
     from plonky2_merkle_trees_b200 import mmr
-    # both forms: torch.distributed's all_gather between library calls, then pmt_mmr_build_sharded_dev (one call, ncclAllGather inside)
-    for n, in_lib in [(n, f) for f in (False, True) for n in [1 << 14, (1 << 14) - 1, 100100, 77, world]]:
-        eng_used = eng if in_lib else sharded.CudaEngine(ctx)
+    # the three forms again: torch.distributed's all_gather between library calls, then pmt_mmr_build_sharded_dev (one call)
+    for n, how in [(n, m) for m in engines for n in [1 << 14, (1 << 14) - 1, 100100, 77, world]]:
+        eng_used = engines[how]
         leaves = bench.splitmix_numpy(7, n)
         rngs = sharded.mmr_shard_ranges(n, world, rank)
         mine = np.concatenate([leaves[a:a + c] for a, c in rngs]) if rngs else np.zeros(0, np.uint64)
@@ -99,7 +105,7 @@ def main():
             ok_all &= ok
             print(json.dumps({"check": "sharded_mmr_vs_single", "world": world, "n_leaves": n, "rounds": len(sm.rounds),
                               "tail": sm.plan[1],
-                              "roots_exchange": "ncclAllGather inside libpmt" if in_lib else "torch.distributed all_gather", "elements": int(got.shape[0]), "ok": ok}), flush=True)
+                              "roots_exchange": label[how], "elements": int(got.shape[0]), "ok": ok}), flush=True)
     flag = torch.tensor([1 if ok_all else 0], device=dev)
     dist.broadcast(flag, 0)
     dist.destroy_process_group()
