@@ -56,6 +56,7 @@ extern "C" {
     pub fn pmt_nccl_unique_id(ctx: *mut pmt_ctx, id_out_128_bytes: *mut c_void) -> c_int;
     pub fn pmt_comm_init(ctx: *mut pmt_ctx, unique_id_128_bytes: *const c_void, rank: c_int, world: c_int) -> c_int;
     pub fn pmt_comm_destroy(ctx: *mut pmt_ctx) -> c_int;
+    pub fn pmt_comm_uses_peer_memory(ctx: *const pmt_ctx) -> c_int;
     pub fn pmt_merkle_tree_build_sharded_dev(ctx: *mut pmt_ctx, d_local_leaves: *const u64, n_total: usize, width: usize, cap_height: u32,
                                              d_local_digests: *mut u64, d_roots: *mut u64, d_top: *mut u64, d_cap: *mut u64) -> c_int;
     pub fn pmt_mmr_shard_plan(n_total: usize, world: usize, n_rounds: *mut u32, m_out_64: *mut usize, tail: *mut usize) -> c_int;
