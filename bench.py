@@ -387,6 +387,22 @@ def run_ours(args):
     def step():
         return sharded.build_sharded_tree(d_leaves, n_total, CAP_HEIGHT, eng)
 
+    # One untimed build first.  If the peer-memory exchange cannot complete on this box (a rank's mailbox mapped but not
+    # reachable: the kernel's bounded wait reports it through pmt_sync), ALL ranks fall back to ncclAllGather together and the
+    # line says so in "roots_exchange" -- a slower exchange, never a hang and never a different result.
+    if world > 1 and eng.peer_memory:
+        ok = 1
+        try:
+            step()
+            ctx.sync()
+        except _lib.PmtError as e:
+            ok = 0
+            print("rank %d: peer-memory exchange failed (%s); falling back to ncclAllGather" % (rank, e), file=sys.stderr, flush=True)
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            os.environ["PMT_EXCHANGE"] = "nccl"
+            eng.comm_init()
     tree = None
     for _ in range(max(args.warmup, 3)):
         tree = step()
