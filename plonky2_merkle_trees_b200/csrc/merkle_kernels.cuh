@@ -254,6 +254,78 @@ __global__ void __launch_bounds__(BLOCK, PMT_MINB) k_level(Layout lay, int l, si
   }
 }
 
+// SEVERAL consecutive big levels in ONE launch, as a wavefront.  One launch per level pays a drain at the end of every level
+// (the last blocks run alone at a fraction of the machine's throughput: 11 - 22 us per level, profiles/launches_r2_summary.txt)
+// although almost all of the next level's nodes have had their children for a long time.  Here the blocks of level la come
+// first, then those of la + 1, ...: a block of level l + 1 owns 128 nodes whose children are exactly the level-l blocks 2 b and
+// 2 b + 1 (level l starts at an even node: bit l of n0 is 0, checked by the host), waits for their two flags -- set long ago
+// except at the very end of a level -- and runs while the level below drains.  The logical block number is taken from a
+// counter when the block STARTS, so a block only ever waits for blocks that started before it: no deadlock whatever order the
+// hardware dispatches in.  Flags carry the launch's epoch (never reset); the wait is bounded like k_exchange_top's.
+// Level l has the nodes [n0 >> l, n1 >> l), as in launch_level_span.
+// rows != nullptr: la == 1 and the first level is computed from the narrow leaf rows (w <= 4) themselves, as k_leaves_level1
+// does: thread i pads rows 2 i and 2 i + 1 (relative to `rows`, the first leaf of the range) into their level-0 digests, stores
+// both and hashes their parent -- the whole build of a big tree of narrow leaves below the cooperative tail is then ONE launch.
+template <class Layout>
+__global__ void __launch_bounds__(BLOCK, PMT_MINB) k_levels_wave(Layout lay, int la, int n_levels, size_t n0, size_t n1,
+                                                                 unsigned* __restrict__ flags, unsigned epoch, unsigned* __restrict__ counter,
+                                                                 long long timeout_cycles, unsigned* fault,
+                                                                 const uint64_t* __restrict__ rows, size_t w) {
+  __shared__ unsigned s_id;
+  if (threadIdx.x == 0) {
+    s_id = atomicAdd(counter, 1u);
+    if (s_id == gridDim.x - 1) *counter = 0;             // every number has been handed out: ready for the next launch
+  }
+  __syncthreads();
+  size_t id = s_id, off = 0, prev_blocks = 0, k0 = 0, cnt = 0;
+  int j = 0;
+  for (;; j++) {                                         // which level this block belongs to, and which block of it
+    k0 = n0 >> (la + j);
+    cnt = (n1 >> (la + j)) - k0;
+    const size_t nb = (cnt + BLOCK - 1) / BLOCK;
+    if (id < nb || j + 1 == n_levels) break;
+    id -= nb;
+    off += nb;
+    prev_blocks = nb;
+  }
+  if (j > 0) {                                           // the two blocks of the level below that hold this block's children
+    if (threadIdx.x < 2) {
+      const size_t child = 2 * id + threadIdx.x;
+      if (child < prev_blocks) {
+        const volatile unsigned* f = flags + (off - prev_blocks) + child;
+        const long long t0 = clock64();
+        while (*f != epoch) {
+          if (clock64() - t0 > timeout_cycles) { *reinterpret_cast<volatile unsigned*>(fault) = 0x80000000u; break; }
+          __nanosleep(32);
+        }
+      }
+      __threadfence();
+    }
+    __syncthreads();
+  }
+  const size_t i = id * BLOCK + threadIdx.x;
+  if (i < cnt) {
+    Digest l, r;
+    if (rows != nullptr && j == 0) {                     // leaf rows -> level 0 (a canonicalising copy) -> level 1
+      l = hash_or_noop(rows + (2 * i) * w, w);
+      r = hash_or_noop(rows + (2 * i + 1) * w, w);
+      store_digest(lay.at(0, 2 * (k0 + i)), l);
+      store_digest(lay.at(0, 2 * (k0 + i) + 1), r);
+    } else {
+      const uint64_t *a, *b;
+      lay.children(la + j, k0 + i, a, b);                // ld.cg: the children may have been written by another SM in this launch
+#pragma unroll
+      for (int q = 0; q < 4; q++) { l.v[q] = __ldcg(a + q); r.v[q] = __ldcg(b + q); }
+    }
+    store_digest(lay.at(la + j, k0 + i), two_to_one(l, r));
+  }
+  if (j + 1 < n_levels) {                                // publish: every thread's digests device-wide, then the block's flag
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned*>(flags + off + id) = epoch;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // cooperative kernels (several threads per permutation, poseidon_coop.cuh) for everything that is a chain of dependent
 // permutations: levels too small to fill the GPU with one thread per node, proof paths, sponges over few rows.

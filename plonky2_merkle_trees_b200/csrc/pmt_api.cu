@@ -95,6 +95,13 @@ struct pmt_ctx {
   // launch resets its counter); rotating them keeps launches that overlap on different streams apart
   unsigned* tickets = nullptr;
   unsigned ticket_next = 0;
+  // k_levels_wave: one flag per block of a launch (grow-only; a flag holds the epoch of the launch that set it), the
+  // epoch counter, and PMT_WAVE=0 to go back to one launch per level (A/B knob)
+  unsigned* wave_flags = nullptr;
+  size_t wave_flags_n = 0;
+  unsigned wave_epoch = 0;
+  bool wave = true;
+  size_t wave_min = (size_t)1 << 14;      // levels with fewer nodes than this stay one launch each (PMT_WAVE_MIN_LOG2)
   // one process per GPU: the NCCL communicator of pmt_comm_init (pmt_merkle_tree_build_sharded_dev)
   ncclComm_t comm = nullptr;
   int comm_rank = 0, comm_world = 0;
@@ -282,6 +289,32 @@ int launch_level(pmt_ctx* c, const Layout& lay, int l, size_t k0, size_t count) 
   return PMT_OK;
 }
 
+// levels la .. la + n_levels - 1 of the nodes the leaves [n0, n1) complete, all big, in ONE launch (k_levels_wave)
+template <class Layout>
+int launch_wave(pmt_ctx* c, const Layout& lay, int la, int n_levels, size_t n0, size_t n1, size_t blocks,
+                const uint64_t* d_rows = nullptr, size_t w = 0) {
+  if (blocks > c->wave_flags_n) {               // grow-only; a fresh buffer is zero = no epoch
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (c->wave_flags) { CU(c, cudaFree(c->wave_flags)); c->wave_flags = nullptr; c->wave_flags_n = 0; }
+    const size_t want = blocks + blocks / 4 + 1024;
+    CU(c, cudaMalloc((void**)&c->wave_flags, want * sizeof(unsigned)));
+    CU(c, cudaMemset(c->wave_flags, 0, want * sizeof(unsigned)));
+    c->wave_flags_n = want;
+  }
+  if (++c->wave_epoch == 0) {                   // 2^32 launches later: start the epochs over on clean flags
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaMemset(c->wave_flags, 0, c->wave_flags_n * sizeof(unsigned)));
+    c->wave_epoch = 1;
+  }
+  size_t units = 0;
+  for (int j = 0; j < n_levels; j++) units += (n1 >> (la + j)) - (n0 >> (la + j));
+  TAG(c, "k_level", units);
+  k_levels_wave<Layout><<<(unsigned)blocks, BLOCK, 0, c->stream>>>(lay, la, n_levels, n0, n1, c->wave_flags, c->wave_epoch, next_ticket(c, 1),
+                                                                   c->xchg_timeout_cycles, c->fault_d, d_rows, w);
+  CHECK_LAUNCH(c);
+  return PMT_OK;
+}
+
 // levels l_first .. l_last over the nodes that the leaves [n0, n1) complete: level l has the nodes k in [n0 >> l, n1 >> l)
 // (a whole tree, a chunk of the pipelined tree build, a batch append to an MMR).  Big levels: one thread per node, one
 // launch per level (the level has to be written anyway -- proofs need it -- and re-reading it costs 1/50 of the time its
@@ -289,14 +322,40 @@ int launch_level(pmt_ctx* c, const Layout& lay, int l, size_t k0, size_t count) 
 // 38 us per thread-per-state permutation, ~6 us per cooperative one): cooperative launches, fused as far as the range's
 // alignment allows -- for a perfect subtree all the way to its root in one launch.
 template <class Layout>
-int launch_level_span(pmt_ctx* c, const Layout& lay, int l_first, int l_last, size_t n0, size_t n1) {
+int launch_level_span(pmt_ctx* c, const Layout& lay, int l_first, int l_last, size_t n0, size_t n1, const uint64_t* d_rows = nullptr,
+                      size_t w = 0) {
+  // d_rows: l_first == 1 and level 1 is computed from the narrow leaf rows of [n0, n1) themselves (n0 even, w <= 4, more than
+  // coop_max level-1 nodes; the caller handles an unpaired last leaf): the leaf copy rides along with level 1
   for (int l = l_first; l <= l_last;) {
     const size_t k0 = n0 >> l, k1 = n1 >> l;
     if (k1 == 0) break;
     if (k1 <= k0) { l++; continue; }
     const size_t count = k1 - k0;
+    const bool from_rows = d_rows != nullptr && l == 1;
     if (count > c->coop_max) {
-      if (int rc = launch_level(c, lay, l, k0, count)) return rc;
+      // the run of big levels from here that can go into one wavefront launch: level l' + 1 joins while it is big too and
+      // level l' starts at an even node (then the children of its block b are exactly the blocks 2 b, 2 b + 1 of level l').
+      // A wave only starts on a level that more than fills the GPU's resident blocks: below that the blocks of SEVERAL levels
+      // become resident at once and take their numbers in arbitrary order, which spreads the small levels unevenly over the
+      // SMs (measured: 2^16 + 2^15 + 2^14 nodes as a wave 155 us, as three launches 121 us)
+      int l2 = l;
+      size_t blocks = (count + BLOCK - 1) / BLOCK;
+      const bool fills = count > (size_t)c->sms * PMT_MINB * BLOCK;
+      while (c->wave && fills && l2 < l_last && !((n0 >> l2) & 1) && (n1 >> (l2 + 1)) - (n0 >> (l2 + 1)) > c->coop_max &&
+             (n1 >> (l2 + 1)) - (n0 >> (l2 + 1)) >= c->wave_min) {
+        l2++;
+        blocks += ((n1 >> l2) - (n0 >> l2) + BLOCK - 1) / BLOCK;
+      }
+      if (l2 > l && blocks <= 0x7fffffffu) {
+        if (int rc = launch_wave(c, lay, l, l2 - l + 1, n0, n1, blocks, from_rows ? d_rows : nullptr, w)) return rc;
+        l = l2 + 1;
+        continue;
+      }
+      if (from_rows) {
+        TAG(c, "k_level", count);
+        k_leaves_level1<Layout><<<grid_for(c, count), BLOCK, 0, c->stream>>>(lay, d_rows, w, k0, count);
+        CHECK_LAUNCH(c);
+      } else if (int rc = launch_level(c, lay, l, k0, count)) return rc;
       l++;
       continue;
     }
@@ -335,23 +394,18 @@ int launch_leaves(pmt_ctx* c, const Layout& lay, const uint64_t* d_rows, size_t 
 // Layout = Mmr (the whole post-order array is on the device) or MmrAppend (only the old peaks and the new elements are).
 template <class Layout>
 int mmr_extend_plan(pmt_ctx* c, const Layout& lay, size_t n0, const uint64_t* d_new, size_t m) {
-  int first_level = 1;
   if ((n0 & 1) == 0 && m / 2 > c->coop_max) {   // every level-1 node has two NEW leaves: copy them and hash in one pass
-    TAG(c, "k_level", m / 2);
-    k_leaves_level1<Layout><<<grid_for(c, m / 2), BLOCK, 0, c->stream>>>(lay, d_new, 1, n0 / 2, m / 2);
-    CHECK_LAUNCH(c);
     if (m & 1) {                             // the unpaired last leaf
       TAG(c, "k_leaves", 0);
       k_leaves<Layout><<<1, BLOCK, 0, c->stream>>>(lay, d_new + (m - 1), 1, n0 + m - 1, 1);
       CHECK_LAUNCH(c);
     }
-    first_level = 2;
-  } else {
-    TAG(c, "k_leaves", 0);
-    k_leaves<Layout><<<grid_copy(c, m), BLOCK, 0, c->stream>>>(lay, d_new, 1, n0, m);
-    CHECK_LAUNCH(c);
+    return launch_level_span(c, lay, 1, 40, n0, n0 + m, d_new, 1);
   }
-  return launch_level_span(c, lay, first_level, 40, n0, n0 + m);
+  TAG(c, "k_leaves", 0);
+  k_leaves<Layout><<<grid_copy(c, m), BLOCK, 0, c->stream>>>(lay, d_new, 1, n0, m);
+  CHECK_LAUNCH(c);
+  return launch_level_span(c, lay, 1, 40, n0, n0 + m);
 }
 
 // work(0 .. n-1), one host thread per index (index 0 on the calling thread), all joined before it returns.  Never throws:
@@ -408,10 +462,22 @@ int pmt_init(pmt_ctx** out, int device_id) {
     if (lg >= 4 && lg <= 24) c->coop_max = (size_t)1 << lg;
   }
   if (const char* e3 = getenv("PMT_FUSE_SUBTREES")) c->fuse_subtrees = atoi(e3) != 0;
+  if (const char* e4 = getenv("PMT_WAVE")) c->wave = atoi(e4) != 0;
+  if (const char* e5 = getenv("PMT_WAVE_MIN_LOG2")) { const int lg = atoi(e5); if (lg >= 8 && lg <= 40) c->wave_min = (size_t)1 << lg; }
   if (cudaMalloc(&c->tickets, TICKET_RING * sizeof(unsigned)) != cudaSuccess ||
-      cudaMemset(c->tickets, 0, TICKET_RING * sizeof(unsigned)) != cudaSuccess) {
+      cudaMemset(c->tickets, 0, TICKET_RING * sizeof(unsigned)) != cudaSuccess ||
+      // the word a kernel raises when a bounded wait expires (k_exchange_top: a peer; k_levels_wave: a block of the level
+      // below), read by pmt_sync; host-mapped so that it survives whatever the stream does next
+      cudaHostAlloc((void**)&c->fault_h, sizeof(unsigned), cudaHostAllocMapped) != cudaSuccess ||
+      cudaHostGetDevicePointer((void**)&c->fault_d, c->fault_h, 0) != cudaSuccess) {
     pmt_destroy(c);
     return PMT_E_OOM;
+  }
+  *c->fault_h = 0;
+  {
+    long long ms = 20000;                          // a peer that has not arrived after 20 s is reported, not waited for
+    if (const char* e = getenv("PMT_EXCHANGE_TIMEOUT_MS")) { const long long v = atoll(e); if (v > 0) ms = v; }
+    c->xchg_timeout_cycles = ms * (long long)(prop.clockRate > 0 ? prop.clockRate : 1965000);
   }
   // the cooperative kernels stage their round constants from global memory (poseidon_coop.cuh): fill the tables of this device
   poseidon::coop::k_coop_tables_init<<<1, 256, 0, c->stream>>>();
@@ -430,6 +496,7 @@ void pmt_destroy(pmt_ctx* c) {
   for (void* p : c->arena) if (p) cudaFree(p);
   for (void* p : c->user_allocs) cudaFree(p);
   if (c->tickets) cudaFree(c->tickets);
+  if (c->wave_flags) cudaFree(c->wave_flags);
   if (c->comm) pmt_comm_destroy(c);
   if (c->root_ready) cudaEventDestroy(c->root_ready);
   for (void* p : c->ipc_open) cudaIpcCloseMemHandle(p);
@@ -458,10 +525,11 @@ void* pmt_get_stream(const pmt_ctx* c) { return c ? (void*)c->stream : nullptr; 
 int pmt_sync(pmt_ctx* c) {
   if (int rc = bind(c)) return rc;
   CU(c, cudaStreamSynchronize(c->stream));
-  if (c->fault_h && *c->fault_h) {            // a k_exchange_top gave up waiting for a peer: its outputs are garbage
-    const unsigned who = *c->fault_h - 1;
+  if (c->fault_h && *c->fault_h) {            // a kernel gave up a bounded wait: its outputs are garbage
+    const unsigned v = *c->fault_h;
     *c->fault_h = 0;
-    return fail(c, PMT_E_NCCL, "sharded build: rank %u did not deliver its subtree root within the exchange timeout (PMT_EXCHANGE_TIMEOUT_MS)", who);
+    if (v & 0x80000000u) return fail(c, PMT_E_CUDA, "k_levels_wave: a block waited longer than the timeout for the level below (PMT_EXCHANGE_TIMEOUT_MS)");
+    return fail(c, PMT_E_NCCL, "sharded build: rank %u did not deliver its subtree root within the exchange timeout (PMT_EXCHANGE_TIMEOUT_MS)", v - 1);
   }
   return PMT_OK;
 }
@@ -617,12 +685,7 @@ int pmt_simple_tree_build_dev(pmt_ctx* c, const uint64_t* d_leaves, size_t n, ui
   if (lg < 1) return fail(c, PMT_E_INVALID_ARG, "simple tree: needs at least 2 leaves (simple_merkle_tree.rs:38)");
   if (!d_leaves || !d_levels || !d_root) return fail(c, PMT_E_INVALID_ARG, "simple tree: null pointer");
   LevelMajor lay{d_levels, d_root, n, lg};
-  if (n / 2 > c->coop_max) {   // big tree: the leaf copy rides along with level 1
-    TAG(c, "k_level", n / 2);
-    k_leaves_level1<LevelMajor><<<grid_for(c, n / 2), BLOCK, 0, c->stream>>>(lay, d_leaves, 1, 0, n / 2);
-    CHECK_LAUNCH(c);
-    return run_levels(c, lay, 2, lg, n / 4);
-  }
+  if (n / 2 > c->coop_max) return launch_level_span(c, lay, 1, lg, 0, n, d_leaves, 1);   // big tree: the leaf copy rides along with level 1
   TAG(c, "k_leaves", 0);
   k_leaves<LevelMajor><<<grid_copy(c, n), BLOCK, 0, c->stream>>>(lay, d_leaves, 1, 0, n);
   CHECK_LAUNCH(c);
@@ -691,11 +754,7 @@ int pmt_merkle_tree_build_dev(pmt_ctx* c, const uint64_t* d_leaves, size_t n, si
   const int L = lg - (int)cap_height;
   Plonky2 lay{d_digests, d_cap, L};
   if (w <= 4 && L >= 1 && n / 2 > c->coop_max) {   // narrow leaves, big tree: the leaf copy rides along with level 1
-    TAG(c, "k_level", n / 2);
-    k_leaves_level1<Plonky2><<<grid_for(c, n / 2), BLOCK, 0, c->stream>>>(lay, d_leaves, w, 0, n / 2);
-    CHECK_LAUNCH(c);
-    if (L == 1) return PMT_OK;
-    return run_levels(c, lay, 2, L, n / 4);
+    return launch_level_span(c, lay, 1, L, 0, n, d_leaves, w);
   }
   if (int rc = launch_leaves(c, lay, d_leaves, w, 0, n)) return rc;
   // levels 1 .. L over all subtrees at once: level l has n >> l nodes (2^h subtrees x 2^(L-l))
@@ -779,14 +838,6 @@ static int mail_alloc(pmt_ctx* c) {
   if (!c->mail) {
     CU(c, cudaMalloc((void**)&c->mail, MAIL_BYTES));
     CU(c, cudaMalloc((void**)&c->d_peers, MAIL_MAX_WORLD * sizeof(uint64_t*)));
-    CU(c, cudaHostAlloc((void**)&c->fault_h, sizeof(unsigned), cudaHostAllocMapped));
-    *c->fault_h = 0;
-    CU(c, cudaHostGetDevicePointer((void**)&c->fault_d, c->fault_h, 0));
-    int khz = 0;
-    CU(c, cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c->device));
-    long long ms = 20000;                          // a peer that has not arrived after 20 s is reported, not waited for
-    if (const char* e = getenv("PMT_EXCHANGE_TIMEOUT_MS")) { const long long v = atoll(e); if (v > 0) ms = v; }
-    c->xchg_timeout_cycles = ms * (long long)(khz > 0 ? khz : 1965000);
   }
   // stream first: a kernel of an earlier group may still be reading the mailbox
   CU(c, cudaStreamSynchronize(c->stream));
