@@ -12,7 +12,8 @@ all_gather and the log2(N) top levels are finished on every rank ("scaling": "we
 `value`      leaves/s, inputs resident in HBM, CUDA-event timing on the launching stream, max over ranks.
 `e2e`        the same metric through the host-buffer C ABI call (pmt_merkle_tree_build): pinned host leaves -> H2D ->
              build -> D2H of every digest + cap, all inside the timed region.
-`roofline`   dominant kernel = k_level (one two_to_one per thread).  The path is integer-pipe bound:
+`roofline`   dominant kernel = k_levels_wave (one two_to_one per thread, all big levels of a tree in one launch).  The path is
+             integer-pipe bound:
              achieved = permutations/s x 10 588 MAC32 / measured IMAD.WIDE.U32 issue peak; the HBM view (96 algorithmic
              bytes per permutation against MEASURED_PEAKS.json) is reported beside it as evidence that HBM is not the limit.
 `cpu_baseline` the CPU oracle's restatement of MerkleTree::new (OpenMP fork-join like rayon's) on the host cores, on the
@@ -243,9 +244,9 @@ def workload_config(n_gpus):
 # ------------------------------------------------------------------------------------------------------------------
 def strong_scaling(ctx, eng, dev, world, rank, root24=None):
     """Collective over all ranks.  Three fixed inputs -- a 2^24-leaf tree, a 2^28-leaf tree (4 felts per leaf, cap 0) and an MMR
-    of 2^24 single-felt leaves -- are built (a) on rank 0's GPU alone and (b) sharded over all N ranks (subtree shards, NCCL
-    all_gather of the roots, top levels on every rank), device-resident, timed with CUDA events on each rank's ctx stream,
-    max over ranks, median of 5.  speedup = (a) / (b), both measured here, in this run.  The sharded root / peaks / bag must
+    of 2^24 single-felt leaves -- are built (a) on rank 0's GPU alone and (b) sharded over all N ranks (subtree shards, the roots
+    exchanged inside libpmt, top levels on every rank), device-resident, timed with CUDA events on each rank's ctx stream,
+    max over ranks, median of 5 repetitions of K builds back to back.  speedup = (a) / (b), both measured here, in this run.  The sharded root / peaks / bag must
     equal the single-GPU ones (and, for the 2^24 tree, the oracle's root from the parity leg)."""
     import numpy as np
     import torch
@@ -260,7 +261,10 @@ def strong_scaling(ctx, eng, dev, world, rank, root24=None):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, active=True, reps=5, warm=2):
+    def timed(fn, active=True, reps=5, warm=2, k=1):
+        # the headline's protocol (K steps between two barriers, events on the launching stream, max over ranks) on a fixed
+        # input: k builds back to back per repetition, so that the skew with which the ranks leave the barrier -- tens of
+        # microseconds, as much as the whole exchange -- is paid once per k builds and not once per build
         res = None
         for _ in range(warm):
             if active:
@@ -271,9 +275,12 @@ def strong_scaling(ctx, eng, dev, world, rank, root24=None):
             ms = 0.0
             if active:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(stream); res = fn(); e1.record(stream)
+                e0.record(stream)
+                for _ in range(k):
+                    res = fn()
+                e1.record(stream)
                 ctx.sync(); torch.cuda.synchronize()
-                ms = e0.elapsed_time(e1)
+                ms = e0.elapsed_time(e1) / k
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -281,8 +288,8 @@ def strong_scaling(ctx, eng, dev, world, rank, root24=None):
         ts.sort()
         return ts[len(ts) // 2], ts[0], res
 
-    out = {"n_gpus": world, "ok": True, "how": "device-resident, CUDA events on each rank's stream, max over ranks, median of 5; "
-           "1-GPU time measured on rank 0 alone in the same run", "cases": {}}
+    out = {"n_gpus": world, "ok": True, "how": "device-resident, CUDA events on each rank's stream, max over ranks, median of 5 repetitions of K builds back to "
+           "back (K = 10; 4 for 2^28 leaves), like the headline's K steps; 1-GPU time measured on rank 0 alone in the same run, same way", "cases": {}}
     for name, lg in (("tree_2p24", 24), ("tree_2p28", 28)):
         n = 1 << lg
         # (a) one GPU: rank 0 builds the whole tree
@@ -290,7 +297,8 @@ def strong_scaling(ctx, eng, dev, world, rank, root24=None):
         if rank == 0:
             d_all = splitmix_torch(0, n * WIDTH, dev).view(n, WIDTH)
             d_dig, d_cap = dev_u64((2 * n - 2, 4), dev), dev_u64((1, 4), dev)
-        ms1, best1, _ = timed(lambda: ctx.call("pmt_merkle_tree_build_dev", dptr(d_all), n, WIDTH, 0, dptr(d_dig), dptr(d_cap)), active=rank == 0)
+        kk = 10 if lg <= 24 else 4
+        ms1, best1, _ = timed(lambda: ctx.call("pmt_merkle_tree_build_dev", dptr(d_all), n, WIDTH, 0, dptr(d_dig), dptr(d_cap)), active=rank == 0, k=kk)
         if rank == 0:
             cap1 = d_cap.cpu().numpy().view(np.uint64).copy()
             del d_all, d_dig, d_cap
@@ -299,7 +307,7 @@ def strong_scaling(ctx, eng, dev, world, rank, root24=None):
         if world > 1:
             per = n // world
             d_mine = splitmix_torch(rank * per * WIDTH, per * WIDTH, dev).view(per, WIDTH)
-            msn, bestn, tree = timed(lambda: sharded.build_sharded_tree(d_mine, n, 0, eng))
+            msn, bestn, tree = timed(lambda: sharded.build_sharded_tree(d_mine, n, 0, eng), k=kk)
             capn = tree.cap.cpu().numpy().view(np.uint64)
             ok = True
             if rank == 0:
@@ -319,7 +327,7 @@ def strong_scaling(ctx, eng, dev, world, rank, root24=None):
     if rank == 0:
         d_leaves = splitmix_torch(0, n, dev)
         d_el = dev_u64((size, 4), dev)
-    ms1, _, _ = timed(lambda: ctx.call("pmt_mmr_extend_dev", dptr(d_el), 0, dptr(d_leaves), n), active=rank == 0)
+    ms1, _, _ = timed(lambda: ctx.call("pmt_mmr_extend_dev", dptr(d_el), 0, dptr(d_leaves), n), active=rank == 0, k=10)
     case = {"leaves": n, "ms_1gpu": ms1, "leaves_per_s_1gpu": n / (ms1 * 1e-3)}
     if rank == 0:
         peak1 = d_el[size - 1].cpu().numpy().view(np.uint64).copy()
@@ -328,7 +336,7 @@ def strong_scaling(ctx, eng, dev, world, rank, root24=None):
     if world > 1:
         rngs = sharded.mmr_shard_ranges(n, world, rank)
         d_mine = torch.cat([splitmix_torch(a, c, dev) for a, c in rngs])
-        msn, _, sm = timed(lambda: sharded.build_sharded_mmr(d_mine, n, eng))
+        msn, _, sm = timed(lambda: sharded.build_sharded_mmr(d_mine, n, eng), k=10)
         peaks = np.asarray(sm.get_peaks())
         ok = True
         if rank == 0:
@@ -590,27 +598,28 @@ def run_ours(args):
     mac32 = perms_per_s * MAC32_PER_PERM
     hbm_gbs = perms_per_s * ALG_BYTES_PER_PERM / 1e9
     total_prof_ms = sum(v["ms"] for v in prof.values()) or 1.0
-    # traffic / hardware view: one `ncu --set full` capture of this kernel (profiles/ncu_k_level_r2.json, written by
+    # traffic / hardware view: one `ncu --set full` capture of this kernel (profiles/ncu_k_levels_wave_r2.json, written by
     # tools/ncu_summarize.py), scaled to the average launch of this run -- but only while the kernel sources are still the
     # ones that were profiled (tools/kernel_hash.py): a changed kernel prints null, not a stale figure
     traffic, hardware = None, None
     try:
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         from kernel_hash import kernel_sources_hash
-        with open(os.path.join(ROOT, "profiles", "ncu_k_level_r2.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "ncu_k_levels_wave_r2.json")) as f:
             cap = json.load(f)
         if cap.get("kernel_sources_sha16") == kernel_sources_hash():
             per_perm = (cap["dram_bytes_read"] + cap["dram_bytes_write"]) / cap["permutations_in_launch"]
             traffic = per_perm * lvl["units"] / max(lvl["launches"], 1)
             hardware = dict(cap.get("hardware_view", {}), dram_bytes_per_permutation=per_perm,
-                            source="profiles/%s (ncu --set full, kernel sources %s = this tree)" % (cap.get("summary", "k_level_r2_summary.txt"), cap["kernel_sources_sha16"]))
+                            source="profiles/%s (ncu --set full, kernel sources %s = this tree)" % (cap.get("summary", "k_levels_wave_r2_summary.txt"), cap["kernel_sources_sha16"]))
         else:
-            hardware = {"stale": "profiles/ncu_k_level_r2.json was captured for kernel sources %s, this tree is %s" % (
+            hardware = {"stale": "profiles/ncu_k_levels_wave_r2.json was captured for kernel sources %s, this tree is %s" % (
                 cap.get("kernel_sources_sha16"), kernel_sources_hash())}
     except Exception:
         pass
     roofline = {
-        "kernel": "k_level<Plonky2> (one two_to_one per thread)", "bound": "int32-imad (fma-heavy pipe)",
+        "kernel": "k_levels_wave<Plonky2> (one two_to_one per thread; the leaf copy, level 1 and every level of more than 2^13 nodes "
+                  "in one wavefront launch per tree)", "bound": "int32-imad (fma-heavy pipe)",
         "achieved": mac32 / 1e12, "peak": PEAK_MAC32_PER_S / 1e12, "unit": "TMAC32/s", "frac": mac32 / PEAK_MAC32_PER_S,
         "peak_source": "measured multiply-accumulate issue peak of the fma/fp64 pipes (32-bit IMAD 63.7 lanes/clk/SM), "
                        "tools/perm_bench.cu (profiles/pipes_r1.jsonl)",

@@ -337,6 +337,42 @@ def test_mmr_incremental_and_add_leaf(api, oracle):
     assert np.array_equal(m2.elements, oracle.mmr_extend(None, leaves[:20]))
 
 
+@pytest.mark.parametrize("n0,m", [(0, 250001), (0, (1 << 18) - 1), (1 << 18, 200001), ((1 << 17) + 6, 210000), (3 << 12, (1 << 18) + (1 << 12))])
+def test_big_ragged_mmr_appends_through_the_wavefront_kernel(api, oracle, n0, m):
+    """k_levels_wave on ranges that are not perfect trees: appends big enough for the wavefront launch (level 1 more than fills
+    the GPU) whose levels have ragged ends (last blocks partial, a level-(l+1) block with one child block) and, for n0 > 0, start
+    at nodes that are even only up to some level (the wave stops where bit l of n0 is set and the remaining levels run one
+    launch each).  Device-resident and host-buffer (compact MmrAppend) forms against the sequential add_leaf oracle; both wave
+    settings must agree (PMT_WAVE is read when the context is created)."""
+    import os
+    from plonky2_merkle_trees_b200 import _lib
+    leaves = splitmix_felts(5000 + (n0 % 1000) + m % 1000, n0 + m)
+    want = oracle.mmr_extend(None, leaves)
+    got = {}
+    for wave in ("1", "0"):
+        os.environ["PMT_WAVE"] = wave
+        c = _lib.Context(0)
+        try:
+            mm = api.mmr.MMR.new(c)
+            if n0:
+                mm.extend(leaves[:n0])
+            mm.extend(leaves[n0:])
+            got[wave] = mm.elements.copy()
+            if wave == "1":                       # the host-buffer append: only old peaks up, only new elements down
+                import ctypes as C
+                from plonky2_merkle_trees_b200._lib import u64p
+                el = np.zeros((want.shape[0], 4), np.uint64)
+                size0 = 2 * n0 - bin(n0).count("1")
+                el[:size0] = want[:size0]
+                new = np.ascontiguousarray(leaves[n0:])
+                c.call("pmt_mmr_extend", el.ctypes.data_as(u64p), n0, new.ctypes.data_as(u64p), m)
+                assert np.array_equal(el, want)
+        finally:
+            c.close()
+            os.environ.pop("PMT_WAVE", None)
+    assert np.array_equal(got["1"], want) and np.array_equal(got["0"], want)
+
+
 @pytest.mark.parametrize("n", [1, 2, 3, 7, 8, 13, 16, 22, 31, 70, 1031])
 def test_mmr_proofs_and_verify(api, oracle, n):
     leaves = splitmix_felts(2000 + n, n)
