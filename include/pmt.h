@@ -48,7 +48,8 @@ void pmt_destroy(pmt_ctx* ctx);
 const char* pmt_last_error(const pmt_ctx* ctx);
 const char* pmt_version(void);
 int pmt_device_id(const pmt_ctx* ctx);
-/* use an externally owned cudaStream_t (e.g. the caller's current stream); NULL restores the ctx's own stream */
+/* use an externally owned cudaStream_t (e.g. the caller's current stream); NULL restores the ctx's own stream.  Changing the
+ * stream first waits for the work already enqueued on the old one (the ctx's device-side state assumes its launches run in order) */
 int pmt_set_stream(pmt_ctx* ctx, void* cuda_stream);
 void* pmt_get_stream(const pmt_ctx* ctx);
 int pmt_sync(pmt_ctx* ctx);

@@ -517,8 +517,12 @@ const char* pmt_last_error(const pmt_ctx* c) { return c ? c->err : "null ctx"; }
 const char* pmt_version(void) { return "pmt 0.1 (sm_100a)"; }
 int pmt_device_id(const pmt_ctx* c) { return c ? c->device : -1; }
 int pmt_set_stream(pmt_ctx* c, void* s) {
-  if (!c) return PMT_E_INVALID_ARG;
-  c->stream = s ? (cudaStream_t)s : c->own_stream;
+  if (int rc = bind(c)) return rc;
+  cudaStream_t next = s ? (cudaStream_t)s : c->own_stream;
+  // per-ctx device state (ticket counters, wavefront flags, mailbox slots) assumes that the ctx's launches run in order: drain
+  // the stream that is being left before work goes to another one
+  if (next != c->stream) CU(c, cudaStreamSynchronize(c->stream));
+  c->stream = next;
   return PMT_OK;
 }
 void* pmt_get_stream(const pmt_ctx* c) { return c ? (void*)c->stream : nullptr; }
@@ -1271,7 +1275,11 @@ static int drained(pmt_ctx* c, int rc) {
     if (c->copy_out) cudaStreamSynchronize(c->copy_out);
     cudaStreamSynchronize(c->stream);
     cudaGetLastError();
+    return rc;
   }
+  // a host-buffer call has synchronised already: a kernel that gave up a bounded wait (k_levels_wave) has left garbage in the
+  // caller's buffers, and this is the call that must say so
+  if (c->fault_h && *c->fault_h) return pmt_sync(c);
   return rc;
 }
 

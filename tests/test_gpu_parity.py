@@ -943,6 +943,31 @@ def test_dev_entry_points_wait_for_torch_stream(api, ctx, oracle):
 # =====================================================================================================================
 # round 2: the four-threads-per-state cooperative kernels, the one-launch tree tail, ABI hardening, full-size parity
 # =====================================================================================================================
+def test_external_stream_and_switching_back(api, oracle):
+    """pmt_set_stream: builds enqueued on a caller-owned CUDA stream (a torch stream), then on the ctx's own stream again;
+    changing the stream drains the old one first, so results are complete and equal the oracle's either way."""
+    from plonky2_merkle_trees_b200 import _lib
+    from plonky2_merkle_trees_b200.device import dev_u64, dptr, to_device, to_host
+    c = _lib.Context(0)
+    try:
+        side = torch.cuda.Stream(device="cuda:0")
+        for lg, use_side in [(12, True), (16, False), (18, True), (10, False)]:
+            n = 1 << lg
+            rows = splitmix_felts(40 + lg, n * 4).reshape(n, 4)
+            d_rows = to_device(rows, "cuda:0")
+            torch.cuda.synchronize()
+            c.set_stream(side.cuda_stream if use_side else None)
+            d_dig, d_cap = dev_u64((2 * n - 2, 4), "cuda:0"), dev_u64((1, 4), "cuda:0")
+            torch.cuda.synchronize()
+            c.call("pmt_merkle_tree_build_dev", dptr(d_rows), n, 4, 0, dptr(d_dig), dptr(d_cap))
+            c.set_stream(None if use_side else side.cuda_stream)          # leaves the stream the build runs on: must drain it
+            odg, ocap = oracle.merkle_tree_new(rows, 0, threads=4, fast=True)
+            assert np.array_equal(to_host(d_dig), odg) and np.array_equal(to_host(d_cap), ocap)
+        c.set_stream(None)
+    finally:
+        c.close()
+
+
 def test_hasher_small_and_big_batches_agree(api, oracle):
     """Hasher batches of <= 2^12 rows run by quads (k_permute_coop / k_rows_coop), bigger ones one row per thread: both against
     the oracle and against each other, incl. non-canonical inputs"""
