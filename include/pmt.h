@@ -19,7 +19,11 @@
  *   - tuning knobs read from the environment at pmt_init / call time (measurement aids; the defaults are the measured
  *     optima, results never depend on them): PMT_COOP_MAX_LOG2 (levels of at most 2^k nodes run four threads per node,
  *     default 13), PMT_FUSE_SUBTREES (0: one launch per small level instead of ONE launch for the whole tail of a tree),
- *     PMT_PIPELINE_LOG2_CHUNKS (chunks of the pipelined host-buffer tree build, default 4).
+ *     PMT_PIPELINE_LOG2_CHUNKS (chunks of the pipelined host-buffer tree build, default 4), PMT_WAVE (0: one launch per big
+ *     level instead of ONE wavefront launch for all of them), PMT_WAVE_MIN_LOG2 (levels of fewer than 2^k nodes stay out of
+ *     the wavefront, default 14), PMT_COPY_THREADS (host threads that stage pageable caller buffers), PMT_EXCHANGE (nccl:
+ *     sharded builds exchange their roots with ncclAllGather / peer copies instead of peer-memory mailboxes; read at
+ *     pmt_comm_init and per pmt_merkle_tree_build_multi_dev call), PMT_EXCHANGE_TIMEOUT_MS (bounded waits inside kernels).
  *   - every host-buffer entry point that fails has drained its streams first: when it returns, the library no longer
  *     reads or writes the caller's buffers, whatever the status.
  */
