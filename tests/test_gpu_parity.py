@@ -643,11 +643,12 @@ def test_sharded_virtual_ranks(ctx, api, oracle, lg, w, h, G):
     assert np.array_equal(t.assemble_global(chunks), odg)
 
 
-# ---- fused subtree blocks (k_subtree_coop) against one cooperative launch per level ----------------------------------------
+# ---- the tail in one launch (k_tree_coop: block-local 64-node subtrees + ticket rounds) against one cooperative launch per level ----
 @pytest.mark.parametrize("lg,w,h", [(5, 4, 0), (6, 4, 1), (9, 4, 0), (10, 1, 3), (12, 4, 0), (14, 4, 0), (14, 9, 6), (15, 4, 11), (17, 4, 2)])
 def test_fused_subtree_blocks_equal_per_level_launches(api, oracle, lg, w, h, monkeypatch):
-    """the middle levels (<= 2^13 nodes) of a perfect tree run as fused 16-node subtree blocks; PMT_FUSE_SUBTREES=0 keeps the
-    one-launch-per-level plan: both must give the oracle's tree (plonky2 layout, simple tree) with fewer launches fused"""
+    """all levels of at most 2^13 nodes of a perfect tree run in ONE k_tree_coop launch (block-local 64-node subtrees, then two
+    rounds of tickets); PMT_FUSE_SUBTREES=0 keeps one cooperative launch per level: both must give the oracle's tree (plonky2
+    layout, simple tree), the fused plan with fewer launches"""
     from plonky2_merkle_trees_b200 import _lib
     n = 1 << lg
     rows = splitmix_felts(300 + lg + w + h, n * w).reshape(n, w)
@@ -791,7 +792,8 @@ def test_multi_context_mmr_extend_errors(ctx_pool, api):
 
 @pytest.mark.parametrize("n_roots,h", [(2, 0), (2, 1), (8, 0), (8, 2), (64, 0), (1024, 3), (4096, 0), (8192, 1)])
 def test_top_levels_above_gathered_roots(ctx, oracle, n_roots, h):
-    """pmt_top_levels_dev: single cooperative launch up to 4096 roots, one launch per level beyond that."""
+    """pmt_top_levels_dev (TopRoots layout): the levels above 2 .. 8192 gathered subtree roots, one k_tree_coop launch while a
+    level has at most 2^13 nodes"""
     from plonky2_merkle_trees_b200 import sharded
     from plonky2_merkle_trees_b200.device import to_device, to_host
     roots = splitmix_felts(n_roots + h, n_roots * 4).reshape(n_roots, 4)
