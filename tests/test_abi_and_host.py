@@ -334,3 +334,155 @@ def test_mmr_multi_plan_invariants_random():
                 assert not any(lo <= p < lo + 2 * big - 1 for p in coarse)
             assert head + blocks * (2 * big - 1) + len(coarse) + tail == new
     assert split > 3000
+
+# ---- the wavefront launch's block arithmetic, as a model ------------------------------------------------------------------
+def _wave_runs(l_first, l_last, n0, n1, coop_max, resident_nodes, wave_min=1 << 14):
+    """restates launch_level_span (plonky2_merkle_trees_b200/csrc/pmt_api.cu): -> [(la, n_levels)] of the wavefront launches"""
+    runs, l = [], l_first
+    while l <= l_last:
+        k0, k1 = n0 >> l, n1 >> l
+        if k1 == 0:
+            break
+        if k1 <= k0:
+            l += 1
+            continue
+        count = k1 - k0
+        if count <= coop_max:
+            break                                    # the cooperative tail takes over (never followed by a big level again)
+        l2 = l
+        while (count > resident_nodes and l2 < l_last and not ((n0 >> l2) & 1)
+               and (n1 >> (l2 + 1)) - (n0 >> (l2 + 1)) > coop_max and (n1 >> (l2 + 1)) - (n0 >> (l2 + 1)) >= wave_min):
+            l2 += 1
+        if l2 > l:
+            runs.append((l, l2 - l + 1))
+        l = l2 + 1
+    return runs
+
+
+def _wave_block(logical_id, la, n_levels, n0, n1, B=128):
+    """restates the head of k_levels_wave (merkle_kernels.cuh): logical block number -> (level index j, block of the level,
+    first node, node count of the level, flags offset of the level, blocks of the level below)"""
+    idx, off, prev, j = logical_id, 0, 0, 0
+    while True:
+        k0 = n0 >> (la + j)
+        cnt = (n1 >> (la + j)) - k0
+        nb = (cnt + B - 1) // B
+        if idx < nb or j + 1 == n_levels:
+            return j, idx, k0, cnt, off, prev
+        idx -= nb
+        off += nb
+        prev = nb
+        j += 1
+
+
+def test_wavefront_block_arithmetic_model():
+    """k_levels_wave: every node of every level of a run is computed by exactly one block; the children of a block's nodes lie
+    in the two blocks of the level below whose flags it waits for; those blocks have SMALLER logical numbers (they started
+    earlier: no deadlock) and distinct flag slots; a run only crosses levels that start at an even node.  Random perfect and
+    ragged ranges, incl. appends to a non-empty MMR (n0 > 0)."""
+    import random
+    rnd = random.Random(5)
+    B, coop_max, resident = 128, 1 << 13, 148 * 5 * 128
+    checked = 0
+    for it in range(400):
+        kind = it % 4
+        if kind == 0:                                   # a perfect tree
+            lg = rnd.randrange(15, 23)
+            n0, n1 = 0, 1 << lg
+        elif kind == 1:                                 # ragged from empty
+            n0, n1 = 0, rnd.randrange(1 << 17, 1 << 22)
+        elif kind == 2:                                 # append to a non-empty MMR, even start
+            n0 = 2 * rnd.randrange(1, 1 << 20)
+            n1 = n0 + rnd.randrange(1 << 17, 1 << 21)
+        else:                                           # an aligned pipeline chunk
+            b = rnd.randrange(18, 22)
+            n0 = rnd.randrange(0, 16) << b
+            n1 = n0 + (1 << b)
+        for la, n_levels in _wave_runs(1, 40, n0, n1, coop_max, resident):
+            checked += 1
+            for l in range(la, la + n_levels - 1):
+                assert not ((n0 >> l) & 1)
+            blocks = [((n1 >> (la + j)) - (n0 >> (la + j)) + B - 1) // B for j in range(n_levels)]
+            total = sum(blocks)
+            # sample logical ids: all block boundaries of every level and a few random ones
+            ids = set()
+            acc = 0
+            for nb in blocks:
+                ids.update({acc, acc + nb - 1, acc + nb // 2})
+                acc += nb
+            ids.update(rnd.randrange(total) for _ in range(20))
+            seen_flags = {}
+            for lid in sorted(ids):
+                j, idx, k0, cnt, off, prev = _wave_block(lid, la, n_levels, n0, n1)
+                assert 0 <= j < n_levels and idx < blocks[j] and off == sum(blocks[:j]) and prev == (blocks[j - 1] if j else 0)
+                assert k0 == n0 >> (la + j) and cnt == (n1 >> (la + j)) - k0
+                lo, hi = idx * B, min(idx * B + B, cnt)             # this block's nodes, local to the level
+                assert lo < hi
+                assert seen_flags.setdefault(off + idx, lid) == lid  # one flag slot per block
+                if j:
+                    # children of local node i are the local nodes 2 i, 2 i + 1 of the level below (it starts at 2 k0)
+                    assert (n0 >> (la + j - 1)) == 2 * k0
+                    cnt_below = (n1 >> (la + j - 1)) - (n0 >> (la + j - 1))
+                    assert 2 * (hi - 1) + 1 < cnt_below
+                    child_blocks = {(2 * lo) // B, (2 * (hi - 1) + 1) // B}
+                    waited = {c for c in (2 * idx, 2 * idx + 1) if c < prev}
+                    assert child_blocks <= waited
+                    for c in waited:                                 # they were numbered (= started) before this block
+                        assert (off - prev) + c < lid
+            # the blocks of a level tile its nodes exactly
+            for j, nb in enumerate(blocks):
+                cnt = (n1 >> (la + j)) - (n0 >> (la + j))
+                assert (nb - 1) * B < cnt <= nb * B
+    assert checked > 300
+
+# ---- the mailbox exchange's ring / epoch protocol, as a model ---------------------------------------------------------------
+def _mailbox_run(world, exchanges, ring, rnd):
+    """Random interleaving of k_exchange_top's steps on `world` ranks (merkle_kernels.cuh): per exchange s a rank pushes
+    (data, then flag = s + 1) into slot s % ring of every peer's mailbox -- peer by peer, in any order relative to the other
+    ranks --, then waits until all peers' flags of s are in its own mailbox, then reads the peers' data.  Returns the number of
+    reads that saw another exchange's data (0 = the protocol held)."""
+    data = [[[None] * world for _ in range(ring)] for _ in range(world)]      # data[owner][slot][from]
+    flag = [[[0] * world for _ in range(ring)] for _ in range(world)]
+    # per rank: (exchange, phase, progress); phases: 0 push to peers one at a time, 1 wait, 2 read
+    state = [[0, 0, 0] for _ in range(world)]
+    order = [rnd.sample([p for p in range(world) if p != r], world - 1) for r in range(world)]
+    bad = 0
+    live = set(range(world))
+    while live:
+        r = rnd.choice(sorted(live))
+        s, phase, k = state[r]
+        slot = s % ring
+        if phase == 0:
+            p = order[r][k]
+            data[p][slot][r] = (r, s)
+            flag[p][slot][r] = s + 1
+            state[r][2] += 1
+            if state[r][2] == world - 1:
+                state[r][1:] = [1, 0]
+        elif phase == 1:
+            if any(flag[r][slot][p] > s + 1 for p in range(world) if p != r):
+                bad += 1                                 # a later exchange overwrote the flag: the real kernel would time out
+                state[r][1] = 2
+            elif all(flag[r][slot][p] == s + 1 for p in range(world) if p != r):
+                state[r][1] = 2
+        else:
+            bad += sum(data[r][slot][p] != (p, s) for p in range(world) if p != r)
+            if s + 1 == exchanges:
+                live.discard(r)
+            else:
+                state[r] = [s + 1, 0, 0]
+                order[r] = rnd.sample([p for p in range(world) if p != r], world - 1)
+    return bad
+
+
+def test_mailbox_ring_protocol_model():
+    """A rank cannot get more than one exchange ahead of its slowest peer (it needs all flags of exchange s before it leaves s),
+    so slots are never overwritten while a reader still needs them -- with the library's ring of 4 and already with 2; a ring of
+    ONE slot must fail under some interleaving, which shows that the model can see the hazard."""
+    import random
+    rnd = random.Random(17)
+    for world in (2, 4, 8):
+        for ring in (4, 2):
+            for _ in range(30):
+                assert _mailbox_run(world, 12, ring, rnd) == 0
+    assert any(_mailbox_run(4, 12, 1, rnd) > 0 for _ in range(200))
