@@ -274,9 +274,15 @@ def main():
     out.append("#endif")
     path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "plonky2_merkle_trees_b200", "csrc",
                         "poseidon_freq_constants.cuh")
-    with open(path, "w") as f:
-        f.write("\n".join(out) + "\n")
-    print("ok: frequency-domain tables verified against the matrix forms; %s written" % os.path.relpath(path))
+    text = "\n".join(out) + "\n"
+    # an unchanged table is not rewritten: the header is a build dependency of libpmt.so, and touching it (the CPU test suite
+    # runs this script) would make every later import rebuild the library
+    if os.path.exists(path) and open(path).read() == text:
+        print("ok: frequency-domain tables verified against the matrix forms; %s is up to date" % os.path.relpath(path))
+    else:
+        with open(path, "w") as f:
+            f.write(text)
+        print("ok: frequency-domain tables verified against the matrix forms; %s written" % os.path.relpath(path))
 
 
 if __name__ == "__main__":
