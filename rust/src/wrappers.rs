@@ -123,3 +123,85 @@ pub fn plonky2_tree_multi_gpu(ctxs: &[Ctx], leaves: Vec<Vec<F>>, cap_height: usi
         cap: MerkleCap(cap.chunks_exact(4).map(digest).collect()),
     }
 }
+
+// ---- one process per GPU (launched by the host's own launcher: MPI, a job scheduler ...) ------------------------------------
+
+/// a device buffer of `words` u64 owned by a Ctx (pmt_malloc / pmt_free)
+struct DevBuf<'a> {
+    ctx: &'a Ctx,
+    ptr: *mut u64,
+    words: usize,
+}
+impl<'a> DevBuf<'a> {
+    fn new(ctx: &'a Ctx, words: usize) -> Self {
+        let mut p: *mut std::os::raw::c_void = std::ptr::null_mut();
+        ctx.check(unsafe { pmt_malloc(ctx.0, words.max(1) * 8, &mut p) });
+        DevBuf { ctx, ptr: p as *mut u64, words }
+    }
+    fn upload(&self, src: &[u64]) {
+        assert!(src.len() <= self.words);
+        self.ctx.check(unsafe { pmt_memcpy_h2d(self.ctx.0, self.ptr as *mut _, src.as_ptr() as *const _, src.len() * 8) });
+    }
+    fn download(&self, words: usize) -> Vec<u64> {
+        let mut out = vec![0u64; words];
+        self.ctx.check(unsafe { pmt_memcpy_d2h(self.ctx.0, out.as_mut_ptr() as *mut _, self.ptr as *const _, words * 8) });
+        out
+    }
+}
+impl<'a> Drop for DevBuf<'a> {
+    fn drop(&mut self) {
+        unsafe { pmt_free(self.ctx.0, self.ptr as *mut _) };
+    }
+}
+
+/// rank 0 creates the id and hands the 128 bytes to the other ranks by the host's own means
+pub fn nccl_unique_id(ctx: &Ctx) -> [u8; 128] {
+    let mut id = [0u8; 128];
+    ctx.check(unsafe { pmt_nccl_unique_id(ctx.0, id.as_mut_ptr() as *mut _) });
+    id
+}
+
+/// collective over the `world` ranks (a power of two); afterwards `comm_uses_peer_memory` tells whether the subtree roots
+/// travel through peer-memory mailboxes (k_exchange_top) or through ncclAllGather
+pub fn comm_init(ctx: &Ctx, unique_id: &[u8; 128], rank: usize, world: usize) {
+    ctx.check(unsafe { pmt_comm_init(ctx.0, unique_id.as_ptr() as *const _, rank as i32, world as i32) });
+}
+pub fn comm_uses_peer_memory(ctx: &Ctx) -> bool {
+    unsafe { pmt_comm_uses_peer_memory(ctx.0) != 0 }
+}
+
+/// this rank's share of `MerkleTree::new(leaves, cap_height)` over `world` ranks: `local_digests` is the contiguous slice of
+/// upstream's `digests` that belongs to the rank's leaves, `roots` / `top` the gathered subtree roots and the levels above
+/// them (empty when cap_height >= log2 world), `cap` the whole cap -- the same on every rank
+pub struct ShardedTree {
+    pub local_digests: Vec<HashOut<F>>,
+    pub roots: Vec<HashOut<F>>,
+    pub top: Vec<HashOut<F>>,
+    pub cap: MerkleCap<F, PoseidonHash>,
+}
+
+/// collective: every rank passes ITS n_total / world leaf rows (rank r owns rows [r n_total / world, (r + 1) n_total / world))
+pub fn plonky2_tree_sharded(ctx: &Ctx, local_leaves: &[Vec<F>], n_total: usize, cap_height: usize, world: usize) -> ShardedTree {
+    let (per, w) = (local_leaves.len(), local_leaves[0].len());
+    assert_eq!(per * world, n_total);
+    let g = world.trailing_zeros() as usize;
+    let ncap = 1usize << cap_height;
+    let local_cap = if cap_height >= g { ncap / world } else { 1 };
+    let flat: Vec<u64> = local_leaves.iter().flat_map(|r| r.iter().map(|x| x.0)).collect();
+    let d_leaves = DevBuf::new(ctx, per * w);
+    d_leaves.upload(&flat);
+    let ndig = 2 * (per - local_cap);
+    let ntop = if cap_height >= g { 0 } else { world - ncap };
+    let (d_dig, d_roots, d_top, d_cap) = (DevBuf::new(ctx, ndig * 4), DevBuf::new(ctx, world * 4), DevBuf::new(ctx, ntop * 4), DevBuf::new(ctx, ncap * 4));
+    ctx.check(unsafe {
+        pmt_merkle_tree_build_sharded_dev(ctx.0, d_leaves.ptr, n_total, w, cap_height as u32, d_dig.ptr, d_roots.ptr, d_top.ptr, d_cap.ptr)
+    });
+    ctx.check(unsafe { pmt_sync(ctx.0) });
+    let conv = |v: Vec<u64>| -> Vec<HashOut<F>> { v.chunks_exact(4).map(digest).collect() };
+    ShardedTree {
+        local_digests: conv(d_dig.download(ndig * 4)),
+        roots: if ntop > 0 { conv(d_roots.download(world * 4)) } else { Vec::new() },
+        top: conv(d_top.download(ntop * 4)),
+        cap: MerkleCap(conv(d_cap.download(ncap * 4))),
+    }
+}
